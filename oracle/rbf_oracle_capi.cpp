@@ -1,0 +1,201 @@
+// rbf_oracle_capi.cpp — C entry points of the CPU ORACLE (test infrastructure, NOT the product).
+// Loaded through ctypes by oracle/__init__.py; only tests/, __graft_entry__.smoke() and
+// bench.py's cpu_baseline / --impl reference legs may use it.
+#include "rbf_oracle_mapping.hpp"
+
+#include <chrono>
+
+namespace {
+thread_local std::string g_error;
+
+template <typename F>
+int guarded(F &&f)
+{
+  try {
+    f();
+    g_error.clear();
+    return 0;
+  } catch (const std::exception &e) {
+    g_error = e.what();
+    return 1;
+  }
+}
+
+orc::Rbf makeRbf(int basis, double param, double gaussSupport)
+{
+  if (!(gaussSupport > 0) && !(gaussSupport <= 0)) // NaN -> "not given"
+    gaussSupport = std::numeric_limits<double>::infinity();
+  return orc::Rbf::make(static_cast<orc::BasisFunction>(basis), param, gaussSupport);
+}
+} // namespace
+
+extern "C" {
+
+const char *orc_last_error() { return g_error.c_str(); }
+
+int orc_basis_eval(int basis, double param, double gaussSupport, const double *r, int n, double *out)
+{
+  return guarded([&] {
+    const orc::Rbf f = makeRbf(basis, param, gaussSupport);
+    for (int i = 0; i < n; ++i)
+      out[i] = f(r[i]);
+  });
+}
+
+int orc_basis_params(int basis, double param, double gaussSupport, double *p3, int *spd, double *support)
+{
+  return guarded([&] {
+    const orc::Rbf f = makeRbf(basis, param, gaussSupport);
+    p3[0]            = f.p1;
+    p3[1]            = f.p2;
+    p3[2]            = f.p3;
+    *spd             = f.isStrictlyPositiveDefinite();
+    *support         = f.getSupportRadius();
+  });
+}
+
+// ---- clustering only (PartitionOfUnityClusteringTest.cpp) ----
+int orc_create_clustering(const double *inXYZ, int nIn, const double *outXYZ, int nOut, int dim, double overlap, unsigned vpc, int project,
+                          double *radius, double *centers, int maxCenters, int *count)
+{
+  return guarded([&] {
+    orc::PointGrid   gi(inXYZ, nIn), go(outXYZ, nOut);
+    orc::Clustering  c = orc::createClustering(gi, go, dim, overlap, vpc, project != 0);
+    *radius            = c.radius;
+    *count             = c.count();
+    const int n        = std::min(c.count(), maxCenters);
+    if (centers)
+      std::copy(c.centers.begin(), c.centers.begin() + 3 * static_cast<size_t>(n), centers);
+  });
+}
+
+// ---- partition of unity ----
+void *orc_pum_create(int constraint, int dim, int basis, double param, double gaussSupport, int polynomial, unsigned vpc, double overlap, int project)
+{
+  void *h = nullptr;
+  guarded([&] {
+    h = new orc::PumMapping(static_cast<orc::Constraint>(constraint), dim, makeRbf(basis, param, gaussSupport), static_cast<orc::Polynomial>(polynomial), vpc, overlap, project != 0);
+  });
+  return h;
+}
+int orc_pum_compute(void *h, const double *inXYZ, int nIn, const double *outXYZ, int nOut, int threads)
+{
+  return guarded([&] { static_cast<orc::PumMapping *>(h)->computeMapping(inXYZ, nIn, outXYZ, nOut, threads); });
+}
+int orc_pum_map(void *h, const double *in, int dims, double *out, int threads)
+{
+  return guarded([&] { static_cast<orc::PumMapping *>(h)->map(in, dims, out, threads); });
+}
+void   orc_pum_clear(void *h) { static_cast<orc::PumMapping *>(h)->clear(); }
+void   orc_pum_destroy(void *h) { delete static_cast<orc::PumMapping *>(h); }
+double orc_pum_radius(void *h) { return static_cast<orc::PumMapping *>(h)->clusterRadius(); }
+int    orc_pum_num_clusters(void *h) { return static_cast<int>(static_cast<orc::PumMapping *>(h)->clusters().size()); }
+int    orc_pum_cluster_sizes(void *h, int c, double *center, int *nIn, int *nOut, int *polyParams)
+{
+  return guarded([&] {
+    const auto &k = static_cast<orc::PumMapping *>(h)->clusters().at(c);
+    for (int d = 0; d < 3; ++d)
+      center[d] = k.center[d];
+    *nIn        = static_cast<int>(k.inIDs.size());
+    *nOut       = static_cast<int>(k.outIDs.size());
+    *polyParams = k.solver.numberOfPolynomials();
+  });
+}
+int orc_pum_cluster_data(void *h, int c, int *inIDs, int *outIDs, double *weights, double *choleskyL)
+{
+  return guarded([&] {
+    const auto &k = static_cast<orc::PumMapping *>(h)->clusters().at(c);
+    if (inIDs)
+      std::copy(k.inIDs.begin(), k.inIDs.end(), inIDs);
+    if (outIDs)
+      std::copy(k.outIDs.begin(), k.outIDs.end(), outIDs);
+    if (weights)
+      std::copy(k.weights.begin(), k.weights.end(), weights);
+    if (choleskyL) {
+      const auto &L = k.solver.choleskyL();
+      std::copy(L.a.begin(), L.a.end(), choleskyL);
+    }
+  });
+}
+
+// ---- global direct ----
+void *orc_global_create(int constraint, int dim, int basis, double param, double gaussSupport, const int *deadAxis, int polynomial)
+{
+  void *h = nullptr;
+  guarded([&] {
+    h = new orc::GlobalMapping(static_cast<orc::Constraint>(constraint), dim, makeRbf(basis, param, gaussSupport),
+                               {{deadAxis[0] != 0, deadAxis[1] != 0, deadAxis[2] != 0}}, static_cast<orc::Polynomial>(polynomial));
+  });
+  return h;
+}
+int orc_global_compute(void *h, const double *inXYZ, int nIn, const double *outXYZ, int nOut)
+{
+  return guarded([&] { static_cast<orc::GlobalMapping *>(h)->computeMapping(inXYZ, nIn, outXYZ, nOut); });
+}
+int orc_global_map(void *h, const double *in, int dims, double *out)
+{
+  return guarded([&] { static_cast<orc::GlobalMapping *>(h)->map(in, dims, out); });
+}
+void orc_global_clear(void *h) { static_cast<orc::GlobalMapping *>(h)->clear(); }
+void orc_global_destroy(void *h) { delete static_cast<orc::GlobalMapping *>(h); }
+
+// ---- small dense kernels, exposed so the tests can pin them against LAPACK (scipy) ----
+int orc_cholesky(double *A, int n) // column-major in/out (lower), returns 0 on success
+{
+  int rc = 1;
+  guarded([&] {
+    orc::Mat M(n, n);
+    std::copy(A, A + static_cast<size_t>(n) * n, M.a.begin());
+    orc::Cholesky c;
+    c.compute(std::move(M));
+    std::copy(c.L.a.begin(), c.L.a.end(), A);
+    rc = c.ok ? 0 : 1;
+  });
+  return rc;
+}
+int orc_qr_solve(const double *A, int rows, int cols, const double *B, int nrhs, double *X, int transposed, int *rank)
+{
+  return guarded([&] {
+    orc::Mat M(rows, cols);
+    std::copy(A, A + static_cast<size_t>(rows) * cols, M.a.begin());
+    orc::ColPivQR qr;
+    qr.compute(std::move(M));
+    *rank           = qr.rank();
+    const int brows = transposed ? cols : rows;
+    orc::Mat  Bm(brows, nrhs);
+    std::copy(B, B + static_cast<size_t>(brows) * nrhs, Bm.a.begin());
+    const orc::Mat R = transposed ? qr.solveTransposed(Bm) : qr.solve(Bm);
+    std::copy(R.a.begin(), R.a.end(), X);
+  });
+}
+int orc_singular_values(const double *A, int rows, int cols, double *sv)
+{
+  return guarded([&] {
+    orc::Mat M(rows, cols);
+    std::copy(A, A + static_cast<size_t>(rows) * cols, M.a.begin());
+    const auto s = orc::singularValues(std::move(M));
+    std::copy(s.begin(), s.end(), sv);
+  });
+}
+
+// ---- timing helper for bench.py: one computeMapping + one map on the host cores ----
+// returns seconds for (compute, map) in t[0], t[1]
+int orc_pum_time(int constraint, int dim, int basis, double param, int polynomial, unsigned vpc, double overlap, int project,
+                 const double *inXYZ, int nIn, const double *outXYZ, int nOut, const double *in, int dims, double *out, int threads, double *t,
+                 int *nClusters)
+{
+  return guarded([&] {
+    orc::PumMapping m(static_cast<orc::Constraint>(constraint), dim, makeRbf(basis, param, std::numeric_limits<double>::infinity()),
+                      static_cast<orc::Polynomial>(polynomial), vpc, overlap, project != 0);
+    const auto t0 = std::chrono::steady_clock::now();
+    m.computeMapping(inXYZ, nIn, outXYZ, nOut, threads);
+    const auto t1 = std::chrono::steady_clock::now();
+    m.map(in, dims, out, threads);
+    const auto t2 = std::chrono::steady_clock::now();
+    t[0]          = std::chrono::duration<double>(t1 - t0).count();
+    t[1]          = std::chrono::duration<double>(t2 - t1).count();
+    *nClusters    = static_cast<int>(m.clusters().size());
+  });
+}
+
+} // extern "C"
