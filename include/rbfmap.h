@@ -1,0 +1,175 @@
+/* rbfmap.h — C ABI of the B200-native radial-basis-function data-mapping backend.
+ *
+ * This is the drop-in boundary for preCICE's RBF mapping hot path: everything a
+ * `precice::mapping::Mapping` backend for rbf-pum-direct / rbf-global-direct /
+ * rbf-global-iterative needs, as plain pointers and sizes (no C++/torch types), so that the
+ * reference can bind it from `src/mapping` with a thin adapter class.
+ * All citations are relative to /root/reference/src/ (preCICE 3.4.1).
+ *
+ * Conventions
+ *  - coordinates: `double xyz[n][3]`, exactly `mesh::Vertex::rawCoords()` (mesh/Vertex.hpp:75-77);
+ *    2-D meshes carry z = 0.
+ *  - values: vertex-major interleaved `values[i*dims + c]` as in `time::Sample`
+ *    (time/Sample.hpp:52-55, mapping/RadialBasisFctMapping.hpp:257-261).
+ *  - `input` / `output` mean Mapping::input() / Mapping::output(); the swap for conservative
+ *    constraints happens inside (mapping/PartitionOfUnityMapping.hpp:190-198).
+ *  - every call is synchronous and returns RBFMAP_OK or an error code; the message (same texts
+ *    as the reference's PRECICE_CHECKs) is available from rbfmap_last_error().
+ *  - there is no CPU fallback: without a CUDA device every compute call fails with
+ *    RBFMAP_ERR_CUDA.
+ */
+#ifndef RBFMAP_H
+#define RBFMAP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* mapping/config/MappingConfigurationTypes.hpp:11-15 */
+enum rbfmap_polynomial { RBFMAP_POLYNOMIAL_ON = 0, RBFMAP_POLYNOMIAL_OFF = 1, RBFMAP_POLYNOMIAL_SEPARATE = 2 };
+
+/* mapping/config/MappingConfigurationTypes.hpp:17-29 (functors: mapping/impl/BasisFunctions.hpp:87-607) */
+enum rbfmap_basis {
+  RBFMAP_COMPACT_POLYNOMIAL_C0 = 0,
+  RBFMAP_COMPACT_POLYNOMIAL_C2 = 1,
+  RBFMAP_COMPACT_POLYNOMIAL_C4 = 2,
+  RBFMAP_COMPACT_POLYNOMIAL_C6 = 3,
+  RBFMAP_COMPACT_POLYNOMIAL_C8 = 4,
+  RBFMAP_THIN_PLATE_SPLINES    = 5,
+  RBFMAP_MULTIQUADRICS         = 6,
+  RBFMAP_INVERSE_MULTIQUADRICS = 7,
+  RBFMAP_VOLUME_SPLINES        = 8,
+  RBFMAP_GAUSSIAN              = 9,
+  RBFMAP_COMPACT_TPS_C2        = 10
+};
+
+/* mapping/Mapping.hpp:30-35 */
+enum rbfmap_constraint {
+  RBFMAP_CONSISTENT                = 0,
+  RBFMAP_CONSERVATIVE              = 1,
+  RBFMAP_SCALED_CONSISTENT_SURFACE = 2,
+  RBFMAP_SCALED_CONSISTENT_VOLUME  = 3
+};
+
+/* the three XML tags of the hot path (mapping/config/MappingConfiguration.cpp:834-914) */
+enum rbfmap_variant { RBFMAP_GLOBAL_DIRECT = 0, RBFMAP_GLOBAL_ITERATIVE = 1, RBFMAP_PUM_DIRECT = 2 };
+
+enum rbfmap_status {
+  RBFMAP_OK              = 0,
+  RBFMAP_ERR_INVALID     = 1, /* bad argument / configuration (PRECICE_CHECK at construction) */
+  RBFMAP_ERR_CUDA        = 2, /* no device, CUDA runtime failure */
+  RBFMAP_ERR_SINGULAR    = 3, /* RadialBasisFctSolver.hpp:360-365 "... is not invertable ..." */
+  RBFMAP_ERR_UNASSIGNED  = 4, /* PartitionOfUnityMapping.hpp:314-318 "Output vertex ... could not be assigned ..." */
+  RBFMAP_ERR_EMPTY       = 5, /* impl/CreateClustering.hpp:502 "Too many vertices have been filtered out." */
+  RBFMAP_ERR_STATE       = 6, /* map before computeMapping, recompute without clear (PartitionOfUnityMapping.hpp:188) */
+  RBFMAP_ERR_UNSUPPORTED = 7,
+  RBFMAP_ERR_NOT_CONVERGED = 8
+};
+
+/* Constructor arguments of the three mapping classes:
+ *   RadialBasisFctMapping   (mapping/RadialBasisFctMapping.hpp:40-46)
+ *   PartitionOfUnityMapping (mapping/PartitionOfUnityMapping.hpp:48-57)
+ * plus the basis-function constructor argument (mapping/impl/BasisFunctions.hpp) and the
+ * <executor:cuda gpu-device-id=...> attribute (mapping/config/MappingConfiguration.cpp:283-338). */
+typedef struct rbfmap_config {
+  int      variant;              /* rbfmap_variant */
+  int      constraint;           /* rbfmap_constraint */
+  int      dimensions;           /* 2 or 3 */
+  int      basis;                /* rbfmap_basis */
+  double   support_radius;       /* compact polynomials / compact TPS; optional (>0) for gaussian */
+  double   shape_parameter;      /* gaussian, (inverse) multiquadrics */
+  int      polynomial;           /* rbfmap_polynomial */
+  int      dead_axis[3];         /* x-dead / y-dead / z-dead (global variants only) */
+  unsigned vertices_per_cluster; /* PUM, default 50 */
+  double   relative_overlap;     /* PUM, default 0.15 */
+  int      project_to_input;     /* PUM, default 1 */
+  double   solver_rtol;          /* global-iterative, default 1e-9 */
+  int      max_iterations;       /* global-iterative, default 1000000 (GinkgoRadialBasisFctSolver.hpp:337-374) */
+  int      device_id;            /* CUDA device ordinal; -1 = current device */
+} rbfmap_config;
+
+typedef struct rbfmap_handle rbfmap_handle;
+
+/* Fills *cfg with the XML defaults (MappingConfiguration.cpp:227-248). */
+void rbfmap_default_config(rbfmap_config *cfg);
+
+/* Mapping constructor. Validates the configuration like the reference constructors do
+ * (RadialBasisFctMapping.hpp:90, PartitionOfUnityMapping.hpp:165, BasisFunctions.hpp ctor checks). */
+int rbfmap_create(const rbfmap_config *cfg, rbfmap_handle **out);
+
+/* Mapping::computeMapping() (mapping/Mapping.hpp:101) with the meshes handed over by value
+ * (what Mapping::setMeshes + mesh.vertex(i).rawCoords() provide). Host pointers. */
+int rbfmap_compute_mapping(rbfmap_handle *h, const double *input_xyz, int64_t n_input, const double *output_xyz, int64_t n_output);
+
+/* Mapping::map(Sample, VectorXd&) dispatch (mapping/Mapping.cpp:158-173): conservative ->
+ * mapConservative, otherwise mapConsistent. `in` has n_input*dims, `out` n_output*dims doubles.
+ * `out` is overwritten with the mapped values (the reference accumulates into a pre-zeroed vector,
+ * precice/impl/DataContext.cpp:148-150). Scaled-consistent post-scaling (Mapping.cpp:175-246) needs
+ * mesh connectivity and stays with the caller. Host pointers. */
+int rbfmap_map(rbfmap_handle *h, const double *in, int dims, double *out);
+int rbfmap_map_consistent(rbfmap_handle *h, const double *in, int dims, double *out);   /* Mapping.hpp:337 */
+int rbfmap_map_conservative(rbfmap_handle *h, const double *in, int dims, double *out); /* Mapping.hpp:324 */
+
+/* Same two calls with DEVICE pointers (coordinates / values already resident in HBM); used by
+ * device-resident callers and by bench.py's kernel-only figure. The work is enqueued on the
+ * library's stream and the call returns after it completed. */
+int rbfmap_compute_mapping_device(rbfmap_handle *h, const double *d_input_xyz, int64_t n_input, const double *d_output_xyz, int64_t n_output);
+int rbfmap_map_device(rbfmap_handle *h, const double *d_in, int dims, double *d_out);
+
+/* Mapping::clear() (Mapping.hpp:134), Mapping::hasComputedMapping(), destructor, Mapping::getName(). */
+int         rbfmap_clear(rbfmap_handle *h);
+int         rbfmap_has_computed_mapping(const rbfmap_handle *h);
+void        rbfmap_destroy(rbfmap_handle *h);
+const char *rbfmap_get_name(const rbfmap_handle *h);
+
+/* Message of the last failing call on this handle (or of a failed rbfmap_create if h == NULL). */
+const char *rbfmap_last_error(const rbfmap_handle *h);
+
+/* Counters for profiling::Event::addData ("n clusters", PartitionOfUnityMapping.hpp:203) and for the
+ * roofline bookkeeping in bench.py (algorithmic flops per SURVEY.md §8d). */
+typedef struct rbfmap_stats {
+  int64_t n_in;               /* solver-side inMesh size (after the conservative swap) */
+  int64_t n_out;              /* solver-side outMesh size */
+  int64_t n_clusters;         /* PUM */
+  double  cluster_radius;     /* PUM */
+  int64_t sum_n;              /* sum over clusters of in-vertices n_c */
+  int64_t sum_m;              /* sum over clusters of out-vertices m_c */
+  int64_t sum_n2;             /* sum n_c^2 */
+  int64_t sum_n3;             /* sum n_c^3 */
+  int64_t sum_mn;             /* sum m_c n_c */
+  int64_t max_n;              /* largest cluster */
+  int64_t device_bytes;       /* bytes held on the device by this mapping */
+  int     iterations;         /* global-iterative: iterations of the last solve (max over components) */
+  double  residual;           /* global-iterative: relative residual of the last solve */
+  float   ms_compute_kernels; /* device time of the last computeMapping (CUDA events, whole call) */
+  float   ms_map_kernels;     /* device time of the last map */
+  float   ms_assembly_factor; /* device time of the dominant assembly(+factorisation) kernel(s) of the last computeMapping */
+  int     kernel_launches;    /* kernels launched by the last compute + map calls */
+} rbfmap_stats;
+int rbfmap_get_stats(const rbfmap_handle *h, rbfmap_stats *stats);
+
+/* Debug/inspection access used by the parity tests (sizes first, then data). PUM only.
+ * ids are vertex IDs of the solver-side inMesh / outMesh, sorted ascending per cluster
+ * (impl/SphericalVertexCluster.hpp:161-162). Any output pointer may be NULL. */
+int rbfmap_pum_get_clusters(const rbfmap_handle *h, double *centers /* n_clusters*3 */, int64_t *in_offsets /* n_clusters+1 */,
+                            int64_t *out_offsets /* n_clusters+1 */);
+int rbfmap_pum_get_cluster_ids(const rbfmap_handle *h, int32_t *in_ids /* sum_n */, int32_t *out_ids /* sum_m */);
+
+/* Basis function evaluated on the device for `n` radii (host pointers) — exposes a1 of SURVEY §8
+ * (mapping/impl/BasisFunctions.hpp) for bit-exact parity tests. */
+int rbfmap_eval_basis(int basis, double support_radius, double shape_parameter, const double *radii, int64_t n, double *values);
+
+/* Library / device probe: number of visible CUDA devices (0 if none), compute capability of device 0. */
+int rbfmap_device_count(void);
+int rbfmap_device_info(int device, int *sm_major, int *sm_minor, int *sm_count, int64_t *global_mem_bytes);
+
+/* Measured FP64 FMA peak of the current device (dependency-free DFMA loop, best of 4): the roofline denominator of
+ * the FP64-bound kernels; bench.py reports it next to every roofline fraction. */
+int rbfmap_measure_fp64_peak(double *tflops, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RBFMAP_H */

@@ -1,0 +1,102 @@
+"""ctypes binding of the C ABI in include/rbfmap.h (precice_b200/librbfmap.so).
+
+The shared library is the product; this module only loads it and declares the signatures. There is
+no CPU fallback: if the library is missing, loading fails loudly; if there is no CUDA device, every
+compute call returns RBFMAP_ERR_CUDA and raises MappingError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librbfmap.so")
+
+# enums of include/rbfmap.h
+POLYNOMIAL = {"on": 0, "off": 1, "separate": 2}
+BASIS = {
+    "compact-polynomial-c0": 0, "compact-polynomial-c2": 1, "compact-polynomial-c4": 2,
+    "compact-polynomial-c6": 3, "compact-polynomial-c8": 4, "thin-plate-splines": 5,
+    "multiquadrics": 6, "inverse-multiquadrics": 7, "volume-splines": 8, "gaussian": 9,
+    "compact-tps-c2": 10,
+}
+CONSTRAINT = {"consistent": 0, "conservative": 1, "scaled-consistent-surface": 2, "scaled-consistent-volume": 3}
+VARIANT = {"rbf-global-direct": 0, "rbf-global-iterative": 1, "rbf-pum-direct": 2}
+STATUS = {0: "OK", 1: "INVALID", 2: "CUDA", 3: "SINGULAR", 4: "UNASSIGNED", 5: "EMPTY", 6: "STATE", 7: "UNSUPPORTED",
+          8: "NOT_CONVERGED"}
+
+# every symbol include/rbfmap.h declares (checked by tests/test_abi.py)
+EXPORTS = [
+    "rbfmap_default_config", "rbfmap_create", "rbfmap_compute_mapping", "rbfmap_map", "rbfmap_map_consistent",
+    "rbfmap_map_conservative", "rbfmap_compute_mapping_device", "rbfmap_map_device", "rbfmap_clear",
+    "rbfmap_has_computed_mapping", "rbfmap_destroy", "rbfmap_get_name", "rbfmap_last_error", "rbfmap_get_stats",
+    "rbfmap_pum_get_clusters", "rbfmap_pum_get_cluster_ids", "rbfmap_eval_basis", "rbfmap_device_count",
+    "rbfmap_device_info", "rbfmap_measure_fp64_peak",
+]
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("variant", C.c_int), ("constraint", C.c_int), ("dimensions", C.c_int), ("basis", C.c_int),
+        ("support_radius", C.c_double), ("shape_parameter", C.c_double), ("polynomial", C.c_int),
+        ("dead_axis", C.c_int * 3), ("vertices_per_cluster", C.c_uint), ("relative_overlap", C.c_double),
+        ("project_to_input", C.c_int), ("solver_rtol", C.c_double), ("max_iterations", C.c_int), ("device_id", C.c_int),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("n_in", C.c_int64), ("n_out", C.c_int64), ("n_clusters", C.c_int64), ("cluster_radius", C.c_double),
+        ("sum_n", C.c_int64), ("sum_m", C.c_int64), ("sum_n2", C.c_int64), ("sum_n3", C.c_int64), ("sum_mn", C.c_int64),
+        ("max_n", C.c_int64), ("device_bytes", C.c_int64), ("iterations", C.c_int), ("residual", C.c_double),
+        ("ms_compute_kernels", C.c_float), ("ms_map_kernels", C.c_float), ("ms_assembly_factor", C.c_float),
+        ("kernel_launches", C.c_int),
+    ]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+_lib = None
+
+
+def build():
+    """Compiles librbfmap.so in-tree with nvcc for sm_100a (used by __graft_entry__.build())."""
+    import subprocess
+    subprocess.run(["make", "-C", os.path.join(_HERE, "csrc"), "-j", str(os.cpu_count() or 4)], check=True)
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(nvcc, sm_100a). precice_b200 has no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+        vp = C.c_void_p
+        L.rbfmap_default_config.argtypes = [C.POINTER(Config)]
+        L.rbfmap_default_config.restype = None
+        L.rbfmap_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+        L.rbfmap_compute_mapping.argtypes = [vp, vp, C.c_int64, vp, C.c_int64]
+        L.rbfmap_compute_mapping_device.argtypes = [vp, vp, C.c_int64, vp, C.c_int64]
+        for f in (L.rbfmap_map, L.rbfmap_map_consistent, L.rbfmap_map_conservative, L.rbfmap_map_device):
+            f.argtypes = [vp, vp, C.c_int, vp]
+        L.rbfmap_clear.argtypes = [vp]
+        L.rbfmap_has_computed_mapping.argtypes = [vp]
+        L.rbfmap_destroy.argtypes = [vp]
+        L.rbfmap_destroy.restype = None
+        L.rbfmap_get_name.argtypes = [vp]
+        L.rbfmap_get_name.restype = C.c_char_p
+        L.rbfmap_last_error.argtypes = [vp]
+        L.rbfmap_last_error.restype = C.c_char_p
+        L.rbfmap_get_stats.argtypes = [vp, C.POINTER(Stats)]
+        L.rbfmap_pum_get_clusters.argtypes = [vp, vp, vp, vp]
+        L.rbfmap_pum_get_cluster_ids.argtypes = [vp, vp, vp]
+        L.rbfmap_eval_basis.argtypes = [C.c_int, C.c_double, C.c_double, dp, C.c_int64, dp]
+        L.rbfmap_device_count.argtypes = []
+        L.rbfmap_device_info.argtypes = [C.c_int, ip, ip, ip, C.POINTER(C.c_int64)]
+        L.rbfmap_measure_fp64_peak.argtypes = [dp, dp]
+        _lib = L
+    return _lib

@@ -1,0 +1,391 @@
+// capi.cu — the extern "C" boundary declared in include/rbfmap.h.
+#include "mapping.cuh"
+#include "pum.cuh"
+
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <mutex>
+
+namespace rbfmap {
+
+// ---------------------------------------------------------------------------------------------
+// basis-function parameters (host): same derivation and argument checks as the reference functor
+// constructors (mapping/impl/BasisFunctions.hpp:120-124, 159-166, 229-252, 307-316, 361-370, ...)
+// ---------------------------------------------------------------------------------------------
+namespace {
+double hostGaussian(double radius, double shape, double support, double deltaY)
+{
+  if (radius > support)
+    return 0.0;
+  const double sr = shape * radius;
+  return std::exp(-(sr * sr)) - deltaY;
+}
+const char *compactName(int kind)
+{
+  switch (kind) {
+  case RBFMAP_COMPACT_TPS_C2: return "compact thin-plate-splines c2";
+  case RBFMAP_COMPACT_POLYNOMIAL_C0: return "compact polynomial c0";
+  case RBFMAP_COMPACT_POLYNOMIAL_C2: return "compact polynomial c2";
+  case RBFMAP_COMPACT_POLYNOMIAL_C4: return "compact polynomial c4";
+  default: return "compact polynomial c6"; // the reference's C8 constructor also says "c6" (BasisFunctions.hpp:569)
+  }
+}
+} // namespace
+
+RbfParams makeRbfParams(int kind, double supportRadius, double shapeParameter)
+{
+  RbfParams f{kind, 0.0, 0.0, 0.0};
+  switch (kind) {
+  case RBFMAP_THIN_PLATE_SPLINES:
+  case RBFMAP_VOLUME_SPLINES:
+    break;
+  case RBFMAP_MULTIQUADRICS:
+    f.p1 = shapeParameter * shapeParameter;
+    break;
+  case RBFMAP_INVERSE_MULTIQUADRICS:
+    if (!(shapeParameter > 0.0))
+      throw MapError(RBFMAP_ERR_INVALID, "Shape parameter for radial-basis-function inverse multiquadric has to be larger than zero. Please update the \"shape-parameter\" attribute.");
+    f.p1 = shapeParameter * shapeParameter;
+    break;
+  case RBFMAP_GAUSSIAN: {
+    const double support = supportRadius > 0.0 ? supportRadius : std::numeric_limits<double>::infinity();
+    if (!(shapeParameter > 0.0))
+      throw MapError(RBFMAP_ERR_INVALID, "Shape parameter for radial-basis-function gaussian has to be larger than zero. Please update the \"shape-parameter\" attribute.");
+    const double threshold = std::sqrt(-std::log(1e-9)) / shapeParameter; // cutoffThreshold, BasisFunctions.hpp:281
+    f.p1                   = shapeParameter;
+    f.p2                   = std::min(support, threshold);
+    f.p3                   = 0.0;
+    if (support < std::numeric_limits<double>::infinity())
+      f.p3 = hostGaussian(support, f.p1, f.p2, 0.0);
+    break;
+  }
+  case RBFMAP_COMPACT_TPS_C2:
+  case RBFMAP_COMPACT_POLYNOMIAL_C0:
+  case RBFMAP_COMPACT_POLYNOMIAL_C2:
+  case RBFMAP_COMPACT_POLYNOMIAL_C4:
+  case RBFMAP_COMPACT_POLYNOMIAL_C6:
+  case RBFMAP_COMPACT_POLYNOMIAL_C8:
+    if (!(supportRadius > 0.0))
+      throw MapError(RBFMAP_ERR_INVALID, std::string("Support radius for radial-basis-function ") + compactName(kind) +
+                                             " has to be larger than zero. Please update the \"support-radius\" attribute.");
+    f.p1 = 1.0 / supportRadius;
+    break;
+  default:
+    throw MapError(RBFMAP_ERR_INVALID, "unknown basis function");
+  }
+  return f;
+}
+
+double basisSupportRadius(const RbfParams &f)
+{
+  if (!basisHasCompactSupport(f.kind))
+    return std::numeric_limits<double>::max();
+  if (f.kind == RBFMAP_GAUSSIAN)
+    return f.p2;
+  return 1.0 / f.p1;
+}
+
+// ---------------------------------------------------------------------------------------------
+DeviceMapping::DeviceMapping(const rbfmap_config &cfg)
+    : _cfg(cfg)
+{
+  stats = rbfmap_stats{};
+  if (cfg.dimensions != 2 && cfg.dimensions != 3)
+    throw MapError(RBFMAP_ERR_INVALID, "dimensions has to be 2 or 3");
+  if (cfg.constraint < RBFMAP_CONSISTENT || cfg.constraint > RBFMAP_SCALED_CONSISTENT_VOLUME)
+    throw MapError(RBFMAP_ERR_INVALID, "unknown mapping constraint");
+  _rbf = makeRbfParams(cfg.basis, cfg.support_radius, cfg.shape_parameter);
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    throw MapError(RBFMAP_ERR_CUDA, "rbfmap: no CUDA device available; this backend has no CPU fallback.");
+  }
+  if (cfg.device_id >= 0) {
+    if (cfg.device_id >= count)
+      throw MapError(RBFMAP_ERR_CUDA, "rbfmap: gpu-device-id out of range.");
+    RBF_CUDA(cudaSetDevice(cfg.device_id));
+  }
+  RBF_CUDA(cudaStreamCreateWithFlags(&_stream, cudaStreamNonBlocking));
+}
+
+DeviceMapping::~DeviceMapping()
+{
+  if (_stream)
+    cudaStreamDestroy(_stream);
+}
+
+bool pumInspect(DeviceMapping *m, int64_t &nClusters, const double *&centers, const PumMembership *&mem);
+
+namespace {
+__global__ void evalBasisKernel(RbfParams f, const double *__restrict__ r, long long n, double *__restrict__ out)
+{
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i < n)
+    out[i] = evalBasis(r[i], f);
+}
+thread_local std::string g_createError;
+} // namespace
+
+} // namespace rbfmap
+
+using namespace rbfmap;
+
+struct rbfmap_handle {
+  std::unique_ptr<DeviceMapping> impl;
+  std::string                    lastError;
+  std::string                    name;
+  // staging buffers of the host-pointer API
+  DevBuf<double> dInXyz, dOutXyz, dIn, dOut;
+};
+
+namespace {
+template <typename F>
+int guarded(rbfmap_handle *h, F &&f)
+{
+  try {
+    f();
+    if (h)
+      h->lastError.clear();
+    return RBFMAP_OK;
+  } catch (const MapError &e) {
+    (h ? h->lastError : g_createError) = e.what();
+    cudaGetLastError();
+    return e.code;
+  } catch (const std::exception &e) {
+    (h ? h->lastError : g_createError) = e.what();
+    return RBFMAP_ERR_INVALID;
+  }
+}
+} // namespace
+
+extern "C" {
+
+void rbfmap_default_config(rbfmap_config *cfg)
+{
+  std::memset(cfg, 0, sizeof(*cfg));
+  cfg->variant              = RBFMAP_PUM_DIRECT;
+  cfg->constraint           = RBFMAP_CONSISTENT;
+  cfg->dimensions           = 3;
+  cfg->basis                = RBFMAP_COMPACT_POLYNOMIAL_C6;
+  cfg->polynomial           = RBFMAP_POLYNOMIAL_SEPARATE; // MappingConfiguration.cpp:227
+  cfg->vertices_per_cluster = 50;                         // :243-248
+  cfg->relative_overlap     = 0.15;
+  cfg->project_to_input     = 1;
+  cfg->solver_rtol          = 1e-9; // :237
+  cfg->max_iterations       = 1000000;
+  cfg->device_id            = -1;
+}
+
+int rbfmap_create(const rbfmap_config *cfg, rbfmap_handle **out)
+{
+  if (!cfg || !out)
+    return RBFMAP_ERR_INVALID;
+  *out = nullptr;
+  return guarded(nullptr, [&] {
+    auto h = std::make_unique<rbfmap_handle>();
+    switch (cfg->variant) {
+    case RBFMAP_PUM_DIRECT: h->impl = makePumMapping(*cfg); break;
+    case RBFMAP_GLOBAL_DIRECT: h->impl = makeGlobalDirectMapping(*cfg); break;
+    case RBFMAP_GLOBAL_ITERATIVE: h->impl = makeGlobalIterativeMapping(*cfg); break;
+    default: throw MapError(RBFMAP_ERR_INVALID, "unknown mapping variant");
+    }
+    h->name = h->impl->name();
+    *out    = h.release();
+  });
+}
+
+int rbfmap_compute_mapping_device(rbfmap_handle *h, const double *d_input_xyz, int64_t n_input, const double *d_output_xyz, int64_t n_output)
+{
+  if (!h)
+    return RBFMAP_ERR_INVALID;
+  return guarded(h, [&] {
+    if (n_input < 0 || n_output < 0)
+      throw MapError(RBFMAP_ERR_INVALID, "negative mesh size");
+    h->impl->computeMapping(d_input_xyz, n_input, d_output_xyz, n_output);
+  });
+}
+
+int rbfmap_compute_mapping(rbfmap_handle *h, const double *input_xyz, int64_t n_input, const double *output_xyz, int64_t n_output)
+{
+  if (!h)
+    return RBFMAP_ERR_INVALID;
+  return guarded(h, [&] {
+    if (n_input < 0 || n_output < 0)
+      throw MapError(RBFMAP_ERR_INVALID, "negative mesh size");
+    cudaStream_t s = h->impl->stream();
+    h->dInXyz.alloc(3 * std::max<int64_t>(n_input, 1));
+    h->dOutXyz.alloc(3 * std::max<int64_t>(n_output, 1));
+    if (n_input > 0)
+      RBF_CUDA(cudaMemcpyAsync(h->dInXyz.p, input_xyz, 3 * n_input * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (n_output > 0)
+      RBF_CUDA(cudaMemcpyAsync(h->dOutXyz.p, output_xyz, 3 * n_output * sizeof(double), cudaMemcpyHostToDevice, s));
+    RBF_CUDA(cudaStreamSynchronize(s));
+    h->impl->computeMapping(h->dInXyz.p, n_input, h->dOutXyz.p, n_output);
+    // the mapping keeps its own copies; release the staging buffers
+    h->dInXyz.release();
+    h->dOutXyz.release();
+  });
+}
+
+static void mapDeviceImpl(rbfmap_handle *h, int mode /*0 dispatch, 1 consistent, 2 conservative*/, const double *d_in, int dims, double *d_out)
+{
+  DeviceMapping *m    = h->impl.get();
+  const bool     cons = mode == 2 || (mode == 0 && m->isConservative());
+  if (cons)
+    m->mapConservative(d_in, dims, d_out);
+  else
+    m->mapConsistent(d_in, dims, d_out);
+  RBF_CUDA(cudaStreamSynchronize(m->stream()));
+}
+
+static int mapHostImpl(rbfmap_handle *h, int mode, const double *in, int dims, double *out)
+{
+  if (!h)
+    return RBFMAP_ERR_INVALID;
+  return guarded(h, [&] {
+    DeviceMapping *m = h->impl.get();
+    if (!m->hasComputedMapping())
+      throw MapError(RBFMAP_ERR_STATE, "The mapping has not been computed; call computeMapping() first.");
+    if (dims < 1)
+      throw MapError(RBFMAP_ERR_INVALID, "data dimension has to be positive");
+    cudaStream_t  s    = m->stream();
+    const int64_t nIn  = m->nInput() * dims;
+    const int64_t nOut = m->nOutput() * dims;
+    if (h->dIn.n < static_cast<size_t>(std::max<int64_t>(nIn, 1)))
+      h->dIn.alloc(std::max<int64_t>(nIn, 1));
+    if (h->dOut.n < static_cast<size_t>(std::max<int64_t>(nOut, 1)))
+      h->dOut.alloc(std::max<int64_t>(nOut, 1));
+    if (nIn > 0)
+      RBF_CUDA(cudaMemcpyAsync(h->dIn.p, in, nIn * sizeof(double), cudaMemcpyHostToDevice, s));
+    mapDeviceImpl(h, mode, h->dIn.p, dims, h->dOut.p);
+    if (nOut > 0)
+      RBF_CUDA(cudaMemcpyAsync(out, h->dOut.p, nOut * sizeof(double), cudaMemcpyDeviceToHost, s));
+    RBF_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+int rbfmap_map(rbfmap_handle *h, const double *in, int dims, double *out) { return mapHostImpl(h, 0, in, dims, out); }
+int rbfmap_map_consistent(rbfmap_handle *h, const double *in, int dims, double *out) { return mapHostImpl(h, 1, in, dims, out); }
+int rbfmap_map_conservative(rbfmap_handle *h, const double *in, int dims, double *out) { return mapHostImpl(h, 2, in, dims, out); }
+
+int rbfmap_map_device(rbfmap_handle *h, const double *d_in, int dims, double *d_out)
+{
+  if (!h)
+    return RBFMAP_ERR_INVALID;
+  return guarded(h, [&] {
+    if (!h->impl->hasComputedMapping())
+      throw MapError(RBFMAP_ERR_STATE, "The mapping has not been computed; call computeMapping() first.");
+    mapDeviceImpl(h, 0, d_in, dims, d_out);
+  });
+}
+
+int rbfmap_clear(rbfmap_handle *h)
+{
+  if (!h)
+    return RBFMAP_ERR_INVALID;
+  return guarded(h, [&] { h->impl->clear(); });
+}
+
+int rbfmap_has_computed_mapping(const rbfmap_handle *h) { return h && h->impl->hasComputedMapping() ? 1 : 0; }
+
+void rbfmap_destroy(rbfmap_handle *h) { delete h; }
+
+const char *rbfmap_get_name(const rbfmap_handle *h) { return h ? h->name.c_str() : ""; }
+
+const char *rbfmap_last_error(const rbfmap_handle *h) { return h ? h->lastError.c_str() : g_createError.c_str(); }
+
+int rbfmap_get_stats(const rbfmap_handle *h, rbfmap_stats *stats)
+{
+  if (!h || !stats)
+    return RBFMAP_ERR_INVALID;
+  *stats = h->impl->stats;
+  return RBFMAP_OK;
+}
+
+int rbfmap_pum_get_clusters(const rbfmap_handle *h, double *centers, int64_t *in_offsets, int64_t *out_offsets)
+{
+  if (!h)
+    return RBFMAP_ERR_INVALID;
+  return guarded(const_cast<rbfmap_handle *>(h), [&] {
+    int64_t              nc  = 0;
+    const double        *c   = nullptr;
+    const PumMembership *mem = nullptr;
+    if (!pumInspect(h->impl.get(), nc, c, mem))
+      throw MapError(RBFMAP_ERR_INVALID, "not a partition-of-unity mapping");
+    if (nc == 0)
+      return;
+    if (centers)
+      RBF_CUDA(cudaMemcpy(centers, c, 3 * nc * sizeof(double), cudaMemcpyDeviceToHost));
+    if (in_offsets)
+      RBF_CUDA(cudaMemcpy(in_offsets, mem->inOff.p, (nc + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    if (out_offsets)
+      RBF_CUDA(cudaMemcpy(out_offsets, mem->outOff.p, (nc + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  });
+}
+
+int rbfmap_pum_get_cluster_ids(const rbfmap_handle *h, int32_t *in_ids, int32_t *out_ids)
+{
+  if (!h)
+    return RBFMAP_ERR_INVALID;
+  return guarded(const_cast<rbfmap_handle *>(h), [&] {
+    int64_t              nc  = 0;
+    const double        *c   = nullptr;
+    const PumMembership *mem = nullptr;
+    if (!pumInspect(h->impl.get(), nc, c, mem))
+      throw MapError(RBFMAP_ERR_INVALID, "not a partition-of-unity mapping");
+    if (nc == 0)
+      return;
+    if (in_ids && mem->sumIn > 0)
+      RBF_CUDA(cudaMemcpy(in_ids, mem->inIds.p, mem->sumIn * sizeof(int), cudaMemcpyDeviceToHost));
+    if (out_ids && mem->sumOut > 0)
+      RBF_CUDA(cudaMemcpy(out_ids, mem->outIds.p, mem->sumOut * sizeof(int), cudaMemcpyDeviceToHost));
+  });
+}
+
+int rbfmap_eval_basis(int basis, double support_radius, double shape_parameter, const double *radii, int64_t n, double *values)
+{
+  return guarded(nullptr, [&] {
+    const RbfParams f = makeRbfParams(basis, support_radius, shape_parameter);
+    int             count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+      cudaGetLastError();
+      throw MapError(RBFMAP_ERR_CUDA, "rbfmap: no CUDA device available; this backend has no CPU fallback.");
+    }
+    if (n <= 0)
+      return;
+    DevBuf<double> r, v;
+    r.alloc(n);
+    v.alloc(n);
+    RBF_CUDA(cudaMemcpy(r.p, radii, n * sizeof(double), cudaMemcpyHostToDevice));
+    evalBasisKernel<<<divUp(n, 256), 256>>>(f, r.p, n, v.p);
+    RBF_CUDA(cudaGetLastError());
+    RBF_CUDA(cudaMemcpy(values, v.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+  });
+}
+
+int rbfmap_device_count(void)
+{
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return count;
+}
+
+int rbfmap_device_info(int device, int *sm_major, int *sm_minor, int *sm_count, int64_t *global_mem_bytes)
+{
+  cudaDeviceProp p{};
+  if (cudaGetDeviceProperties(&p, device) != cudaSuccess) {
+    cudaGetLastError();
+    return RBFMAP_ERR_CUDA;
+  }
+  if (sm_major) *sm_major = p.major;
+  if (sm_minor) *sm_minor = p.minor;
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (global_mem_bytes) *global_mem_bytes = static_cast<int64_t>(p.totalGlobalMem);
+  return RBFMAP_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,131 @@
+// common.cuh — shared host/device plumbing of the sm_100a RBF mapping library.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/rbfmap.h"
+
+namespace rbfmap {
+
+struct MapError : std::runtime_error {
+  int code;
+  MapError(int c, const std::string &msg)
+      : std::runtime_error(msg), code(c) {}
+};
+
+#define RBF_CUDA(call)                                                                                                            \
+  do {                                                                                                                            \
+    cudaError_t e_ = (call);                                                                                                      \
+    if (e_ != cudaSuccess)                                                                                                        \
+      throw ::rbfmap::MapError(RBFMAP_ERR_CUDA, std::string("CUDA failure: ") + cudaGetErrorString(e_) + " (" #call ") at " __FILE__ ":" + \
+                                                    std::to_string(__LINE__));                                                    \
+  } while (0)
+
+// math/differences.hpp:8
+constexpr double kZeroDiff = 1.0e-14;
+
+// Device buffer with stream-ordered allocation; owns its memory.
+template <typename T>
+struct DevBuf {
+  T     *p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf &)            = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  DevBuf(DevBuf &&o) noexcept
+      : p(o.p), n(o.n)
+  {
+    o.p = nullptr;
+    o.n = 0;
+  }
+  DevBuf &operator=(DevBuf &&o) noexcept
+  {
+    if (this != &o) {
+      release();
+      p   = o.p;
+      n   = o.n;
+      o.p = nullptr;
+      o.n = 0;
+    }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void alloc(size_t count)
+  {
+    release();
+    n = count;
+    if (count > 0)
+      RBF_CUDA(cudaMalloc(reinterpret_cast<void **>(&p), count * sizeof(T)));
+  }
+  void release()
+  {
+    if (p)
+      cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  size_t bytes() const { return n * sizeof(T); }
+};
+
+inline int divUp(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / b); }
+
+// number of SMs of the current device (cached)
+int smCount();
+
+// Exclusive prefix sums (own kernels, scan.cu): out has n+1 entries, out[n] = total.
+void exclusiveScan(const int *in, int *out, int64_t n, cudaStream_t s);
+void exclusiveScan(const int *in, int64_t *out, int64_t n, cudaStream_t s);
+void exclusiveScan(const int64_t *in, int64_t *out, int64_t n, cudaStream_t s);
+
+// counts kernels launched by this library on the calling thread (for bench.py's gpu_launches)
+extern thread_local int g_launches;
+#define RBF_LAUNCHED() (++::rbfmap::g_launches)
+
+// ---- device helpers ----
+#ifdef __CUDACC__
+// order-preserving map double -> uint64 so that atomicMin/atomicMax work on doubles
+__device__ __forceinline__ unsigned long long encodeOrdered(double d)
+{
+  unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(d));
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__host__ __device__ __forceinline__ double decodeOrdered(unsigned long long k)
+{
+  unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+#ifdef __CUDA_ARCH__
+  return __longlong_as_double(static_cast<long long>(b));
+#else
+  double d;
+  memcpy(&d, &b, 8);
+  return d;
+#endif
+}
+
+// RadialBasisFctSolver.hpp:102-113 with all axes active; no FMA contraction so that the value is
+// bit-identical to the reference's (a-b)*(a-b) accumulated left to right.
+__device__ __forceinline__ double sqDist3(double ax, double ay, double az, double bx, double by, double bz)
+{
+  const double dx = __dsub_rn(ax, bx), dy = __dsub_rn(ay, by), dz = __dsub_rn(az, bz);
+  double       s  = __dadd_rn(0.0, __dmul_rn(dx, dx));
+  s               = __dadd_rn(s, __dmul_rn(dy, dy));
+  s               = __dadd_rn(s, __dmul_rn(dz, dz));
+  return s;
+}
+// with an activity mask (1.0 / 0.0 per axis): (u - v) * active
+__device__ __forceinline__ double sqDist3Masked(double ax, double ay, double az, double bx, double by, double bz, double mx, double my, double mz)
+{
+  const double dx = __dmul_rn(__dsub_rn(ax, bx), mx), dy = __dmul_rn(__dsub_rn(ay, by), my), dz = __dmul_rn(__dsub_rn(az, bz), mz);
+  double       s  = __dadd_rn(0.0, __dmul_rn(dx, dx));
+  s               = __dadd_rn(s, __dmul_rn(dy, dy));
+  s               = __dadd_rn(s, __dmul_rn(dz, dz));
+  return s;
+}
+#endif
+
+} // namespace rbfmap

@@ -1,0 +1,72 @@
+// mapping.cuh — host-side mapping objects behind the C ABI (one per XML tag of the hot path).
+#pragma once
+
+#include "basis.cuh"
+#include "common.cuh"
+
+#include <memory>
+#include <string>
+
+namespace rbfmap {
+
+// Common interface; mirrors the virtuals of mapping::Mapping that the hot path implements
+// (mapping/Mapping.hpp:101 computeMapping, :134 clear, :324/:337 mapConservative/mapConsistent, :197 getName).
+class DeviceMapping {
+public:
+  explicit DeviceMapping(const rbfmap_config &cfg);
+  virtual ~DeviceMapping();
+
+  // input/output = Mapping::input()/output() coordinates on the device (AoS n x 3)
+  virtual void        computeMapping(const double *dInputXyz, int64_t nInput, const double *dOutputXyz, int64_t nOutput) = 0;
+  virtual void        mapConsistent(const double *dIn, int dims, double *dOut)                                         = 0;
+  virtual void        mapConservative(const double *dIn, int dims, double *dOut)                                       = 0;
+  virtual void        clear()                                                                                          = 0;
+  virtual std::string name() const                                                                                     = 0;
+
+  bool                 hasComputedMapping() const { return _computed; }
+  bool                 isConservative() const { return _cfg.constraint == RBFMAP_CONSERVATIVE; }
+  const rbfmap_config &config() const { return _cfg; }
+  cudaStream_t         stream() const { return _stream; }
+  int64_t              nInput() const { return _nInput; }
+  int64_t              nOutput() const { return _nOutput; }
+  rbfmap_stats         stats;
+
+protected:
+  rbfmap_config _cfg;
+  RbfParams     _rbf;
+  cudaStream_t  _stream   = nullptr;
+  bool          _computed = false;
+  int64_t       _nInput = 0, _nOutput = 0;
+};
+
+std::unique_ptr<DeviceMapping> makePumMapping(const rbfmap_config &cfg);
+std::unique_ptr<DeviceMapping> makeGlobalDirectMapping(const rbfmap_config &cfg);
+std::unique_ptr<DeviceMapping> makeGlobalIterativeMapping(const rbfmap_config &cfg);
+
+// simple CUDA-event stopwatch on a stream
+struct EventTimer {
+  cudaEvent_t  a = nullptr, b = nullptr;
+  cudaStream_t s;
+  explicit EventTimer(cudaStream_t stream)
+      : s(stream)
+  {
+    RBF_CUDA(cudaEventCreate(&a));
+    RBF_CUDA(cudaEventCreate(&b));
+  }
+  ~EventTimer()
+  {
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+  }
+  void  start() { RBF_CUDA(cudaEventRecord(a, s)); }
+  float stop()
+  {
+    RBF_CUDA(cudaEventRecord(b, s));
+    RBF_CUDA(cudaEventSynchronize(b));
+    float ms = 0.f;
+    RBF_CUDA(cudaEventElapsedTime(&ms, a, b));
+    return ms;
+  }
+};
+
+} // namespace rbfmap

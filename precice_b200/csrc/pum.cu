@@ -1,0 +1,432 @@
+// pum.cu — host driver of the partition-of-unity mapping (rbf-pum-direct).
+//
+// Mirrors mapping::PartitionOfUnityMapping (mapping/PartitionOfUnityMapping.hpp:181-380) and
+// impl::createClustering / estimateClusterRadius (mapping/impl/CreateClustering.hpp:223-505). The scalar
+// lattice arithmetic stays on the host (a few dozen flops); everything that touches vertices runs in kernels.
+#include "mapping.cuh"
+#include "pum.cuh"
+
+#include <algorithm>
+#include <array>
+#include <climits>
+#include <cmath>
+#include <numeric>
+#include <sstream>
+
+namespace rbfmap {
+namespace {
+
+__global__ void latticeKernel(const double *__restrict__ ax, const double *__restrict__ ay, const double *__restrict__ az, int nx, int ny, int nz,
+                              double *__restrict__ centers, int *__restrict__ tag)
+{
+  const long long total = static_cast<long long>(nx) * ny * nz;
+  const long long id    = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (id >= total)
+    return;
+  // linear index (x * ny + y) * nz + z  (impl/CreateClustering.hpp:36-45)
+  const int z = static_cast<int>(id % nz);
+  const int y = static_cast<int>((id / nz) % ny);
+  const int x = static_cast<int>(id / (static_cast<long long>(nz) * ny));
+  centers[3 * id]     = ax[x];
+  centers[3 * id + 1] = ay[y];
+  centers[3 * id + 2] = az[z];
+  tag[id]             = 0;
+}
+
+class PumMapping final : public DeviceMapping {
+public:
+  explicit PumMapping(const rbfmap_config &cfg)
+      : DeviceMapping(cfg)
+  {
+    // PartitionOfUnityMapping.hpp:163-168
+    if (cfg.polynomial == RBFMAP_POLYNOMIAL_ON)
+      throw MapError(RBFMAP_ERR_INVALID, "Integrated polynomial is not supported for partition of unity data mappings.");
+    if (!(cfg.relative_overlap < 1.0))
+      throw MapError(RBFMAP_ERR_INVALID, "The relative overlap has to be smaller than one.");
+    if (cfg.vertices_per_cluster == 0)
+      throw MapError(RBFMAP_ERR_INVALID, "The number of vertices per cluster has to be greater zero.");
+    if (!basisIsSpd(cfg.basis))
+      throw MapError(RBFMAP_ERR_UNSUPPORTED, "rbf-pum-direct on the device requires a strictly positive definite basis function "
+                                             "(compact polynomials, compact thin-plate splines, gaussian, inverse multiquadrics).");
+  }
+
+  std::string name() const override { return "partition-of-unity RBF (cuda-executor)"; }
+
+  void computeMapping(const double *dInputXyz, int64_t nInput, const double *dOutputXyz, int64_t nOutput) override;
+  void mapConsistent(const double *dIn, int dims, double *dOut) override { map(false, dIn, dims, dOut); }
+  void mapConservative(const double *dIn, int dims, double *dOut) override { map(true, dIn, dims, dOut); }
+  void clear() override
+  {
+    // PartitionOfUnityMapping.hpp:593-600
+    _inXyz.release();
+    _outXyz.release();
+    _centers.release();
+    _mem = PumMembership();
+    _mat.release();
+    _poly.release();
+    _wsum.release();
+    _wcount.release();
+    for (auto &l : _lists)
+      l.release();
+    _nClusters = 0;
+    _radius    = 0.0;
+    _computed  = false;
+    stats      = rbfmap_stats{};
+  }
+
+  // inspection (tests)
+  int64_t              nClusters() const { return _nClusters; }
+  const DevBuf<double> &centers() const { return _centers; }
+  const PumMembership  &membership() const { return _mem; }
+
+private:
+  void   map(bool conservative, const double *dIn, int dims, double *dOut);
+  double estimateClusterRadius(const double bbMin[3], const double bbMax[3]);
+  PumSolveArgs solveArgs() const;
+
+  DevBuf<double>  _inXyz, _outXyz; // solver-side inMesh / outMesh
+  int64_t         _nIn = 0, _nOut = 0;
+  double          _radius    = 0.0;
+  int64_t         _nClusters = 0;
+  DevBuf<double>  _centers;
+  PumMembership   _mem;
+  DevBuf<double>  _mat;
+  DevBuf<PolyRec> _poly;
+  DevBuf<double>  _wsum;
+  DevBuf<int>     _wcount;
+  DevBuf<int>     _lists[3];
+  int64_t         _listCount[3] = {0, 0, 0};
+  int             _listMaxN[3]  = {0, 0, 0};
+};
+
+PumSolveArgs PumMapping::solveArgs() const
+{
+  PumSolveArgs a{};
+  a.rbf     = _rbf;
+  a.dim     = _cfg.dimensions;
+  a.radius  = _radius;
+  a.inXyz   = _inXyz.p;
+  a.outXyz  = _outXyz.p;
+  a.centers = _centers.p;
+  a.nIn     = _mem.nIn.p;
+  a.nOut    = _mem.nOut.p;
+  a.inOff   = reinterpret_cast<const long long *>(_mem.inOff.p);
+  a.outOff  = reinterpret_cast<const long long *>(_mem.outOff.p);
+  a.matOff  = reinterpret_cast<const long long *>(_mem.matOff.p);
+  a.inIds   = _mem.inIds.p;
+  a.outIds  = _mem.outIds.p;
+  a.mat     = _mat.p;
+  a.poly    = _poly.p;
+  a.wsum    = _wsum.p;
+  a.wcount  = _wcount.p;
+  return a;
+}
+
+// impl/CreateClustering.hpp:223-278
+double PumMapping::estimateClusterRadius(const double bbMin[3], const double bbMax[3])
+{
+  const int dim = _cfg.dimensions;
+  double    center[3] = {0, 0, 0};
+  for (int d = 0; d < dim; ++d)
+    center[d] = (bbMax[d] + bbMin[d]) * 0.5;
+  std::vector<double> probes(center, center + 3);
+  for (int d = 0; d < dim; ++d) {
+    double s[3] = {center[0], center[1], center[2]};
+    const double edge = std::abs(bbMax[d] - bbMin[d]);
+    s[d] -= edge * 0.25;
+    probes.insert(probes.end(), s, s + 3);
+    s[d] += edge * 0.5;
+    probes.insert(probes.end(), s, s + 3);
+  }
+  const int        nProbes = static_cast<int>(probes.size() / 3);
+  std::vector<int> samples(nProbes);
+  nearestVertices(_inXyz.p, _nIn, probes.data(), nProbes, samples.data(), _stream);
+
+  // starting radius for the k-nearest search from the mean density of the bounding box
+  double vol  = 1.0;
+  int    live = 0;
+  for (int d = 0; d < dim; ++d)
+    if (bbMax[d] > bbMin[d]) {
+      vol *= (bbMax[d] - bbMin[d]);
+      ++live;
+    }
+  const double guess = live > 0 ? 0.8 * std::pow(vol * static_cast<double>(_cfg.vertices_per_cluster) / static_cast<double>(_nIn), 1.0 / live) : 1.0;
+  std::vector<double> radii(nProbes);
+  kthNeighbourDistance(_inXyz.p, _nIn, samples.data(), nProbes, static_cast<int>(_cfg.vertices_per_cluster), guess, radii.data(), _stream);
+  const size_t middle = radii.size() / 2;
+  std::nth_element(radii.begin(), radii.begin() + middle, radii.end());
+  return radii[middle];
+}
+
+void PumMapping::computeMapping(const double *dInputXyz, int64_t nInput, const double *dOutputXyz, int64_t nOutput)
+{
+  if (_computed)
+    throw MapError(RBFMAP_ERR_STATE, "Please clear the mapping before recomputing."); // PartitionOfUnityMapping.hpp:188
+  g_launches = 0;
+  EventTimer whole(_stream);
+  whole.start();
+  _nInput  = nInput;
+  _nOutput = nOutput;
+  // PartitionOfUnityMapping.hpp:190-198
+  const bool    cons   = isConservative();
+  const double *srcIn  = cons ? dOutputXyz : dInputXyz;
+  const double *srcOut = cons ? dInputXyz : dOutputXyz;
+  _nIn                 = cons ? nOutput : nInput;
+  _nOut                = cons ? nInput : nOutput;
+  if (_nIn > INT_MAX / 4 || _nOut > INT_MAX / 4)
+    throw MapError(RBFMAP_ERR_UNSUPPORTED, "mesh too large for 32-bit vertex IDs");
+  _inXyz.alloc(3 * std::max<int64_t>(_nIn, 1));
+  _outXyz.alloc(3 * std::max<int64_t>(_nOut, 1));
+  if (_nIn > 0)
+    RBF_CUDA(cudaMemcpyAsync(_inXyz.p, srcIn, 3 * _nIn * sizeof(double), cudaMemcpyDeviceToDevice, _stream));
+  if (_nOut > 0)
+    RBF_CUDA(cudaMemcpyAsync(_outXyz.p, srcOut, 3 * _nOut * sizeof(double), cudaMemcpyDeviceToDevice, _stream));
+
+  stats       = rbfmap_stats{};
+  stats.n_in  = _nIn;
+  stats.n_out = _nOut;
+  _nClusters  = 0;
+  _radius     = 0.0;
+
+  // impl/CreateClustering.hpp:314-316: nothing to do for empty meshes
+  if (_nIn == 0 || _nOut == 0) {
+    _computed = true;
+    return;
+  }
+  const int dim = _cfg.dimensions;
+  double    bbMin[3], bbMax[3], obMin[3], obMax[3];
+  computeBounds(_inXyz.p, _nIn, bbMin, bbMax, _stream); // :334 (bounds of the inMesh)
+  computeBounds(_outXyz.p, _nOut, obMin, obMax, _stream);
+  auto edge = [&](int d) { return std::abs(bbMax[d] - bbMin[d]); };
+
+  BinGrid inGrid, outGrid;
+  if (static_cast<uint64_t>(_nIn) < static_cast<uint64_t>(_cfg.vertices_per_cluster) * 2) {
+    // single-cluster fallback :352-359
+    double cRadius = 0.0;
+    for (int d = 0; d < dim; ++d)
+      cRadius = d == 0 ? (bbMax[d] - bbMin[d]) : std::max(cRadius, bbMax[d] - bbMin[d]);
+    if (cRadius == 0)
+      cRadius = 1;
+    _radius     = cRadius * 2;
+    double c[3] = {0, 0, 0};
+    for (int d = 0; d < dim; ++d)
+      c[d] = (bbMax[d] + bbMin[d]) * 0.5;
+    _centers.alloc(3);
+    RBF_CUDA(cudaMemcpyAsync(_centers.p, c, sizeof(c), cudaMemcpyHostToDevice, _stream));
+    RBF_CUDA(cudaStreamSynchronize(_stream));
+    _nClusters = 1;
+    inGrid.build(_inXyz.p, _nIn, bbMin, bbMax, _radius, _stream);
+    outGrid.build(_outXyz.p, _nOut, obMin, obMax, _radius, _stream);
+  } else {
+    _radius = estimateClusterRadius(bbMin, bbMax);
+    if (!(_radius > 0.0))
+      throw MapError(RBFMAP_ERR_SINGULAR, "rbf-pum-direct: the estimated cluster radius is zero (duplicated vertices?).");
+    // :366-427 lattice of tentative centres
+    const bool   startGridAtEdge       = _cfg.project_to_input != 0;
+    const double maximumCenterDistance = std::sqrt(4. / dim) * _radius * (1 - _cfg.relative_overlap);
+    std::array<unsigned, 3> nGlobal{{1, 1, 1}};
+    for (int d = 0; d < dim; ++d)
+      nGlobal[d] = static_cast<unsigned>(std::ceil(std::max(1., edge(d) / maximumCenterDistance)));
+    std::vector<double> distances(dim), start(dim);
+    for (int d = 0; d < dim; ++d) {
+      distances[d] = edge(d) / nGlobal[d];
+      start[d]     = bbMin[d];
+    }
+    if (startGridAtEdge) {
+      for (int d = 0; d < dim; ++d)
+        if (edge(d) > kZeroDiff)
+          nGlobal[d] += 1;
+    } else {
+      for (int d = 0; d < dim; ++d)
+        start[d] = start[d] + 0.5 * distances[d];
+    }
+    std::array<unsigned, 3> nLocal{{1, 1, 1}};
+    for (int d = 0; d < dim; ++d)
+      if (distances[d] > 0) {
+        start[d] += std::ceil(((bbMin[d] - start[d]) / distances[d]) - kZeroDiff) * distances[d];
+        nLocal[d] = static_cast<unsigned>(1 + std::floor(((bbMax[d] - start[d]) / distances[d]) + kZeroDiff));
+      }
+    const double totalD = static_cast<double>(nLocal[0]) * nLocal[1] * nLocal[2];
+    if (totalD > 1.0e9)
+      throw MapError(RBFMAP_ERR_UNSUPPORTED, "rbf-pum-direct: the tentative cluster lattice is too large.");
+    PumClustering cl;
+    cl.total  = static_cast<int64_t>(totalD);
+    cl.radius = _radius;
+    // :438-463 — coordinates grow by repeated addition, exactly like the reference loops
+    std::vector<double> axis[3];
+    for (int d = 0; d < 3; ++d) {
+      axis[d].assign(nLocal[d], 0.0);
+      if (d < dim) {
+        double v = start[d];
+        for (unsigned i = 0; i < nLocal[d]; ++i, v += distances[d])
+          axis[d][i] = v;
+      }
+    }
+    DevBuf<double> dAxis[3];
+    for (int d = 0; d < 3; ++d) {
+      dAxis[d].alloc(axis[d].size());
+      RBF_CUDA(cudaMemcpyAsync(dAxis[d].p, axis[d].data(), axis[d].size() * sizeof(double), cudaMemcpyHostToDevice, _stream));
+    }
+    cl.centers.alloc(3 * cl.total);
+    cl.tag.alloc(cl.total);
+    latticeKernel<<<divUp(cl.total, 256), 256, 0, _stream>>>(dAxis[0].p, dAxis[1].p, dAxis[2].p, nLocal[0], nLocal[1], nLocal[2], cl.centers.p, cl.tag.p);
+    RBF_LAUNCHED();
+
+    inGrid.build(_inXyz.p, _nIn, bbMin, bbMax, _radius, _stream);
+    outGrid.build(_outXyz.p, _nOut, obMin, obMax, _radius, _stream);
+
+    // :468-471
+    cl.tagEmpty(inGrid, _stream);
+    cl.tagEmpty(outGrid, _stream);
+    if (_cfg.project_to_input) { // :475-496
+      cl.project(inGrid, _stream);
+      const double     threshold = 0.4 * (*std::min_element(distances.begin(), distances.end()));
+      NeighbourOffsets offs{};
+      const bool       twoD = nLocal[2] == 1;
+      for (int dx = -1; dx <= 1; ++dx)
+        for (int dy = -1; dy <= 1; ++dy)
+          for (int dz = (twoD ? 0 : -1); dz <= (twoD ? 0 : 1); ++dz) {
+            if (dx == 0 && dy == 0 && dz == 0)
+              continue;
+            offs.off[offs.n++] = (static_cast<long long>(dx) * nLocal[1] + dy) * static_cast<long long>(nLocal[2]) + dz;
+          }
+      cl.tagDuplicates(offs, threshold, _stream);
+      cl.tagEmpty(outGrid, _stream);
+    }
+    _nClusters = cl.compact(_centers, _stream);
+    if (_nClusters == 0)
+      throw MapError(RBFMAP_ERR_EMPTY, "Too many vertices have been filtered out."); // :502
+  }
+
+  // per-cluster vertex sets (SphericalVertexCluster.hpp:153-162)
+  pumBuildMembership(_centers.p, _nClusters, inGrid, outGrid, _radius, _mem, _stream);
+
+  // partition-of-unity weight sums (PartitionOfUnityMapping.hpp:263-276, 290-341)
+  {
+    double cMin[3], cMax[3];
+    computeBounds(_centers.p, _nClusters, cMin, cMax, _stream);
+    BinGrid centerGrid;
+    centerGrid.build(_centers.p, _nClusters, cMin, cMax, _radius, _stream);
+    _wsum.alloc(_nOut);
+    _wcount.alloc(_nOut);
+    const int64_t bad = pumWeightSums(_outXyz.p, _nOut, centerGrid, _radius, _wsum.p, _wcount.p, _stream);
+    if (bad >= 0) {
+      double v[3];
+      RBF_CUDA(cudaMemcpy(v, _outXyz.p + 3 * bad, sizeof(v), cudaMemcpyDeviceToHost));
+      std::ostringstream os;
+      os.precision(17);
+      os << "Output vertex " << v[0] << " " << v[1];
+      if (dim == 3)
+        os << " " << v[2];
+      os << " of mesh \"" << (cons ? "input" : "output")
+         << "\" could not be assigned to any cluster in the rbf-pum mapping. This probably means that the meshes do not match well geometry-wise: "
+            "Visualize the exported preCICE meshes to confirm. If the meshes are fine geometry-wise, you can try to increase the number of "
+            "\"vertices-per-cluster\" (default is 50), the \"relative-overlap\" (default is 0.15), or disable the option \"project-to-input\". "
+            "These options are only valid for the <mapping:rbf-pum-direct/> tag.";
+      throw MapError(RBFMAP_ERR_UNASSIGNED, os.str());
+    }
+  }
+
+  // size classes + statistics (host pass over the per-cluster counts)
+  std::vector<int> hIn(_nClusters), hOut(_nClusters);
+  RBF_CUDA(cudaMemcpyAsync(hIn.data(), _mem.nIn.p, _nClusters * sizeof(int), cudaMemcpyDeviceToHost, _stream));
+  RBF_CUDA(cudaMemcpyAsync(hOut.data(), _mem.nOut.p, _nClusters * sizeof(int), cudaMemcpyDeviceToHost, _stream));
+  RBF_CUDA(cudaStreamSynchronize(_stream));
+  std::vector<int> lists[3];
+  for (int64_t c = 0; c < _nClusters; ++c) {
+    const int64_t n = hIn[c], m = hOut[c];
+    stats.sum_n += n;
+    stats.sum_m += m;
+    stats.sum_n2 += n * n;
+    stats.sum_n3 += n * n * n;
+    stats.sum_mn += m * n;
+    stats.max_n = std::max<int64_t>(stats.max_n, n);
+    const int cls = n <= kClassSmall ? 0 : (n <= kClassMedium ? 1 : 2);
+    lists[cls].push_back(static_cast<int>(c));
+    _listMaxN[cls] = std::max<int>(_listMaxN[cls], static_cast<int>(n));
+  }
+  for (int k = 0; k < 3; ++k) {
+    _listCount[k] = static_cast<int64_t>(lists[k].size());
+    _lists[k].alloc(std::max<size_t>(lists[k].size(), 1));
+    if (!lists[k].empty())
+      RBF_CUDA(cudaMemcpyAsync(_lists[k].p, lists[k].data(), lists[k].size() * sizeof(int), cudaMemcpyHostToDevice, _stream));
+  }
+  RBF_CUDA(cudaStreamSynchronize(_stream));
+  stats.n_clusters     = _nClusters;
+  stats.cluster_radius = _radius;
+
+  // separated polynomial + assembly/factorisation of all local systems
+  _poly.alloc(_nClusters);
+  _mat.alloc(std::max<int64_t>(_mem.sumTri, 1));
+  const PumSolveArgs args = solveArgs();
+  pumPolySetup(args, _nClusters, _cfg.polynomial, _stream);
+  DevBuf<int> fail;
+  fail.alloc(1);
+  const int noFail = INT_MAX;
+  RBF_CUDA(cudaMemcpyAsync(fail.p, &noFail, sizeof(int), cudaMemcpyHostToDevice, _stream));
+  EventTimer tf(_stream);
+  tf.start();
+  static const int classes[3] = {kClassSmall, kClassMedium, INT_MAX};
+  for (int k = 0; k < 3; ++k)
+    pumFactor(args, _lists[k].p, _listCount[k], classes[k], _listMaxN[k], fail.p, _stream);
+  stats.ms_assembly_factor = tf.stop();
+  int failed = INT_MAX;
+  RBF_CUDA(cudaMemcpy(&failed, fail.p, sizeof(int), cudaMemcpyDeviceToHost));
+  if (failed != INT_MAX) {
+    // RadialBasisFctSolver.hpp:360-365
+    const char *inName = cons ? "output" : "input", *outName = cons ? "input" : "output";
+    throw MapError(RBFMAP_ERR_SINGULAR, std::string("The interpolation matrix of the RBF mapping from mesh \"") + inName + "\" to mesh \"" + outName +
+                                            "\" is not invertable. This means that the mapping problem is not well-posed. "
+                                            "Please check if your coupling meshes are correct (e.g. no vertices are duplicated) or reconfigure "
+                                            "your basis-function (e.g. reduce the support-radius).");
+  }
+  stats.device_bytes       = static_cast<int64_t>(_inXyz.bytes() + _outXyz.bytes() + _centers.bytes() + _mem.bytes() + _mat.bytes() + _poly.bytes() + _wsum.bytes() + _wcount.bytes());
+  stats.ms_compute_kernels = whole.stop();
+  stats.kernel_launches    = g_launches;
+  _computed                = true;
+}
+
+void PumMapping::map(bool conservative, const double *dIn, int dims, double *dOut)
+{
+  if (!_computed)
+    throw MapError(RBFMAP_ERR_STATE, "The mapping has not been computed; call computeMapping() first.");
+  if (dims < 1)
+    throw MapError(RBFMAP_ERR_INVALID, "data dimension has to be positive");
+  const int launchesBefore = g_launches;
+  EventTimer t(_stream);
+  t.start();
+  // result lives on the solver-side outMesh (consistent) or inMesh (conservative)
+  const int64_t nRes = conservative ? _nIn : _nOut;
+  if (nRes > 0)
+    RBF_CUDA(cudaMemsetAsync(dOut, 0, static_cast<size_t>(nRes) * dims * sizeof(double), _stream));
+  if (_nClusters > 0) {
+    const PumSolveArgs args       = solveArgs();
+    static const int   classes[3] = {kClassSmall, kClassMedium, INT_MAX};
+    for (int k = 0; k < 3; ++k) {
+      if (conservative)
+        pumMapConservative(args, _lists[k].p, _listCount[k], classes[k], _listMaxN[k], dIn, dims, dOut, _stream);
+      else
+        pumMapConsistent(args, _lists[k].p, _listCount[k], classes[k], _listMaxN[k], dIn, dims, dOut, _stream);
+    }
+  }
+  stats.ms_map_kernels = t.stop();
+  stats.kernel_launches += g_launches - launchesBefore;
+}
+
+} // namespace
+
+std::unique_ptr<DeviceMapping> makePumMapping(const rbfmap_config &cfg) { return std::make_unique<PumMapping>(cfg); }
+
+// ---- inspection helpers used by capi.cu ----
+bool pumInspect(DeviceMapping *m, int64_t &nClusters, const double *&centers, const PumMembership *&mem)
+{
+  auto *p = dynamic_cast<PumMapping *>(m);
+  if (!p)
+    return false;
+  nClusters = p->nClusters();
+  centers   = p->centers().p;
+  mem       = &p->membership();
+  return true;
+}
+
+} // namespace rbfmap

@@ -1,0 +1,83 @@
+// pum.cuh — partition-of-unity mapping on the device: data structures shared by the clustering
+// kernels (pum_cluster.cu), the per-cluster algebra kernels (pum_solve.cu) and the host driver (pum.cu).
+#pragma once
+
+#include "basis.cuh"
+#include "common.cuh"
+#include "spatial.cuh"
+
+namespace rbfmap {
+
+// index offsets of the 8 / 26 lattice neighbours (impl/CreateClustering.hpp:54-82)
+struct NeighbourOffsets {
+  long long off[26];
+  int       n;
+};
+
+// tentative centre lattice and its tags (impl/CreateClustering.hpp:411-496)
+struct PumClustering {
+  int64_t        total  = 0;
+  double         radius = 0.0;
+  DevBuf<double> centers; // total x 3
+  DevBuf<int>    tag;     // 1 = tagged for removal
+
+  void    tagEmpty(const BinGrid &mesh, cudaStream_t s);
+  void    project(const BinGrid &inMesh, cudaStream_t s);
+  void    tagDuplicates(const NeighbourOffsets &offs, double threshold, cudaStream_t s);
+  int64_t compact(DevBuf<double> &out, cudaStream_t s); // returns the number of surviving centres
+};
+
+// CSR description of all clusters (impl/SphericalVertexCluster.hpp:153-162): sorted vertex IDs
+struct PumMembership {
+  DevBuf<int>     nIn, nOut;             // per cluster
+  DevBuf<int64_t> tri;                   // n(n+1)/2 per cluster
+  DevBuf<int64_t> inOff, outOff, matOff; // nClusters + 1 each
+  DevBuf<int>     inIds, outIds;
+  int64_t         sumIn = 0, sumOut = 0, sumTri = 0;
+  size_t          bytes() const
+  {
+    return nIn.bytes() + nOut.bytes() + tri.bytes() + inOff.bytes() + outOff.bytes() + matOff.bytes() + inIds.bytes() + outIds.bytes();
+  }
+};
+
+void    pumBuildMembership(const double *dCenters, int64_t nClusters, const BinGrid &inMesh, const BinGrid &outMesh, double radius, PumMembership &m, cudaStream_t s);
+int64_t pumWeightSums(const double *dOutXyz, int64_t nOut, const BinGrid &centerGrid, double radius, double *wsum, int *wcount, cudaStream_t s);
+
+// Per-cluster separated-polynomial record (RadialBasisFctSolver.hpp:377-410 condensed).
+//  mode 0: no polynomial
+//  mode 1: n >= p, full column rank. Basis [1, (x_a - c_a)/r ...] over the active axes `mask`,
+//          G = inverse Gram matrix of that basis (row-major 4x4, leading p x p block used).
+//  mode 2: n < p (under-determined, SphericalVertexCluster.hpp:170-172): G holds the p x n operator S with
+//          beta = S f in the RAW basis [1, x_a ...] (S[q*4 + i]), i.e. ColPivHouseholderQR::solve.
+struct PolyRec {
+  double G[16];
+  int    mode, mask, p, pad;
+};
+
+struct PumSolveArgs {
+  RbfParams        rbf;
+  int              dim;
+  double           radius; // cluster radius
+  const double    *inXyz, *outXyz; // solver-side meshes (device AoS)
+  const double    *centers;
+  const int       *nIn, *nOut;
+  const long long *inOff, *outOff, *matOff;
+  const int       *inIds, *outIds;
+  double          *mat; // packed factors
+  PolyRec         *poly;
+  const double    *wsum;
+  const int       *wcount;
+};
+
+// cluster size classes handled by different kernel instantiations
+constexpr int kClassSmall  = 64;  // n <= 64 : 8x8 threads, 8x8 register tile per thread
+constexpr int kClassMedium = 128; // n <= 128: 16x16 threads
+// larger clusters go through the global-memory kernels
+
+void pumPolySetup(const PumSolveArgs &a, int64_t nClusters, int polynomial, cudaStream_t s);
+// `list` = device array of cluster indices of one class; fail = device int (first failing cluster or INT_MAX)
+void pumFactor(const PumSolveArgs &a, const int *list, int64_t count, int sizeClass, int maxN, int *fail, cudaStream_t s);
+void pumMapConsistent(const PumSolveArgs &a, const int *list, int64_t count, int sizeClass, int maxN, const double *in, int dims, double *out, cudaStream_t s);
+void pumMapConservative(const PumSolveArgs &a, const int *list, int64_t count, int sizeClass, int maxN, const double *in, int dims, double *out, cudaStream_t s);
+
+} // namespace rbfmap

@@ -1,0 +1,411 @@
+// pum_cluster.cu — device side of the partition-of-unity clustering and vertex/cluster association.
+//
+// Replaces (on the device) the host R-tree driven parts of
+//   impl/CreateClustering.hpp:132-140  tagEmptyClusters
+//   impl/CreateClustering.hpp:150-160  projectClusterCentersToinputMesh
+//   impl/CreateClustering.hpp:96-122, 173-195  getNeighborsWithinSphere / tagDuplicateCenters
+//   impl/CreateClustering.hpp:205-208  removeTaggedVertices
+//   impl/SphericalVertexCluster.hpp:153-162  per-cluster sphere queries + sorted ID sets
+//   PartitionOfUnityMapping.hpp:290-341  computeNormalizedWeight (the per-vertex weight sums)
+#include "pum.cuh"
+
+#include <algorithm>
+
+namespace rbfmap {
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kBlockThreads  = kWarpsPerBlock * 32;
+
+inline int warpGrid(int64_t nWarps) { return static_cast<int>(std::max<int64_t>(1, (nWarps + kWarpsPerBlock - 1) / kWarpsPerBlock)); }
+
+// ---- tagEmptyClusters: one warp per centre --------------------------------------------------
+__global__ void tagEmptyKernel(const double *__restrict__ centers, int *__restrict__ tag, int64_t total, BinGridView g, double radius)
+{
+  const int64_t c    = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int     lane = threadIdx.x & 31;
+  if (c >= total || tag[c] != 0)
+    return;
+  const double cx = centers[3 * c], cy = centers[3 * c + 1], cz = centers[3 * c + 2];
+  bool         found = false;
+  forNeighbourhoodWarp(g, cx, cy, cz, lane, [&](int pos, bool valid) {
+    bool hit = false;
+    if (valid)
+      hit = __dsqrt_rn(sqDist3(cx, cy, cz, g.xyz[3 * pos], g.xyz[3 * pos + 1], g.xyz[3 * pos + 2])) < radius;
+    if (__any_sync(0xffffffffu, hit)) {
+      found = true;
+      return true;
+    }
+    return false;
+  });
+  if (!found && lane == 0)
+    tag[c] = 1;
+}
+
+// ---- projectClusterCentersToinputMesh: one warp per centre ----------------------------------
+__global__ void projectKernel(double *__restrict__ centers, const int *__restrict__ tag, int64_t total, BinGridView g)
+{
+  const int64_t c    = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int     lane = threadIdx.x & 31;
+  if (c >= total || tag[c] != 0)
+    return;
+  const double cx = centers[3 * c], cy = centers[3 * c + 1], cz = centers[3 * c + 2];
+  double       best = 1.7976931348623157e308;
+  int          bestId = 0x7fffffff, bestPos = -1;
+  forNeighbourhoodWarp(g, cx, cy, cz, lane, [&](int pos, bool valid) {
+    if (valid) {
+      const double d2 = sqDist3(cx, cy, cz, g.xyz[3 * pos], g.xyz[3 * pos + 1], g.xyz[3 * pos + 2]);
+      const int    id = g.ids[pos];
+      if (d2 < best || (d2 == best && id < bestId)) {
+        best    = d2;
+        bestId  = id;
+        bestPos = pos;
+      }
+    }
+    return false;
+  });
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int    oi = __shfl_xor_sync(0xffffffffu, bestId, o);
+    const int    op = __shfl_xor_sync(0xffffffffu, bestPos, o);
+    if (ob < best || (ob == best && oi < bestId)) {
+      best    = ob;
+      bestId  = oi;
+      bestPos = op;
+    }
+  }
+  if (lane < 3 && bestPos >= 0)
+    centers[3 * c + lane] = g.xyz[3 * bestPos + lane];
+}
+
+// ---- tagDuplicateCenters ---------------------------------------------------------------------
+// state: 0 = untagged (final), 1 = tagged (final), 2 = undecided
+__global__ void dupInitKernel(const double *__restrict__ centers, const int *__restrict__ tag, int64_t total, NeighbourOffsets offs, double thr2,
+                              int *__restrict__ state, unsigned *__restrict__ lowMask)
+{
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= total)
+    return;
+  if (tag[i] != 0) {
+    state[i]   = 1;
+    lowMask[i] = 0;
+    return;
+  }
+  const double cx = centers[3 * i], cy = centers[3 * i + 1], cz = centers[3 * i + 2];
+  bool         higher = false;
+  unsigned     low    = 0;
+  for (int k = 0; k < offs.n; ++k) {
+    const long long off = offs.off[k];
+    if (off == 0)
+      continue; // CreateClustering.hpp:103-105
+    const long long nb = i + off;
+    if (nb < 0 || nb >= total || tag[nb] != 0)
+      continue;
+    if (sqDist3(cx, cy, cz, centers[3 * nb], centers[3 * nb + 1], centers[3 * nb + 2]) < thr2) {
+      if (nb > i)
+        higher = true;
+      else
+        low |= (1u << k);
+    }
+  }
+  // a close neighbour with a HIGHER index has not been visited yet by the sequential sweep of the
+  // reference, hence it is untagged when centre i is visited -> i gets tagged
+  state[i]   = higher ? 1 : (low == 0 ? 0 : 2);
+  lowMask[i] = low;
+}
+
+__global__ void dupResolveKernel(int64_t total, NeighbourOffsets offs, int *__restrict__ state, const unsigned *__restrict__ lowMask, int *__restrict__ undecided)
+{
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= total || state[i] != 2)
+    return;
+  const unsigned low = lowMask[i];
+  bool           anyUntagged = false, anyUndecided = false;
+  for (int k = 0; k < offs.n; ++k)
+    if (low & (1u << k)) {
+      const int s = reinterpret_cast<volatile int *>(state)[i + offs.off[k]];
+      anyUntagged |= (s == 0);
+      anyUndecided |= (s == 2);
+    }
+  if (anyUntagged)
+    state[i] = 1;
+  else if (!anyUndecided)
+    state[i] = 0;
+  else
+    atomicAdd(undecided, 1);
+}
+
+__global__ void stateToTagKernel(int64_t total, const int *__restrict__ state, int *__restrict__ tag)
+{
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < total)
+    tag[i] = state[i] != 0 ? 1 : 0;
+}
+
+// ---- removeTaggedVertices (stream compaction, order preserving) ------------------------------
+__global__ void keepFlagKernel(int64_t total, const int *__restrict__ tag, int *__restrict__ keep)
+{
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < total)
+    keep[i] = tag[i] == 0 ? 1 : 0;
+}
+__global__ void compactKernel(int64_t total, const int *__restrict__ tag, const int *__restrict__ pos, const double *__restrict__ centers, double *__restrict__ out)
+{
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < total && tag[i] == 0) {
+    const int64_t o = pos[i];
+    out[3 * o]      = centers[3 * i];
+    out[3 * o + 1]  = centers[3 * i + 1];
+    out[3 * o + 2]  = centers[3 * i + 2];
+  }
+}
+
+// ---- cluster membership: one warp per cluster ------------------------------------------------
+__global__ void memberCountKernel(const double *__restrict__ centers, int64_t nClusters, BinGridView gin, BinGridView gout, double rIn, double rOut,
+                                  int *__restrict__ nIn, int *__restrict__ nOut, long long *__restrict__ tri)
+{
+  const int64_t c    = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int     lane = threadIdx.x & 31;
+  if (c >= nClusters)
+    return;
+  const double cx = centers[3 * c], cy = centers[3 * c + 1], cz = centers[3 * c + 2];
+  int          ci = 0, co = 0;
+  forNeighbourhoodWarp(gin, cx, cy, cz, lane, [&](int pos, bool valid) {
+    if (valid && __dsqrt_rn(sqDist3(cx, cy, cz, gin.xyz[3 * pos], gin.xyz[3 * pos + 1], gin.xyz[3 * pos + 2])) < rIn)
+      ++ci;
+    return false;
+  });
+  forNeighbourhoodWarp(gout, cx, cy, cz, lane, [&](int pos, bool valid) {
+    if (valid && __dsqrt_rn(sqDist3(cx, cy, cz, gout.xyz[3 * pos], gout.xyz[3 * pos + 1], gout.xyz[3 * pos + 2])) < rOut)
+      ++co;
+    return false;
+  });
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ci += __shfl_xor_sync(0xffffffffu, ci, o);
+    co += __shfl_xor_sync(0xffffffffu, co, o);
+  }
+  if (lane == 0) {
+    nIn[c]  = ci;
+    nOut[c] = co;
+    tri[c]  = static_cast<long long>(ci) * (ci + 1) / 2;
+  }
+}
+
+// warp-cooperative ascending sort of seg[0..n) (global memory) through a shared staging buffer
+__device__ void warpSortSegment(int *seg, int n, int *stage, int stageCap, int lane)
+{
+  if (n <= 1)
+    return;
+  if (n <= stageCap) {
+    int p = 1;
+    while (p < n)
+      p <<= 1;
+    for (int i = lane; i < p; i += 32)
+      stage[i] = i < n ? seg[i] : 0x7fffffff;
+    __syncwarp();
+    for (int k = 2; k <= p; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = lane; i < p; i += 32) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const int  a = stage[i], b = stage[ixj];
+            const bool up = (i & k) == 0;
+            if ((a > b) == up) {
+              stage[i]   = b;
+              stage[ixj] = a;
+            }
+          }
+        }
+        __syncwarp();
+      }
+    for (int i = lane; i < n; i += 32)
+      seg[i] = stage[i];
+    __syncwarp();
+  } else {
+    // rare: very large cluster — odd-even transposition sort in global memory
+    for (int round = 0; round < n; ++round) {
+      for (int i = 2 * lane + (round & 1); i + 1 < n; i += 64) {
+        const int a = seg[i], b = seg[i + 1];
+        if (a > b) {
+          seg[i]     = b;
+          seg[i + 1] = a;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+constexpr int kSortCap = 1024; // ints staged per warp
+
+__device__ void gatherMembers(const BinGridView &g, double cx, double cy, double cz, double r, int *seg, int lane)
+{
+  int base = 0;
+  forNeighbourhoodWarp(g, cx, cy, cz, lane, [&](int pos, bool valid) {
+    const bool     hit = valid && __dsqrt_rn(sqDist3(cx, cy, cz, g.xyz[3 * pos], g.xyz[3 * pos + 1], g.xyz[3 * pos + 2])) < r;
+    const unsigned m   = __ballot_sync(0xffffffffu, hit);
+    if (hit)
+      seg[base + __popc(m & ((1u << lane) - 1u))] = g.ids[pos];
+    base += __popc(m);
+    return false;
+  });
+  __syncwarp();
+}
+
+__global__ void memberFillKernel(const double *__restrict__ centers, int64_t nClusters, BinGridView gin, BinGridView gout, double rIn, double rOut,
+                                 const long long *__restrict__ inOff, const long long *__restrict__ outOff, int *__restrict__ inIds, int *__restrict__ outIds)
+{
+  __shared__ int stage[kWarpsPerBlock][kSortCap];
+  const int64_t  c    = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int      lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (c >= nClusters)
+    return;
+  const double cx = centers[3 * c], cy = centers[3 * c + 1], cz = centers[3 * c + 2];
+  int         *segIn = inIds + inOff[c], *segOut = outIds + outOff[c];
+  const int    ni = static_cast<int>(inOff[c + 1] - inOff[c]), no = static_cast<int>(outOff[c + 1] - outOff[c]);
+  gatherMembers(gin, cx, cy, cz, rIn, segIn, lane);
+  warpSortSegment(segIn, ni, stage[w], kSortCap, lane);
+  gatherMembers(gout, cx, cy, cz, rOut, segOut, lane);
+  warpSortSegment(segOut, no, stage[w], kSortCap, lane);
+}
+
+// ---- weight sums: one thread per out-vertex -------------------------------------------------
+// PartitionOfUnityMapping.hpp:306-333: clusters with |x - c| < r; w_c = C2(|x - c| / r); sum of w.
+__global__ void weightSumKernel(const double *__restrict__ outXyz, int64_t nOut, BinGridView gc, double radius, double rinv, double *__restrict__ wsum,
+                                int *__restrict__ wcount, int *__restrict__ firstUnassigned)
+{
+  const int64_t v = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (v >= nOut)
+    return;
+  const double x = outXyz[3 * v], y = outXyz[3 * v + 1], z = outXyz[3 * v + 2];
+  double       sum = 0.0;
+  int          cnt = 0;
+  forNeighbourhoodThread(gc, x, y, z, [&](int pos) {
+    // computeWeight (SphericalVertexCluster.hpp:337-344): squared difference (centre, vertex)
+    const double d = __dsqrt_rn(sqDist3(gc.xyz[3 * pos], gc.xyz[3 * pos + 1], gc.xyz[3 * pos + 2], x, y, z));
+    if (d < radius) {
+      sum = __dadd_rn(sum, pumWeight(d, rinv));
+      ++cnt;
+    }
+  });
+  wsum[v]   = sum;
+  wcount[v] = cnt;
+  if (cnt == 0)
+    atomicMin(firstUnassigned, static_cast<int>(v));
+}
+
+} // namespace
+
+// =============================================================================================
+void PumClustering::tagEmpty(const BinGrid &mesh, cudaStream_t s)
+{
+  tagEmptyKernel<<<warpGrid(total), kBlockThreads, 0, s>>>(centers.p, tag.p, total, mesh.view(), radius);
+  RBF_LAUNCHED();
+}
+
+void PumClustering::project(const BinGrid &inMesh, cudaStream_t s)
+{
+  projectKernel<<<warpGrid(total), kBlockThreads, 0, s>>>(centers.p, tag.p, total, inMesh.view());
+  RBF_LAUNCHED();
+}
+
+void PumClustering::tagDuplicates(const NeighbourOffsets &offs, double threshold, cudaStream_t s)
+{
+  DevBuf<int>      state, undecided;
+  DevBuf<unsigned> low;
+  state.alloc(total);
+  low.alloc(total);
+  undecided.alloc(1);
+  const int grid = divUp(total, 256);
+  // CreateClustering.hpp:112: squared distance < pow_int<2>(radius)
+  dupInitKernel<<<grid, 256, 0, s>>>(centers.p, tag.p, total, offs, threshold * threshold, state.p, low.p);
+  RBF_LAUNCHED();
+  for (int64_t it = 0; it <= total; ++it) {
+    RBF_CUDA(cudaMemsetAsync(undecided.p, 0, sizeof(int), s));
+    dupResolveKernel<<<grid, 256, 0, s>>>(total, offs, state.p, low.p, undecided.p);
+    RBF_LAUNCHED();
+    int left = 0;
+    RBF_CUDA(cudaMemcpyAsync(&left, undecided.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    RBF_CUDA(cudaStreamSynchronize(s));
+    if (left == 0)
+      break;
+  }
+  stateToTagKernel<<<grid, 256, 0, s>>>(total, state.p, tag.p);
+  RBF_LAUNCHED();
+  RBF_CUDA(cudaStreamSynchronize(s));
+}
+
+int64_t PumClustering::compact(DevBuf<double> &out, cudaStream_t s)
+{
+  DevBuf<int> keep, pos;
+  keep.alloc(total);
+  pos.alloc(total + 1);
+  const int grid = divUp(total, 256);
+  keepFlagKernel<<<grid, 256, 0, s>>>(total, tag.p, keep.p);
+  RBF_LAUNCHED();
+  exclusiveScan(keep.p, pos.p, total, s);
+  int count = 0;
+  RBF_CUDA(cudaMemcpyAsync(&count, pos.p + total, sizeof(int), cudaMemcpyDeviceToHost, s));
+  RBF_CUDA(cudaStreamSynchronize(s));
+  out.alloc(3 * static_cast<size_t>(std::max(count, 1)));
+  if (count > 0) {
+    compactKernel<<<grid, 256, 0, s>>>(total, tag.p, pos.p, centers.p, out.p);
+    RBF_LAUNCHED();
+  }
+  RBF_CUDA(cudaStreamSynchronize(s));
+  return count;
+}
+
+void pumBuildMembership(const double *dCenters, int64_t nClusters, const BinGrid &inMesh, const BinGrid &outMesh, double radius, PumMembership &m, cudaStream_t s)
+{
+  const double rOut = radius - kZeroDiff; // SphericalVertexCluster.hpp:155
+  DevBuf<int>  nIn, nOut;
+  nIn.alloc(nClusters);
+  nOut.alloc(nClusters);
+  m.tri.alloc(nClusters);
+  m.inOff.alloc(nClusters + 1);
+  m.outOff.alloc(nClusters + 1);
+  m.matOff.alloc(nClusters + 1);
+  m.nIn.alloc(nClusters);
+  m.nOut.alloc(nClusters);
+  memberCountKernel<<<warpGrid(nClusters), kBlockThreads, 0, s>>>(dCenters, nClusters, inMesh.view(), outMesh.view(), radius, rOut, m.nIn.p, m.nOut.p,
+                                                                 reinterpret_cast<long long *>(m.tri.p));
+  RBF_LAUNCHED();
+  exclusiveScan(m.nIn.p, m.inOff.p, nClusters, s);
+  exclusiveScan(m.nOut.p, m.outOff.p, nClusters, s);
+  exclusiveScan(m.tri.p, m.matOff.p, nClusters, s);
+  int64_t totals[3];
+  RBF_CUDA(cudaMemcpyAsync(&totals[0], m.inOff.p + nClusters, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  RBF_CUDA(cudaMemcpyAsync(&totals[1], m.outOff.p + nClusters, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  RBF_CUDA(cudaMemcpyAsync(&totals[2], m.matOff.p + nClusters, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  RBF_CUDA(cudaStreamSynchronize(s));
+  m.sumIn  = totals[0];
+  m.sumOut = totals[1];
+  m.sumTri = totals[2];
+  m.inIds.alloc(std::max<int64_t>(m.sumIn, 1));
+  m.outIds.alloc(std::max<int64_t>(m.sumOut, 1));
+  memberFillKernel<<<warpGrid(nClusters), kBlockThreads, 0, s>>>(dCenters, nClusters, inMesh.view(), outMesh.view(), radius, rOut,
+                                                                reinterpret_cast<const long long *>(m.inOff.p), reinterpret_cast<const long long *>(m.outOff.p),
+                                                                m.inIds.p, m.outIds.p);
+  RBF_LAUNCHED();
+  RBF_CUDA(cudaGetLastError());
+}
+
+int64_t pumWeightSums(const double *dOutXyz, int64_t nOut, const BinGrid &centerGrid, double radius, double *wsum, int *wcount, cudaStream_t s)
+{
+  DevBuf<int> first;
+  first.alloc(1);
+  RBF_CUDA(cudaMemsetAsync(first.p, 0x7f, sizeof(int), s));
+  if (nOut > 0) {
+    weightSumKernel<<<divUp(nOut, 256), 256, 0, s>>>(dOutXyz, nOut, centerGrid.view(), radius, 1.0 / radius, wsum, wcount, first.p);
+    RBF_LAUNCHED();
+  }
+  int f = 0;
+  RBF_CUDA(cudaMemcpyAsync(&f, first.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  RBF_CUDA(cudaStreamSynchronize(s));
+  return f == 0x7f7f7f7f ? -1 : f;
+}
+
+} // namespace rbfmap

@@ -1,0 +1,329 @@
+// spatial.cu — device implementations of the neighbour-search primitives declared in spatial.cuh.
+#include "spatial.cuh"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+namespace rbfmap {
+namespace {
+
+constexpr int kBlock = 256;
+
+inline int gridFor(int64_t n, int perThread = 1)
+{
+  const int64_t want = (n + static_cast<int64_t>(kBlock) * perThread - 1) / (static_cast<int64_t>(kBlock) * perThread);
+  const int64_t cap  = static_cast<int64_t>(smCount()) * 16; // grid-stride loops; a multiple of the SM count
+  return static_cast<int>(std::max<int64_t>(1, std::min(want, cap)));
+}
+
+// ------------------------------------------------------------------ bounds
+__global__ void boundsKernel(const double *__restrict__ xyz, int64_t n, unsigned long long *__restrict__ keys /*6: min xyz, max xyz*/)
+{
+  double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const double v = xyz[3 * i + d];
+      lo[d]          = fmin(lo[d], v);
+      hi[d]          = fmax(hi[d], v);
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[d] = fmin(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+      hi[d] = fmax(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      atomicMin(&keys[d], encodeOrdered(lo[d]));
+      atomicMax(&keys[3 + d], encodeOrdered(hi[d]));
+    }
+  }
+}
+
+// ------------------------------------------------------------------ nearest vertex to a few probe points
+constexpr int kMaxProbes = 8;
+struct Probes {
+  double x[kMaxProbes], y[kMaxProbes], z[kMaxProbes];
+  double r2[kMaxProbes]; // per-probe squared search radius (collectWithinKernel); negative = skip
+  int    n;
+};
+
+__global__ void probeMinDistKernel(const double *__restrict__ xyz, int64_t n, Probes pr, unsigned long long *__restrict__ best)
+{
+  double b[kMaxProbes];
+#pragma unroll
+  for (int p = 0; p < kMaxProbes; ++p)
+    b[p] = DBL_MAX;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+#pragma unroll
+    for (int p = 0; p < kMaxProbes; ++p)
+      if (p < pr.n)
+        b[p] = fmin(b[p], sqDist3(pr.x[p], pr.y[p], pr.z[p], x, y, z));
+  }
+#pragma unroll
+  for (int p = 0; p < kMaxProbes; ++p) {
+    if (p < pr.n) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+        b[p] = fmin(b[p], __shfl_xor_sync(0xffffffffu, b[p], o));
+      if ((threadIdx.x & 31) == 0)
+        atomicMin(&best[p], encodeOrdered(b[p]));
+    }
+  }
+}
+
+__global__ void probeArgMinKernel(const double *__restrict__ xyz, int64_t n, Probes pr, const unsigned long long *__restrict__ best, int *__restrict__ ids)
+{
+  double b[kMaxProbes];
+#pragma unroll
+  for (int p = 0; p < kMaxProbes; ++p)
+    b[p] = p < pr.n ? decodeOrdered(best[p]) : 0.0;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+#pragma unroll
+    for (int p = 0; p < kMaxProbes; ++p)
+      if (p < pr.n && sqDist3(pr.x[p], pr.y[p], pr.z[p], x, y, z) == b[p])
+        atomicMin(&ids[p], static_cast<int>(i));
+  }
+}
+
+// ------------------------------------------------------------------ k-th neighbour distance
+__global__ void collectWithinKernel(const double *__restrict__ xyz, int64_t n, Probes pr, double *__restrict__ cand, int cap, int *__restrict__ counts)
+{
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+#pragma unroll
+    for (int p = 0; p < kMaxProbes; ++p)
+      if (p < pr.n) {
+        // RadialBasisFctSolver.hpp:102-113 argument order: (mesh vertex, sample vertex)
+        const double d2 = sqDist3(x, y, z, pr.x[p], pr.y[p], pr.z[p]);
+        if (d2 <= pr.r2[p]) {
+          const int slot = atomicAdd(&counts[p], 1);
+          if (slot < cap)
+            cand[static_cast<size_t>(p) * cap + slot] = d2;
+        }
+      }
+  }
+}
+
+// ------------------------------------------------------------------ binning
+__global__ void binCountKernel(const double *__restrict__ xyz, int64_t n, BinGridView g, int *__restrict__ cellOf, int *__restrict__ counts)
+{
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    int cx = cellCoordUnclamped(xyz[3 * i], g.ox, g.ihx, g.nx);
+    int cy = cellCoordUnclamped(xyz[3 * i + 1], g.oy, g.ihy, g.ny);
+    int cz = cellCoordUnclamped(xyz[3 * i + 2], g.oz, g.ihz, g.nz);
+    cx     = min(max(cx, 0), g.nx - 1);
+    cy     = min(max(cy, 0), g.ny - 1);
+    cz     = min(max(cz, 0), g.nz - 1);
+    const int c = (cx * g.ny + cy) * g.nz + cz;
+    cellOf[i]   = c;
+    atomicAdd(&counts[c], 1);
+  }
+}
+
+__global__ void binScatterKernel(int64_t n, const int *__restrict__ cellOf, const int *__restrict__ cellStart, int *__restrict__ cursor, int *__restrict__ ids)
+{
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c               = cellOf[i];
+    const int slot            = atomicAdd(&cursor[c], 1);
+    ids[cellStart[c] + slot]  = static_cast<int>(i);
+  }
+}
+
+// ascending vertex IDs inside every cell -> the binned order is deterministic
+__global__ void binSortCellsKernel(int64_t nCells, const int *__restrict__ cellStart, int *__restrict__ ids)
+{
+  for (int64_t c = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; c < nCells; c += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int beg = cellStart[c], end = cellStart[c + 1];
+    for (int a = beg + 1; a < end; ++a) {
+      const int v = ids[a];
+      int       b = a - 1;
+      while (b >= beg && ids[b] > v) {
+        ids[b + 1] = ids[b];
+        --b;
+      }
+      ids[b + 1] = v;
+    }
+  }
+}
+
+__global__ void binGatherKernel(const double *__restrict__ xyz, int64_t n, const int *__restrict__ ids, double *__restrict__ binned)
+{
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t v   = ids[i];
+    binned[3 * i]     = xyz[3 * v];
+    binned[3 * i + 1] = xyz[3 * v + 1];
+    binned[3 * i + 2] = xyz[3 * v + 2];
+  }
+}
+
+Probes makeProbes(const double *pts, int nProbes)
+{
+  if (nProbes > kMaxProbes)
+    throw MapError(RBFMAP_ERR_INVALID, "too many probe points");
+  Probes pr{};
+  pr.n = nProbes;
+  for (int p = 0; p < nProbes; ++p) {
+    pr.x[p] = pts[3 * p];
+    pr.y[p] = pts[3 * p + 1];
+    pr.z[p] = pts[3 * p + 2];
+  }
+  return pr;
+}
+
+} // namespace
+
+void computeBounds(const double *dXyz, int64_t n, double bbMin[3], double bbMax[3], cudaStream_t s)
+{
+  DevBuf<unsigned long long> keys;
+  keys.alloc(6);
+  unsigned long long init[6];
+  for (int d = 0; d < 3; ++d) {
+    init[d]     = ~0ull;
+    init[3 + d] = 0ull;
+  }
+  RBF_CUDA(cudaMemcpyAsync(keys.p, init, sizeof(init), cudaMemcpyHostToDevice, s));
+  boundsKernel<<<gridFor(n, 4), kBlock, 0, s>>>(dXyz, n, keys.p);
+  RBF_LAUNCHED();
+  unsigned long long out[6];
+  RBF_CUDA(cudaMemcpyAsync(out, keys.p, sizeof(out), cudaMemcpyDeviceToHost, s));
+  RBF_CUDA(cudaStreamSynchronize(s));
+  for (int d = 0; d < 3; ++d) {
+    bbMin[d] = decodeOrdered(out[d]);
+    bbMax[d] = decodeOrdered(out[3 + d]);
+  }
+}
+
+void nearestVertices(const double *dXyz, int64_t n, const double *probes, int nProbes, int *nearestIds, cudaStream_t s)
+{
+  const Probes               pr = makeProbes(probes, nProbes);
+  DevBuf<unsigned long long> best;
+  DevBuf<int>                ids;
+  best.alloc(kMaxProbes);
+  ids.alloc(kMaxProbes);
+  RBF_CUDA(cudaMemsetAsync(best.p, 0xff, kMaxProbes * sizeof(unsigned long long), s));
+  RBF_CUDA(cudaMemsetAsync(ids.p, 0x7f, kMaxProbes * sizeof(int), s));
+  probeMinDistKernel<<<gridFor(n, 4), kBlock, 0, s>>>(dXyz, n, pr, best.p);
+  RBF_LAUNCHED();
+  probeArgMinKernel<<<gridFor(n, 4), kBlock, 0, s>>>(dXyz, n, pr, best.p, ids.p);
+  RBF_LAUNCHED();
+  RBF_CUDA(cudaMemcpyAsync(nearestIds, ids.p, nProbes * sizeof(int), cudaMemcpyDeviceToHost, s));
+  RBF_CUDA(cudaStreamSynchronize(s));
+}
+
+void kthNeighbourDistance(const double *dXyz, int64_t n, const int *probeIds, int nProbes, int k, double guess, double *result, cudaStream_t s)
+{
+  k = static_cast<int>(std::min<int64_t>(k, n));
+  if (k < 1)
+    throw MapError(RBFMAP_ERR_INVALID, "vertices-per-cluster has to be greater zero.");
+  // coordinates of the probe vertices
+  std::vector<double> pts(3 * static_cast<size_t>(nProbes));
+  for (int p = 0; p < nProbes; ++p)
+    RBF_CUDA(cudaMemcpyAsync(&pts[3 * p], dXyz + 3 * static_cast<int64_t>(probeIds[p]), 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  RBF_CUDA(cudaStreamSynchronize(s));
+  Probes pr = makeProbes(pts.data(), nProbes);
+
+  const int      cap = std::max(4096, 8 * k);
+  DevBuf<double> cand;
+  DevBuf<int>    counts;
+  cand.alloc(static_cast<size_t>(kMaxProbes) * cap);
+  counts.alloc(kMaxProbes);
+  std::vector<double> host(static_cast<size_t>(cap));
+  std::vector<char>   done(nProbes, 0);
+  // every probe searches with its own radius: grow while fewer than k vertices are inside, shrink (bisect) when the
+  // candidate buffer overflows
+  std::vector<double> radius(nProbes, guess > 0 && std::isfinite(guess) ? guess : 1.0), lo(nProbes, 0.0),
+      hi(nProbes, std::numeric_limits<double>::infinity());
+  int nDone = 0;
+  for (int iter = 0; iter < 400 && nDone < nProbes; ++iter) {
+    for (int p = 0; p < nProbes; ++p)
+      pr.r2[p] = done[p] ? -1.0 : radius[p] * radius[p];
+    RBF_CUDA(cudaMemsetAsync(counts.p, 0, kMaxProbes * sizeof(int), s));
+    collectWithinKernel<<<gridFor(n, 4), kBlock, 0, s>>>(dXyz, n, pr, cand.p, cap, counts.p);
+    RBF_LAUNCHED();
+    int cnt[kMaxProbes];
+    RBF_CUDA(cudaMemcpyAsync(cnt, counts.p, sizeof(cnt), cudaMemcpyDeviceToHost, s));
+    RBF_CUDA(cudaStreamSynchronize(s));
+    for (int p = 0; p < nProbes; ++p) {
+      if (done[p])
+        continue;
+      if (cnt[p] > cap) {
+        hi[p]     = radius[p];
+        radius[p] = lo[p] > 0 ? 0.5 * (lo[p] + hi[p]) : 0.5 * radius[p];
+      } else if (cnt[p] < k) {
+        lo[p]     = radius[p];
+        radius[p] = std::isfinite(hi[p]) ? 0.5 * (lo[p] + hi[p]) : 2.0 * radius[p];
+      } else {
+        RBF_CUDA(cudaMemcpy(host.data(), cand.p + static_cast<size_t>(p) * cap, cnt[p] * sizeof(double), cudaMemcpyDeviceToHost));
+        std::nth_element(host.begin(), host.begin() + (k - 1), host.begin() + cnt[p]);
+        result[p] = std::sqrt(host[k - 1]);
+        done[p]   = 1;
+        ++nDone;
+      }
+    }
+  }
+  if (nDone < nProbes)
+    throw MapError(RBFMAP_ERR_INVALID, "cluster radius estimation did not converge");
+}
+
+void BinGrid::build(const double *dXyz, int64_t nPts, const double bbMin[3], const double bbMax[3], double minCell, cudaStream_t s)
+{
+  n = nPts;
+  // cell edge slightly above the query radius so that the 3x3x3 neighbourhood is conservative under rounding
+  double cell = minCell * (1.0 + 1e-9);
+  if (!(cell > 0) || !std::isfinite(cell))
+    cell = 1.0;
+  const double  capCells = static_cast<double>(std::min<int64_t>(std::max<int64_t>(8 * nPts, 1 << 20), int64_t(1) << 27));
+  for (int it = 0; it < 200; ++it) {
+    double total = 1.0;
+    for (int d = 0; d < 3; ++d) {
+      const double e  = std::max(0.0, bbMax[d] - bbMin[d]);
+      const double c  = std::floor(e / cell) + 1.0;
+      dims[d]         = static_cast<int>(std::min(c, 2097152.0));
+      total *= static_cast<double>(dims[d]);
+    }
+    if (total <= capCells)
+      break;
+    cell *= 1.26;
+  }
+  for (int d = 0; d < 3; ++d) {
+    origin[d] = bbMin[d];
+    h[d]      = cell;
+  }
+  const int64_t nCells = static_cast<int64_t>(dims[0]) * dims[1] * dims[2];
+  cellStart.alloc(nCells + 1);
+  ids.alloc(std::max<int64_t>(nPts, 1));
+  xyz.alloc(3 * std::max<int64_t>(nPts, 1));
+  DevBuf<int> cellOf, counts;
+  cellOf.alloc(std::max<int64_t>(nPts, 1));
+  counts.alloc(nCells);
+  RBF_CUDA(cudaMemsetAsync(counts.p, 0, nCells * sizeof(int), s));
+  const BinGridView g = view();
+  if (nPts > 0) {
+    binCountKernel<<<gridFor(nPts), kBlock, 0, s>>>(dXyz, nPts, g, cellOf.p, counts.p);
+    RBF_LAUNCHED();
+  }
+  exclusiveScan(counts.p, cellStart.p, nCells, s);
+  if (nPts > 0) {
+    RBF_CUDA(cudaMemsetAsync(counts.p, 0, nCells * sizeof(int), s));
+    binScatterKernel<<<gridFor(nPts), kBlock, 0, s>>>(nPts, cellOf.p, cellStart.p, counts.p, ids.p);
+    RBF_LAUNCHED();
+    binSortCellsKernel<<<gridFor(nCells), kBlock, 0, s>>>(nCells, cellStart.p, ids.p);
+    RBF_LAUNCHED();
+    binGatherKernel<<<gridFor(nPts), kBlock, 0, s>>>(dXyz, nPts, ids.p, xyz.p);
+    RBF_LAUNCHED();
+  }
+  RBF_CUDA(cudaGetLastError());
+  RBF_CUDA(cudaStreamSynchronize(s)); // temporaries go out of scope
+}
+
+} // namespace rbfmap
