@@ -259,6 +259,29 @@ def pum_time(constraint, dim, basis, param, polynomial, vpc, overlap, project, i
     return t[0], t[1], out, ncl.value
 
 
-__all__ = ["BASIS", "POLYNOMIAL", "CONSTRAINT", "OracleError", "build", "lib", "as_xyz", "basis_eval", "basis_params",
+def pum_time_ranks(constraint, dim, basis, param, polynomial, vpc, overlap, project, in_parts, out_parts, val_parts, dims):
+    """One independent computeMapping + map per partition, each on its own host thread (one preCICE rank per core).
+    Returns (t_compute, t_map, [out per partition], n_clusters)."""
+    ins = [as_xyz(a) for a in in_parts]
+    outs = [as_xyz(a) for a in out_parts]
+    a, b = np.ascontiguousarray(np.concatenate(ins)), np.ascontiguousarray(np.concatenate(outs))
+    v = np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=np.float64).reshape(-1) for x in val_parts]))
+    in_off = np.zeros(len(ins) + 1, dtype=np.int64)
+    out_off = np.zeros(len(outs) + 1, dtype=np.int64)
+    in_off[1:] = np.cumsum([x.shape[0] for x in ins])
+    out_off[1:] = np.cumsum([x.shape[0] for x in outs])
+    out = np.zeros(b.shape[0] * dims)
+    t = np.zeros(2)
+    ncl = C.c_longlong(0)
+    _check(lib().orc_pum_time_ranks(C.c_int(CONSTRAINT[constraint]), C.c_int(dim), C.c_int(BASIS[basis]), C.c_double(param),
+                                    C.c_int(POLYNOMIAL[polynomial]), C.c_uint(vpc), C.c_double(overlap), C.c_int(int(project)),
+                                    _dp(a), in_off.ctypes.data_as(C.POINTER(C.c_longlong)), _dp(b),
+                                    out_off.ctypes.data_as(C.POINTER(C.c_longlong)), _dp(v), C.c_int(dims), _dp(out),
+                                    C.c_int(len(ins)), _dp(t), C.byref(ncl)))
+    res = [out[out_off[r] * dims:out_off[r + 1] * dims] for r in range(len(ins))]
+    return t[0], t[1], res, ncl.value
+
+
+__all__ = ["pum_time_ranks", "BASIS", "POLYNOMIAL", "CONSTRAINT", "OracleError", "build", "lib", "as_xyz", "basis_eval", "basis_params",
            "create_clustering", "PumMapping", "GlobalMapping", "cholesky", "qr_solve", "singular_values", "pum_time"]
 _ = math

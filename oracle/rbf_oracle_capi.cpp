@@ -198,4 +198,46 @@ int orc_pum_time(int constraint, int dim, int basis, double param, int polynomia
   });
 }
 
+// ---- CPU-N baseline: `ranks` independent mappings, one per host thread, like one preCICE rank per core (each rank
+// clusters and maps its own partition without communication, BatchedRBFSolver.hpp:29-31). Partition r uses the
+// vertices [inOff[r], inOff[r+1]) / [outOff[r], outOff[r+1]). t[0] = wall seconds of the slowest rank for
+// computeMapping, t[1] for map.
+int orc_pum_time_ranks(int constraint, int dim, int basis, double param, int polynomial, unsigned vpc, double overlap, int project,
+                       const double *inXYZ, const long long *inOff, const double *outXYZ, const long long *outOff, const double *in, int dims,
+                       double *out, int ranks, double *t, long long *nClusters)
+{
+  return guarded([&] {
+    std::vector<double>      tc(ranks, 0.0), tm(ranks, 0.0);
+    std::vector<long long>   ncl(ranks, 0);
+    std::vector<std::string> errors(ranks);
+    std::vector<std::thread> pool;
+    for (int r = 0; r < ranks; ++r)
+      pool.emplace_back([&, r]() {
+        try {
+          orc::PumMapping m(static_cast<orc::Constraint>(constraint), dim, makeRbf(basis, param, std::numeric_limits<double>::infinity()),
+                            static_cast<orc::Polynomial>(polynomial), vpc, overlap, project != 0);
+          const int  nIn = static_cast<int>(inOff[r + 1] - inOff[r]), nOut = static_cast<int>(outOff[r + 1] - outOff[r]);
+          const auto t0 = std::chrono::steady_clock::now();
+          m.computeMapping(inXYZ + 3 * inOff[r], nIn, outXYZ + 3 * outOff[r], nOut, 1);
+          const auto t1 = std::chrono::steady_clock::now();
+          m.map(in + inOff[r] * dims, dims, out + outOff[r] * dims, 1);
+          const auto t2 = std::chrono::steady_clock::now();
+          tc[r]         = std::chrono::duration<double>(t1 - t0).count();
+          tm[r]         = std::chrono::duration<double>(t2 - t1).count();
+          ncl[r]        = static_cast<long long>(m.clusters().size());
+        } catch (const std::exception &e) {
+          errors[r] = e.what();
+        }
+      });
+    for (auto &th : pool)
+      th.join();
+    for (auto &e : errors)
+      if (!e.empty())
+        throw orc::Error(e);
+    t[0]       = *std::max_element(tc.begin(), tc.end());
+    t[1]       = *std::max_element(tm.begin(), tm.end());
+    *nClusters = std::accumulate(ncl.begin(), ncl.end(), 0LL);
+  });
+}
+
 } // extern "C"

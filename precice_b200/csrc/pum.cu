@@ -163,6 +163,10 @@ void PumMapping::computeMapping(const double *dInputXyz, int64_t nInput, const d
   if (_computed)
     throw MapError(RBFMAP_ERR_STATE, "Please clear the mapping before recomputing."); // PartitionOfUnityMapping.hpp:188
   g_launches = 0;
+  for (int k = 0; k < 3; ++k) {
+    _listCount[k] = 0;
+    _listMaxN[k]  = 0;
+  }
   EventTimer whole(_stream);
   whole.start();
   _nInput  = nInput;
@@ -297,6 +301,9 @@ void PumMapping::computeMapping(const double *dInputXyz, int64_t nInput, const d
     if (_nClusters == 0)
       throw MapError(RBFMAP_ERR_EMPTY, "Too many vertices have been filtered out."); // :502
   }
+
+  stats.n_clusters     = _nClusters;
+  stats.cluster_radius = _radius;
 
   // per-cluster vertex sets (SphericalVertexCluster.hpp:153-162)
   pumBuildMembership(_centers.p, _nClusters, inGrid, outGrid, _radius, _mem, _stream);

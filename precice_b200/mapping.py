@@ -85,6 +85,8 @@ class _Mapping:
         self._check(self._L.rbfmap_compute_mapping(self._h, a.ctypes.data, a.shape[0], b.ctypes.data, b.shape[0]))
 
     def _map(self, fn_host, values, dims, out=None):
+        if not self.hasComputedMapping():
+            self._check(fn_host(self._h, None, dims, None))  # -> RBFMAP_ERR_STATE with the library's message
         if _is_torch(values):
             import torch
             v = values.contiguous()
