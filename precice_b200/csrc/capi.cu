@@ -3,7 +3,9 @@
 #include "pum.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <limits>
 #include <mutex>
 
@@ -113,6 +115,32 @@ DeviceMapping::~DeviceMapping()
 {
   if (_stream)
     cudaStreamDestroy(_stream);
+}
+
+double PhaseTrace::now()
+{
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+PhaseTrace::PhaseTrace(const char *what_, cudaStream_t stream)
+    : s(stream), what(what_)
+{
+  const char *e = getenv("RBFMAP_TRACE");
+  on            = e && e[0] == '1';
+  if (on) {
+    cudaStreamSynchronize(s);
+    t0 = now();
+  }
+}
+void PhaseTrace::phase(const char *name)
+{
+  if (!on)
+    return;
+  cudaStreamSynchronize(s);
+  const double t = now();
+  fprintf(stderr, "[rbfmap trace] %s: %-28s %9.3f ms\n", what, name, t - t0);
+  t0 = t;
 }
 
 bool pumInspect(DeviceMapping *m, int64_t &nClusters, const double *&centers, const PumMembership *&mem);

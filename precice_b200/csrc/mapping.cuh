@@ -43,6 +43,18 @@ std::unique_ptr<DeviceMapping> makePumMapping(const rbfmap_config &cfg);
 std::unique_ptr<DeviceMapping> makeGlobalDirectMapping(const rbfmap_config &cfg);
 std::unique_ptr<DeviceMapping> makeGlobalIterativeMapping(const rbfmap_config &cfg);
 
+// Phase tracing for development: RBFMAP_TRACE=1 prints the wall time of every phase of computeMapping/map to stderr
+// (a stream synchronisation is inserted at each phase boundary, so traced runs are slower than untraced ones).
+struct PhaseTrace {
+  bool         on;
+  cudaStream_t s;
+  double       t0;
+  const char  *what;
+  static double now();
+  PhaseTrace(const char *what_, cudaStream_t stream);
+  void phase(const char *name);
+};
+
 // simple CUDA-event stopwatch on a stream
 struct EventTimer {
   cudaEvent_t  a = nullptr, b = nullptr;

@@ -169,6 +169,7 @@ void PumMapping::computeMapping(const double *dInputXyz, int64_t nInput, const d
   }
   EventTimer whole(_stream);
   whole.start();
+  PhaseTrace trace("pum.computeMapping", _stream);
   _nInput  = nInput;
   _nOutput = nOutput;
   // PartitionOfUnityMapping.hpp:190-198
@@ -201,6 +202,7 @@ void PumMapping::computeMapping(const double *dInputXyz, int64_t nInput, const d
   double    bbMin[3], bbMax[3], obMin[3], obMax[3];
   computeBounds(_inXyz.p, _nIn, bbMin, bbMax, _stream); // :334 (bounds of the inMesh)
   computeBounds(_outXyz.p, _nOut, obMin, obMax, _stream);
+  trace.phase("copy + bounds");
   auto edge = [&](int d) { return std::abs(bbMax[d] - bbMin[d]); };
 
   BinGrid inGrid, outGrid;
@@ -223,6 +225,7 @@ void PumMapping::computeMapping(const double *dInputXyz, int64_t nInput, const d
     outGrid.build(_outXyz.p, _nOut, obMin, obMax, _radius, _stream);
   } else {
     _radius = estimateClusterRadius(bbMin, bbMax);
+    trace.phase("estimateClusterRadius");
     if (!(_radius > 0.0))
       throw MapError(RBFMAP_ERR_SINGULAR, "rbf-pum-direct: the estimated cluster radius is zero (duplicated vertices?).");
     // :366-427 lattice of tentative centres
@@ -276,14 +279,18 @@ void PumMapping::computeMapping(const double *dInputXyz, int64_t nInput, const d
     latticeKernel<<<divUp(cl.total, 256), 256, 0, _stream>>>(dAxis[0].p, dAxis[1].p, dAxis[2].p, nLocal[0], nLocal[1], nLocal[2], cl.centers.p, cl.tag.p);
     RBF_LAUNCHED();
 
+    trace.phase("lattice");
     inGrid.build(_inXyz.p, _nIn, bbMin, bbMax, _radius, _stream);
     outGrid.build(_outXyz.p, _nOut, obMin, obMax, _radius, _stream);
+    trace.phase("bin meshes");
 
     // :468-471
     cl.tagEmpty(inGrid, _stream);
     cl.tagEmpty(outGrid, _stream);
+    trace.phase("tagEmpty x2");
     if (_cfg.project_to_input) { // :475-496
       cl.project(inGrid, _stream);
+      trace.phase("project");
       const double     threshold = 0.4 * (*std::min_element(distances.begin(), distances.end()));
       NeighbourOffsets offs{};
       const bool       twoD = nLocal[2] == 1;
@@ -295,9 +302,12 @@ void PumMapping::computeMapping(const double *dInputXyz, int64_t nInput, const d
             offs.off[offs.n++] = (static_cast<long long>(dx) * nLocal[1] + dy) * static_cast<long long>(nLocal[2]) + dz;
           }
       cl.tagDuplicates(offs, threshold, _stream);
+      trace.phase("tagDuplicates");
       cl.tagEmpty(outGrid, _stream);
+      trace.phase("tagEmpty");
     }
     _nClusters = cl.compact(_centers, _stream);
+    trace.phase("compact");
     if (_nClusters == 0)
       throw MapError(RBFMAP_ERR_EMPTY, "Too many vertices have been filtered out."); // :502
   }
@@ -307,6 +317,7 @@ void PumMapping::computeMapping(const double *dInputXyz, int64_t nInput, const d
 
   // per-cluster vertex sets (SphericalVertexCluster.hpp:153-162)
   pumBuildMembership(_centers.p, _nClusters, inGrid, outGrid, _radius, _mem, _stream);
+  trace.phase("membership");
 
   // partition-of-unity weight sums (PartitionOfUnityMapping.hpp:263-276, 290-341)
   {
@@ -334,6 +345,7 @@ void PumMapping::computeMapping(const double *dInputXyz, int64_t nInput, const d
     }
   }
 
+  trace.phase("weights");
   // size classes + statistics (host pass over the per-cluster counts)
   std::vector<int> hIn(_nClusters), hOut(_nClusters);
   RBF_CUDA(cudaMemcpyAsync(hIn.data(), _mem.nIn.p, _nClusters * sizeof(int), cudaMemcpyDeviceToHost, _stream));
@@ -362,11 +374,14 @@ void PumMapping::computeMapping(const double *dInputXyz, int64_t nInput, const d
   stats.n_clusters     = _nClusters;
   stats.cluster_radius = _radius;
 
+  trace.phase("classes (host)");
   // separated polynomial + assembly/factorisation of all local systems
   _poly.alloc(_nClusters);
   _mat.alloc(std::max<int64_t>(_mem.sumTri, 1));
   const PumSolveArgs args = solveArgs();
+  trace.phase("alloc factors");
   pumPolySetup(args, _nClusters, _cfg.polynomial, _stream);
+  trace.phase("polySetup");
   DevBuf<int> fail;
   fail.alloc(1);
   const int noFail = INT_MAX;
@@ -377,6 +392,7 @@ void PumMapping::computeMapping(const double *dInputXyz, int64_t nInput, const d
   for (int k = 0; k < 3; ++k)
     pumFactor(args, _lists[k].p, _listCount[k], classes[k], _listMaxN[k], fail.p, _stream);
   stats.ms_assembly_factor = tf.stop();
+  trace.phase("assembly + factorisation");
   int failed = INT_MAX;
   RBF_CUDA(cudaMemcpy(&failed, fail.p, sizeof(int), cudaMemcpyDeviceToHost));
   if (failed != INT_MAX) {
