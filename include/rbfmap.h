@@ -161,6 +161,9 @@ int rbfmap_pum_get_cluster_ids(const rbfmap_handle *h, int32_t *in_ids /* sum_n 
  * (mapping/impl/BasisFunctions.hpp) for bit-exact parity tests. */
 int rbfmap_eval_basis(int basis, double support_radius, double shape_parameter, const double *radii, int64_t n, double *values);
 
+/* Test hook: the branch-free square root the kernels apply to squared vertex distances (host pointers). */
+int rbfmap_debug_dist_sqrt(const double *x, int64_t n, double *out);
+
 /* Library / device probe: number of visible CUDA devices (0 if none), compute capability of device 0. */
 int rbfmap_device_count(void);
 int rbfmap_device_info(int device, int *sm_major, int *sm_minor, int *sm_count, int64_t *global_mem_bytes);

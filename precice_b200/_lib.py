@@ -31,7 +31,7 @@ EXPORTS = [
     "rbfmap_map_conservative", "rbfmap_compute_mapping_device", "rbfmap_map_device", "rbfmap_clear",
     "rbfmap_has_computed_mapping", "rbfmap_destroy", "rbfmap_get_name", "rbfmap_last_error", "rbfmap_get_stats",
     "rbfmap_pum_get_clusters", "rbfmap_pum_get_cluster_ids", "rbfmap_eval_basis", "rbfmap_device_count",
-    "rbfmap_device_info", "rbfmap_measure_fp64_peak",
+    "rbfmap_device_info", "rbfmap_measure_fp64_peak", "rbfmap_debug_dist_sqrt",
 ]
 
 
@@ -98,5 +98,6 @@ def lib():
         L.rbfmap_device_count.argtypes = []
         L.rbfmap_device_info.argtypes = [C.c_int, ip, ip, ip, C.POINTER(C.c_int64)]
         L.rbfmap_measure_fp64_peak.argtypes = [dp, dp]
+        L.rbfmap_debug_dist_sqrt.argtypes = [dp, C.c_int64, dp]
         _lib = L
     return _lib

@@ -109,6 +109,7 @@ DeviceMapping::DeviceMapping(const rbfmap_config &cfg)
     RBF_CUDA(cudaSetDevice(cfg.device_id));
   }
   RBF_CUDA(cudaStreamCreateWithFlags(&_stream, cudaStreamNonBlocking));
+  configureMemoryPool();
 }
 
 DeviceMapping::~DeviceMapping()
@@ -144,6 +145,7 @@ void PhaseTrace::phase(const char *name)
 }
 
 bool pumInspect(DeviceMapping *m, int64_t &nClusters, const double *&centers, const PumMembership *&mem);
+void debugDistSqrt(const double *dX, long long n, double *dOut);
 
 namespace {
 __global__ void evalBasisKernel(RbfParams f, const double *__restrict__ r, long long n, double *__restrict__ out)
@@ -241,7 +243,8 @@ int rbfmap_compute_mapping(rbfmap_handle *h, const double *input_xyz, int64_t n_
   return guarded(h, [&] {
     if (n_input < 0 || n_output < 0)
       throw MapError(RBFMAP_ERR_INVALID, "negative mesh size");
-    cudaStream_t s = h->impl->stream();
+    cudaStream_t     s = h->impl->stream();
+    AllocStreamScope allocScope(s);
     h->dInXyz.alloc(3 * std::max<int64_t>(n_input, 1));
     h->dOutXyz.alloc(3 * std::max<int64_t>(n_output, 1));
     if (n_input > 0)
@@ -277,8 +280,9 @@ static int mapHostImpl(rbfmap_handle *h, int mode, const double *in, int dims, d
       throw MapError(RBFMAP_ERR_STATE, "The mapping has not been computed; call computeMapping() first.");
     if (dims < 1)
       throw MapError(RBFMAP_ERR_INVALID, "data dimension has to be positive");
-    cudaStream_t  s    = m->stream();
-    const int64_t nIn  = m->nInput() * dims;
+    cudaStream_t     s = m->stream();
+    AllocStreamScope allocScope(s);
+    const int64_t    nIn  = m->nInput() * dims;
     const int64_t nOut = m->nOutput() * dims;
     if (h->dIn.n < static_cast<size_t>(std::max<int64_t>(nIn, 1)))
       h->dIn.alloc(std::max<int64_t>(nIn, 1));
@@ -312,7 +316,10 @@ int rbfmap_clear(rbfmap_handle *h)
 {
   if (!h)
     return RBFMAP_ERR_INVALID;
-  return guarded(h, [&] { h->impl->clear(); });
+  return guarded(h, [&] {
+    AllocStreamScope allocScope(h->impl->stream());
+    h->impl->clear();
+  });
 }
 
 int rbfmap_has_computed_mapping(const rbfmap_handle *h) { return h && h->impl->hasComputedMapping() ? 1 : 0; }
@@ -389,6 +396,21 @@ int rbfmap_eval_basis(int basis, double support_radius, double shape_parameter, 
     evalBasisKernel<<<divUp(n, 256), 256>>>(f, r.p, n, v.p);
     RBF_CUDA(cudaGetLastError());
     RBF_CUDA(cudaMemcpy(values, v.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+  });
+}
+
+int rbfmap_debug_dist_sqrt(const double *x, int64_t n, double *out)
+{
+  return guarded(nullptr, [&] {
+    if (n <= 0)
+      return;
+    DevBuf<double> a, b;
+    a.alloc(n);
+    b.alloc(n);
+    RBF_CUDA(cudaMemcpy(a.p, x, n * sizeof(double), cudaMemcpyHostToDevice));
+    debugDistSqrt(a.p, n, b.p);
+    RBF_CUDA(cudaDeviceSynchronize());
+    RBF_CUDA(cudaMemcpy(out, b.p, n * sizeof(double), cudaMemcpyDeviceToHost));
   });
 }
 

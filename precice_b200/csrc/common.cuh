@@ -30,16 +30,32 @@ struct MapError : std::runtime_error {
 // math/differences.hpp:8
 constexpr double kZeroDiff = 1.0e-14;
 
+// Stream on which DevBuf allocates and frees (stream-ordered, from the device's default memory pool whose release
+// threshold is raised so that freed blocks are reused by the next computeMapping instead of going back to the
+// driver). Set by the mapping objects for the duration of each call.
+extern thread_local cudaStream_t g_allocStream;
+void configureMemoryPool();
+struct AllocStreamScope {
+  cudaStream_t prev;
+  explicit AllocStreamScope(cudaStream_t s)
+      : prev(g_allocStream)
+  {
+    g_allocStream = s;
+  }
+  ~AllocStreamScope() { g_allocStream = prev; }
+};
+
 // Device buffer with stream-ordered allocation; owns its memory.
 template <typename T>
 struct DevBuf {
-  T     *p = nullptr;
-  size_t n = 0;
+  T           *p = nullptr;
+  size_t       n = 0;
+  cudaStream_t s = nullptr;
   DevBuf() = default;
   DevBuf(const DevBuf &)            = delete;
   DevBuf &operator=(const DevBuf &) = delete;
   DevBuf(DevBuf &&o) noexcept
-      : p(o.p), n(o.n)
+      : p(o.p), n(o.n), s(o.s)
   {
     o.p = nullptr;
     o.n = 0;
@@ -50,6 +66,7 @@ struct DevBuf {
       release();
       p   = o.p;
       n   = o.n;
+      s   = o.s;
       o.p = nullptr;
       o.n = 0;
     }
@@ -60,13 +77,14 @@ struct DevBuf {
   {
     release();
     n = count;
+    s = g_allocStream;
     if (count > 0)
-      RBF_CUDA(cudaMalloc(reinterpret_cast<void **>(&p), count * sizeof(T)));
+      RBF_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&p), count * sizeof(T), s));
   }
   void release()
   {
     if (p)
-      cudaFree(p);
+      cudaFreeAsync(p, s);
     p = nullptr;
     n = 0;
   }
@@ -112,7 +130,7 @@ __host__ __device__ __forceinline__ double decodeOrdered(unsigned long long k)
 __device__ __forceinline__ double sqDist3(double ax, double ay, double az, double bx, double by, double bz)
 {
   const double dx = __dsub_rn(ax, bx), dy = __dsub_rn(ay, by), dz = __dsub_rn(az, bz);
-  double       s  = __dadd_rn(0.0, __dmul_rn(dx, dx));
+  double       s  = __dmul_rn(dx, dx);
   s               = __dadd_rn(s, __dmul_rn(dy, dy));
   s               = __dadd_rn(s, __dmul_rn(dz, dz));
   return s;
@@ -121,7 +139,7 @@ __device__ __forceinline__ double sqDist3(double ax, double ay, double az, doubl
 __device__ __forceinline__ double sqDist3Masked(double ax, double ay, double az, double bx, double by, double bz, double mx, double my, double mz)
 {
   const double dx = __dmul_rn(__dsub_rn(ax, bx), mx), dy = __dmul_rn(__dsub_rn(ay, by), my), dz = __dmul_rn(__dsub_rn(az, bz), mz);
-  double       s  = __dadd_rn(0.0, __dmul_rn(dx, dx));
+  double       s  = __dmul_rn(dx, dx);
   s               = __dadd_rn(s, __dmul_rn(dy, dy));
   s               = __dadd_rn(s, __dmul_rn(dz, dz));
   return s;

@@ -66,8 +66,7 @@ public:
     _poly.release();
     _wsum.release();
     _wcount.release();
-    for (auto &l : _lists)
-      l.release();
+    _buckets.order.release();
     _nClusters = 0;
     _radius    = 0.0;
     _computed  = false;
@@ -94,9 +93,7 @@ private:
   DevBuf<PolyRec> _poly;
   DevBuf<double>  _wsum;
   DevBuf<int>     _wcount;
-  DevBuf<int>     _lists[3];
-  int64_t         _listCount[3] = {0, 0, 0};
-  int             _listMaxN[3]  = {0, 0, 0};
+  PumBuckets      _buckets;
 };
 
 PumSolveArgs PumMapping::solveArgs() const
@@ -163,11 +160,8 @@ void PumMapping::computeMapping(const double *dInputXyz, int64_t nInput, const d
   if (_computed)
     throw MapError(RBFMAP_ERR_STATE, "Please clear the mapping before recomputing."); // PartitionOfUnityMapping.hpp:188
   g_launches = 0;
-  for (int k = 0; k < 3; ++k) {
-    _listCount[k] = 0;
-    _listMaxN[k]  = 0;
-  }
-  EventTimer whole(_stream);
+  AllocStreamScope allocScope(_stream);
+  EventTimer       whole(_stream);
   whole.start();
   PhaseTrace trace("pum.computeMapping", _stream);
   _nInput  = nInput;
@@ -346,35 +340,11 @@ void PumMapping::computeMapping(const double *dInputXyz, int64_t nInput, const d
   }
 
   trace.phase("weights");
-  // size classes + statistics (host pass over the per-cluster counts)
-  std::vector<int> hIn(_nClusters), hOut(_nClusters);
-  RBF_CUDA(cudaMemcpyAsync(hIn.data(), _mem.nIn.p, _nClusters * sizeof(int), cudaMemcpyDeviceToHost, _stream));
-  RBF_CUDA(cudaMemcpyAsync(hOut.data(), _mem.nOut.p, _nClusters * sizeof(int), cudaMemcpyDeviceToHost, _stream));
-  RBF_CUDA(cudaStreamSynchronize(_stream));
-  std::vector<int> lists[3];
-  for (int64_t c = 0; c < _nClusters; ++c) {
-    const int64_t n = hIn[c], m = hOut[c];
-    stats.sum_n += n;
-    stats.sum_m += m;
-    stats.sum_n2 += n * n;
-    stats.sum_n3 += n * n * n;
-    stats.sum_mn += m * n;
-    stats.max_n = std::max<int64_t>(stats.max_n, n);
-    const int cls = n <= kClassSmall ? 0 : (n <= kClassMedium ? 1 : 2);
-    lists[cls].push_back(static_cast<int>(c));
-    _listMaxN[cls] = std::max<int>(_listMaxN[cls], static_cast<int>(n));
-  }
-  for (int k = 0; k < 3; ++k) {
-    _listCount[k] = static_cast<int64_t>(lists[k].size());
-    _lists[k].alloc(std::max<size_t>(lists[k].size(), 1));
-    if (!lists[k].empty())
-      RBF_CUDA(cudaMemcpyAsync(_lists[k].p, lists[k].data(), lists[k].size() * sizeof(int), cudaMemcpyHostToDevice, _stream));
-  }
-  RBF_CUDA(cudaStreamSynchronize(_stream));
+  // size buckets + statistics (device pass over the per-cluster counts)
+  pumClassify(_mem, _nClusters, _buckets, stats, _stream);
   stats.n_clusters     = _nClusters;
   stats.cluster_radius = _radius;
-
-  trace.phase("classes (host)");
+  trace.phase("classify");
   // separated polynomial + assembly/factorisation of all local systems
   _poly.alloc(_nClusters);
   _mat.alloc(std::max<int64_t>(_mem.sumTri, 1));
@@ -388,9 +358,7 @@ void PumMapping::computeMapping(const double *dInputXyz, int64_t nInput, const d
   RBF_CUDA(cudaMemcpyAsync(fail.p, &noFail, sizeof(int), cudaMemcpyHostToDevice, _stream));
   EventTimer tf(_stream);
   tf.start();
-  static const int classes[3] = {kClassSmall, kClassMedium, INT_MAX};
-  for (int k = 0; k < 3; ++k)
-    pumFactor(args, _lists[k].p, _listCount[k], classes[k], _listMaxN[k], fail.p, _stream);
+  pumFactor(args, _buckets, fail.p, _stream);
   stats.ms_assembly_factor = tf.stop();
   trace.phase("assembly + factorisation");
   int failed = INT_MAX;
@@ -415,22 +383,20 @@ void PumMapping::map(bool conservative, const double *dIn, int dims, double *dOu
     throw MapError(RBFMAP_ERR_STATE, "The mapping has not been computed; call computeMapping() first.");
   if (dims < 1)
     throw MapError(RBFMAP_ERR_INVALID, "data dimension has to be positive");
-  const int launchesBefore = g_launches;
-  EventTimer t(_stream);
+  const int        launchesBefore = g_launches;
+  AllocStreamScope allocScope(_stream);
+  EventTimer       t(_stream);
   t.start();
   // result lives on the solver-side outMesh (consistent) or inMesh (conservative)
   const int64_t nRes = conservative ? _nIn : _nOut;
   if (nRes > 0)
     RBF_CUDA(cudaMemsetAsync(dOut, 0, static_cast<size_t>(nRes) * dims * sizeof(double), _stream));
   if (_nClusters > 0) {
-    const PumSolveArgs args       = solveArgs();
-    static const int   classes[3] = {kClassSmall, kClassMedium, INT_MAX};
-    for (int k = 0; k < 3; ++k) {
-      if (conservative)
-        pumMapConservative(args, _lists[k].p, _listCount[k], classes[k], _listMaxN[k], dIn, dims, dOut, _stream);
-      else
-        pumMapConsistent(args, _lists[k].p, _listCount[k], classes[k], _listMaxN[k], dIn, dims, dOut, _stream);
-    }
+    const PumSolveArgs args = solveArgs();
+    if (conservative)
+      pumMapConservative(args, _buckets, dIn, dims, dOut, _stream);
+    else
+      pumMapConsistent(args, _buckets, dIn, dims, dOut, _stream);
   }
   stats.ms_map_kernels = t.stop();
   stats.kernel_launches += g_launches - launchesBefore;

@@ -69,15 +69,33 @@ struct PumSolveArgs {
   const int       *wcount;
 };
 
-// cluster size classes handled by different kernel instantiations
-constexpr int kClassSmall  = 64;  // n <= 64 : 8x8 threads, 8x8 register tile per thread
-constexpr int kClassMedium = 128; // n <= 128: 16x16 threads
-// larger clusters go through the global-memory kernels
+// Clusters are bucketed by size; every bucket is served by its own kernel instantiation:
+//   buckets 0..7  : n <= 64,  8x8 threads,  NB = ceil(n/8)  = 1..8 register blocks per thread and dimension
+//   buckets 8..11 : n <= 128, 16x16 threads, NB = ceil(n/16) = 5..8
+//   bucket  12    : larger clusters, global-memory kernels
+constexpr int    kNumBuckets = 13;
+constexpr size_t kPumMaxSmem = 200 * 1024;
+__host__ __device__ inline int pumBucketOf(int n)
+{
+  if (n <= 64)
+    return (max(n, 1) + 7) / 8 - 1;
+  if (n <= 128)
+    return 8 + (n + 15) / 16 - 5;
+  return 12;
+}
+struct PumBuckets {
+  DevBuf<int> order;                  // cluster indices sorted by bucket
+  int64_t     start[kNumBuckets + 1]; // offsets into `order`
+  int         maxN[kNumBuckets];      // largest cluster of each bucket
+};
+
+// device-side classification + statistics (fills stats.sum_* and stats.max_n)
+void pumClassify(const PumMembership &m, int64_t nClusters, PumBuckets &b, rbfmap_stats &stats, cudaStream_t s);
 
 void pumPolySetup(const PumSolveArgs &a, int64_t nClusters, int polynomial, cudaStream_t s);
-// `list` = device array of cluster indices of one class; fail = device int (first failing cluster or INT_MAX)
-void pumFactor(const PumSolveArgs &a, const int *list, int64_t count, int sizeClass, int maxN, int *fail, cudaStream_t s);
-void pumMapConsistent(const PumSolveArgs &a, const int *list, int64_t count, int sizeClass, int maxN, const double *in, int dims, double *out, cudaStream_t s);
-void pumMapConservative(const PumSolveArgs &a, const int *list, int64_t count, int sizeClass, int maxN, const double *in, int dims, double *out, cudaStream_t s);
+// fail = device int (lowest failing cluster index or INT_MAX)
+void pumFactor(const PumSolveArgs &a, const PumBuckets &b, int *fail, cudaStream_t s);
+void pumMapConsistent(const PumSolveArgs &a, const PumBuckets &b, const double *in, int dims, double *out, cudaStream_t s);
+void pumMapConservative(const PumSolveArgs &a, const PumBuckets &b, const double *in, int dims, double *out, cudaStream_t s);
 
 } // namespace rbfmap

@@ -296,6 +296,66 @@ __global__ void weightSumKernel(const double *__restrict__ outXyz, int64_t nOut,
     atomicMin(firstUnassigned, static_cast<int>(v));
 }
 
+// ---- size buckets + statistics ----------------------------------------------------------------
+// acc: [0..12] bucket counts, [13] sum n, [14] sum m, [15] sum n^2, [16] sum n^3, [17] sum m n, [18] max n, [19..31] max n per bucket
+__global__ void classifyKernel(const int *__restrict__ nIn, const int *__restrict__ nOut, int64_t nClusters, unsigned long long *__restrict__ acc)
+{
+  const int64_t c    = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int     lane = threadIdx.x & 31;
+  unsigned long long n = 0, m = 0;
+  int                b = -1;
+  if (c < nClusters) {
+    n = static_cast<unsigned long long>(nIn[c]);
+    m = static_cast<unsigned long long>(nOut[c]);
+    b = pumBucketOf(static_cast<int>(n));
+  }
+  unsigned long long v[5] = {n, m, n * n, n * n * n, m * n};
+  unsigned long long mx   = n;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int q = 0; q < 5; ++q)
+      v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < 5; ++q)
+      atomicAdd(&acc[13 + q], v[q]);
+    atomicMax(&acc[18], mx);
+  }
+  // warp-aggregated bucket counters
+  const unsigned peers = __match_any_sync(0xffffffffu, b);
+  if (b >= 0) {
+    unsigned long long bm = n;
+    for (unsigned rest = peers; rest;) { // max n among the peers of this bucket
+      const int src = __ffs(rest) - 1;
+      rest &= rest - 1;
+      bm = max(bm, __shfl_sync(peers, n, src));
+    }
+    if (lane == __ffs(peers) - 1) {
+      atomicAdd(&acc[b], static_cast<unsigned long long>(__popc(peers)));
+      atomicMax(&acc[19 + b], bm);
+    }
+  }
+}
+
+__global__ void bucketScatterKernel(const int *__restrict__ nIn, int64_t nClusters, const long long *__restrict__ start, int *__restrict__ cursor, int *__restrict__ order)
+{
+  const int64_t c    = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int     lane = threadIdx.x & 31;
+  const int     b    = c < nClusters ? pumBucketOf(nIn[c]) : -1;
+  const unsigned peers = __match_any_sync(0xffffffffu, b);
+  if (b >= 0) {
+    const int leader = __ffs(peers) - 1;
+    int       base   = 0;
+    if (lane == leader)
+      base = atomicAdd(&cursor[b], __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    order[start[b] + base + __popc(peers & ((1u << lane) - 1u))] = static_cast<int>(c);
+  }
+}
+
 } // namespace
 
 // =============================================================================================
@@ -334,7 +394,6 @@ void PumClustering::tagDuplicates(const NeighbourOffsets &offs, double threshold
   }
   stateToTagKernel<<<grid, 256, 0, s>>>(total, state.p, tag.p);
   RBF_LAUNCHED();
-  RBF_CUDA(cudaStreamSynchronize(s));
 }
 
 int64_t PumClustering::compact(DevBuf<double> &out, cudaStream_t s)
@@ -354,7 +413,6 @@ int64_t PumClustering::compact(DevBuf<double> &out, cudaStream_t s)
     compactKernel<<<grid, 256, 0, s>>>(total, tag.p, pos.p, centers.p, out.p);
     RBF_LAUNCHED();
   }
-  RBF_CUDA(cudaStreamSynchronize(s));
   return count;
 }
 
@@ -408,4 +466,43 @@ int64_t pumWeightSums(const double *dOutXyz, int64_t nOut, const BinGrid &center
   return f == 0x7f7f7f7f ? -1 : f;
 }
 
+} // namespace rbfmap
+
+namespace rbfmap {
+void pumClassify(const PumMembership &m, int64_t nClusters, PumBuckets &b, rbfmap_stats &stats, cudaStream_t s)
+{
+  DevBuf<unsigned long long> acc;
+  DevBuf<long long>          dStart;
+  DevBuf<int>                cursor;
+  acc.alloc(32);
+  dStart.alloc(kNumBuckets + 1);
+  cursor.alloc(kNumBuckets);
+  RBF_CUDA(cudaMemsetAsync(acc.p, 0, 32 * sizeof(unsigned long long), s));
+  RBF_CUDA(cudaMemsetAsync(cursor.p, 0, kNumBuckets * sizeof(int), s));
+  classifyKernel<<<divUp(nClusters, 256), 256, 0, s>>>(m.nIn.p, m.nOut.p, nClusters, acc.p);
+  RBF_LAUNCHED();
+  unsigned long long h[32];
+  RBF_CUDA(cudaMemcpyAsync(h, acc.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+  RBF_CUDA(cudaStreamSynchronize(s));
+  long long start[kNumBuckets + 1];
+  start[0] = 0;
+  for (int k = 0; k < kNumBuckets; ++k) {
+    start[k + 1] = start[k] + static_cast<long long>(h[k]);
+    b.start[k]   = start[k];
+    b.maxN[k]    = static_cast<int>(h[19 + k]);
+  }
+  b.start[kNumBuckets] = start[kNumBuckets];
+  stats.sum_n  = static_cast<int64_t>(h[13]);
+  stats.sum_m  = static_cast<int64_t>(h[14]);
+  stats.sum_n2 = static_cast<int64_t>(h[15]);
+  stats.sum_n3 = static_cast<int64_t>(h[16]);
+  stats.sum_mn = static_cast<int64_t>(h[17]);
+  stats.max_n  = static_cast<int64_t>(h[18]);
+  RBF_CUDA(cudaMemcpyAsync(dStart.p, start, sizeof(start), cudaMemcpyHostToDevice, s));
+  b.order.alloc(std::max<int64_t>(nClusters, 1));
+  bucketScatterKernel<<<divUp(nClusters, 256), 256, 0, s>>>(m.nIn.p, nClusters, dStart.p, cursor.p, b.order.p);
+  RBF_LAUNCHED();
+  RBF_CUDA(cudaGetLastError());
+  RBF_CUDA(cudaStreamSynchronize(s)); // `start` (host stack) and the temporaries must outlive the copies
+}
 } // namespace rbfmap

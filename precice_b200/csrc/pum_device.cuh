@@ -1,0 +1,135 @@
+// pum_device.cuh — device helpers shared by the per-cluster kernels (pum_poly.cu, pum_factor.cu, pum_map_*.cu).
+#pragma once
+
+#include "pum.cuh"
+
+namespace rbfmap {
+
+// packed lower-triangular column-major storage: start of column k of an n x n factor
+__device__ __forceinline__ int colStart32(int k, int n) { return k * n - (k * (k - 1)) / 2; }
+__device__ __forceinline__ long long colStart(int k, int n) { return static_cast<long long>(k) * n - static_cast<long long>(k) * (k - 1) / 2; }
+
+// Basis function with the kind fixed at compile time (hot kinds) or dispatched at run time (KIND_RUNTIME).
+constexpr int KIND_RUNTIME = -1;
+template <int KIND>
+__device__ __forceinline__ double evalBasisK(double r, const RbfParams &f)
+{
+  if (KIND == KIND_RUNTIME)
+    return evalBasis(r, f);
+  else
+    return evalBasisT<KIND>(r, f);
+}
+
+// Host dispatch: compact polynomials get their own instantiation, every other function shares the run-time one.
+#define RBF_DISPATCH_HOT_BASIS(kind, ...)                                                                         \
+  switch (kind) {                                                                                                 \
+  case RBFMAP_COMPACT_POLYNOMIAL_C0: { constexpr int KIND = RBFMAP_COMPACT_POLYNOMIAL_C0; __VA_ARGS__; } break;   \
+  case RBFMAP_COMPACT_POLYNOMIAL_C2: { constexpr int KIND = RBFMAP_COMPACT_POLYNOMIAL_C2; __VA_ARGS__; } break;   \
+  case RBFMAP_COMPACT_POLYNOMIAL_C4: { constexpr int KIND = RBFMAP_COMPACT_POLYNOMIAL_C4; __VA_ARGS__; } break;   \
+  case RBFMAP_COMPACT_POLYNOMIAL_C6: { constexpr int KIND = RBFMAP_COMPACT_POLYNOMIAL_C6; __VA_ARGS__; } break;   \
+  case RBFMAP_COMPACT_POLYNOMIAL_C8: { constexpr int KIND = RBFMAP_COMPACT_POLYNOMIAL_C8; __VA_ARGS__; } break;   \
+  default: { constexpr int KIND = KIND_RUNTIME; __VA_ARGS__; } break;                                             \
+  }
+
+// Square root for squared vertex distances: MUFU.RSQ64H seed, one Newton step on the reciprocal root and one
+// residual correction of the root. No special-case branches; the argument is clamped to >= 1e-300 so that x == 0
+// (coincident vertices, the matrix diagonal) yields 1e-150, which every basis function maps to phi(0) exactly.
+// Faithful (<= 1 ulp), and equal to the IEEE square root except for rare half-ulp ties (checked by
+// tests/test_gpu_parity.py::test_device_sqrt).
+__device__ __forceinline__ double distSqrt(double x)
+{
+  x = fmax(x, 1.0e-300);
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  const double e  = fma(-hx * y, y, 0.5);
+  y               = fma(y, e, y);           // ~2^-43 relative
+  double       s  = x * y;                  // sqrt estimate
+  const double r  = fma(-s, s, x);          // residual
+  s               = fma(r, 0.5 * y, s);     // corrected root
+  return s;
+}
+
+// squared distance, all axes (3-D) or x/y only (2-D meshes carry z = 0, activeAxis = {1,1,0});
+// same operation order as RadialBasisFctSolver.hpp:102-113, no contraction
+template <bool DIM3>
+__device__ __forceinline__ double sqDistD(double ax, double ay, double az, double bx, double by, double bz)
+{
+  const double dx = __dsub_rn(ax, bx), dy = __dsub_rn(ay, by);
+  double       s  = __dmul_rn(dx, dx);
+  s               = __dadd_rn(s, __dmul_rn(dy, dy));
+  if (DIM3) {
+    const double dz = __dsub_rn(az, bz);
+    s               = __dadd_rn(s, __dmul_rn(dz, dz));
+  }
+  return s;
+}
+
+// polynomial basis row of a vertex for a cluster record (mode 1: centred/scaled, mode 2: raw)
+__device__ __forceinline__ void polyRow(int mode, int mask, double x, double y, double z, double cx, double cy, double cz, double rinv, double (&q)[4])
+{
+  q[0] = 1.0;
+  q[1] = q[2] = q[3] = 0.0;
+  double v[3];
+  if (mode == 1) {
+    v[0] = (x - cx) * rinv;
+    v[1] = (y - cy) * rinv;
+    v[2] = (z - cz) * rinv;
+  } else {
+    v[0] = x;
+    v[1] = y;
+    v[2] = z;
+  }
+  int k = 1;
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+    if (mask & (1 << d)) {
+      if (k == 1) q[1] = v[d];
+      else if (k == 2) q[2] = v[d];
+      else q[3] = v[d];
+      ++k;
+    }
+}
+
+// block-wide sum of NV values per thread; result broadcast to all threads through `red` (>= NV * nWarps doubles)
+template <int NV>
+__device__ __forceinline__ void blockReduceSum(double (&v)[NV], double *red, int nThreads)
+{
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = nThreads >> 5;
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+      v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+  }
+  __syncthreads(); // `red` may still be read from a previous reduction
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < NV; ++q)
+      red[w * NV + q] = v[q];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+    double s = 0.0;
+    for (int ww = 0; ww < nw; ++ww)
+      s += red[ww * NV + q];
+    v[q] = s;
+  }
+}
+
+// normalized partition-of-unity weight of out-vertex (x,y,z) in the cluster centred at (cx,cy,cz)
+// (PartitionOfUnityMapping.hpp:321-336)
+__device__ __forceinline__ double normalizedWeight(double x, double y, double z, double cx, double cy, double cz, double rinv, double wsum, int wcount)
+{
+  if (wsum <= 0.0)
+    return __ddiv_rn(1.0, static_cast<double>(wcount));
+  const double w = pumWeight(__dsqrt_rn(sqDist3(cx, cy, cz, x, y, z)), rinv);
+  return __ddiv_rn(w, wsum);
+}
+
+// coordinate of padding vertex i (beyond the cluster size): far away and pairwise distinct, so that every basis
+// function evaluates to (numerically) zero against real vertices without any per-entry conditional
+__device__ __forceinline__ double paddingCoordinate(int i) { return 1.0e100 * static_cast<double>(i + 1); }
+
+} // namespace rbfmap

@@ -5,7 +5,18 @@
 
 namespace rbfmap {
 
-thread_local int g_launches = 0;
+thread_local int          g_launches    = 0;
+thread_local cudaStream_t g_allocStream = nullptr;
+
+void configureMemoryPool()
+{
+  int dev = 0;
+  RBF_CUDA(cudaGetDevice(&dev));
+  cudaMemPool_t pool;
+  RBF_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+  unsigned long long threshold = ~0ull;
+  RBF_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+}
 
 int smCount()
 {
@@ -129,8 +140,7 @@ void scanImpl(const TI *in, TO *out, int64_t n, cudaStream_t s)
   RBF_LAUNCHED();
   addBlockOffsets<TO><<<nBlocks, kThreads, 0, s>>>(out, sums.p, n);
   RBF_LAUNCHED();
-  RBF_CUDA(cudaGetLastError());
-  RBF_CUDA(cudaStreamSynchronize(s)); // `sums` is freed on return
+  RBF_CUDA(cudaGetLastError()); // `sums` is released stream-ordered
 }
 } // namespace
 

@@ -322,8 +322,7 @@ void BinGrid::build(const double *dXyz, int64_t nPts, const double bbMin[3], con
     binGatherKernel<<<gridFor(nPts), kBlock, 0, s>>>(dXyz, nPts, ids.p, xyz.p);
     RBF_LAUNCHED();
   }
-  RBF_CUDA(cudaGetLastError());
-  RBF_CUDA(cudaStreamSynchronize(s)); // temporaries go out of scope
+  RBF_CUDA(cudaGetLastError()); // temporaries are released stream-ordered
 }
 
 } // namespace rbfmap

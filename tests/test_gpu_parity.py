@@ -58,6 +58,23 @@ def test_gaussian_support_radius(pb, orc):
     assert np.all(a[r > 1.0] == 0.0)
 
 
+def test_device_sqrt(pb):
+    """distSqrt (rsqrt seed + Newton + residual correction) against the IEEE square root: faithful everywhere,
+    identical for all but a vanishing fraction of arguments."""
+    import ctypes as C
+    from precice_b200 import _lib
+    rng = np.random.default_rng(7)
+    x = np.concatenate([rng.random(2_000_000) * 3.0, 10.0 ** rng.uniform(-12, 12, 1_000_000), [0.0, 1.0, 4.0, 2.0, 1e-300, 1e200]])
+    out = np.empty_like(x)
+    dp = C.POINTER(C.c_double)
+    assert _lib.lib().rbfmap_debug_dist_sqrt(x.ctypes.data_as(dp), x.size, out.ctypes.data_as(dp)) == 0
+    ref = np.sqrt(x)
+    ref[x == 0.0] = 1e-150  # the clamp: every basis function maps 1e-150 to phi(0) exactly
+    ulp = np.abs(out - ref) / np.spacing(ref)
+    assert ulp.max() <= 1.0, ulp.max()
+    assert np.count_nonzero(out != ref) <= 1e-4 * x.size, np.count_nonzero(out != ref)
+
+
 # ---------------------------------------------------------------------------------------------- reference unit tests (goldens)
 CASES = refcases.pum_cases()
 
