@@ -189,7 +189,7 @@ __global__ void memberCountKernel(const double *__restrict__ centers, int64_t nC
   if (lane == 0) {
     nIn[c]  = ci;
     nOut[c] = co;
-    tri[c]  = static_cast<long long>(ci) * (ci + 1) / 2;
+    tri[c]  = (static_cast<long long>(ci) * (ci + 1) / 2 + 1) & ~1LL; // even count: 16-byte aligned factors for the TMA bulk copy
   }
 }
 

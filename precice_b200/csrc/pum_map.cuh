@@ -1,4 +1,10 @@
-// pum_map.cuh — pieces shared by the consistent and the conservative map kernels.
+// pum_map.cuh — pieces shared by the consistent and the conservative per-cluster map kernels (sm_100a).
+//
+// Shared-memory tile of one cluster (doubles):
+//   ms : packed factor, n(n+1)/2 rounded up to an even count; staged with one TMA bulk copy
+//        (cp.async.bulk global -> shared, completion on an mbarrier) that overlaps the gather and the polynomial fit
+//   vt : vertex tile, n rows of LDV doubles: x, y, z, then the NC right-hand sides / coefficients of the row
+//   red: reduction scratch
 #pragma once
 
 #include "pum_device.cuh"
@@ -8,16 +14,55 @@
 
 namespace rbfmap {
 
-// In-place solve of (M D^-1 M^T) x = b for NC right-hand sides held in shared memory (b[comp*ldb + i]).
-// `mp` is the packed factor (shared or global memory). Blocks of 8 columns: every thread redoes the tiny
-// diagonal solve redundantly (broadcast reads), then updates its own row — one barrier per block.
+// row length of the vertex tile: (x, y, z, b0) or (x, y, z, b0, b1, b2) -> 2 or 3 aligned 16-byte loads per row
 template <int NC>
-__device__ __forceinline__ void blockedSolve(const double *mp, int n, double *b, int ldb, int tid, int nThreads)
+struct TileLd {
+  static constexpr int value = NC == 1 ? 4 : 6;
+};
+
+__host__ __device__ inline long long paddedTri(long long n) { return (n * (n + 1) / 2 + 1) & ~1LL; }
+
+// ---- TMA bulk copy + mbarrier (PTX ISA: cp.async.bulk / mbarrier, sm_90+) ----
+__device__ __forceinline__ unsigned smemAddr(const void *p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void     mbarInit(unsigned long long *bar, unsigned count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulkLoad(void *dstSmem, const void *srcGlobal, unsigned bytes, unsigned long long *bar)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(dstSmem)), "l"(srcGlobal),
+               "r"(bytes), "r"(smemAddr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbarWait(unsigned long long *bar, unsigned phase)
+{
+  unsigned done = 0;
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done)
+                 : "r"(smemAddr(bar)), "r"(phase)
+                 : "memory");
+  }
+}
+
+// In-place solve of (M D^-1 M^T) x = b for NC right-hand sides stored in the vertex tile (b(i, cc) = v[i*LDV + cc]).
+// `mp` is the packed factor: column k = [1/d_k, M(k+1,k), ...]. Blocks of 8 columns: every thread redoes the tiny
+// diagonal solve redundantly from broadcast reads, then updates its own rows — two barriers per block.
+// IDX is int for the shared-memory copy (n <= 128) and long long for the global-memory variant.
+template <int NC, int LDV, typename IDX>
+__device__ __forceinline__ void blockedSolve(const double *__restrict__ mp, int n, double *v, int tid, int nThreads)
 {
   // forward: M y = b ; b <- numerators u = D y
   for (int k0 = 0; k0 < n; k0 += 8) {
     const int nb = min(8, n - k0);
-    double    y[8][NC], un[8][NC];
+    IDX       base[8]; // M(i, k0+q) = mp[base[q] + i]
+    base[0] = static_cast<IDX>(k0) * n - static_cast<IDX>(k0) * (k0 - 1) / 2 - k0;
+#pragma unroll
+    for (int q = 1; q < 8; ++q)
+      base[q] = base[q - 1] + (n - (k0 + q - 1) - 1);
+    double y[8][NC], un[8][NC];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       if (q < nb) {
@@ -25,54 +70,59 @@ __device__ __forceinline__ void blockedSolve(const double *mp, int n, double *b,
         double    u[NC];
 #pragma unroll
         for (int cc = 0; cc < NC; ++cc)
-          u[cc] = b[cc * ldb + k];
+          u[cc] = v[k * LDV + cc];
 #pragma unroll
         for (int q2 = 0; q2 < 8; ++q2)
           if (q2 < q) {
-            const double mkj = mp[colStart(k0 + q2, n) + (k - k0 - q2)];
+            const double mkj = mp[base[q2] + k];
 #pragma unroll
             for (int cc = 0; cc < NC; ++cc)
               u[cc] = fma(-mkj, y[q2][cc], u[cc]);
           }
-        const double rd = mp[colStart(k, n)];
+        const double rd = mp[base[q] + k];
 #pragma unroll
-        for (int cc = 0; cc < NC; ++cc)
-          y[q][cc] = u[cc] * rd;
-#pragma unroll
-        for (int cc = 0; cc < NC; ++cc)
+        for (int cc = 0; cc < NC; ++cc) {
+          y[q][cc]  = u[cc] * rd;
           un[q][cc] = u[cc];
+        }
       }
     }
     __syncthreads(); // everyone has read b[k0..k0+nb) before the owners overwrite it with the numerators
-    for (int q = 0; q < nb; ++q)
-      if (tid == (k0 + q) % nThreads) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (q < nb && tid == (k0 + q) % nThreads) {
 #pragma unroll
         for (int cc = 0; cc < NC; ++cc)
-          b[cc * ldb + k0 + q] = un[q][cc];
+          v[(k0 + q) * LDV + cc] = un[q][cc];
       }
     for (int i = k0 + nb + tid; i < n; i += nThreads) {
       double acc[NC];
 #pragma unroll
       for (int cc = 0; cc < NC; ++cc)
-        acc[cc] = b[cc * ldb + i];
+        acc[cc] = v[i * LDV + cc];
 #pragma unroll
       for (int q = 0; q < 8; ++q)
         if (q < nb) {
-          const double mik = mp[colStart(k0 + q, n) + (i - k0 - q)];
+          const double mik = mp[base[q] + i];
 #pragma unroll
           for (int cc = 0; cc < NC; ++cc)
             acc[cc] = fma(-mik, y[q][cc], acc[cc]);
         }
 #pragma unroll
       for (int cc = 0; cc < NC; ++cc)
-        b[cc * ldb + i] = acc[cc];
+        v[i * LDV + cc] = acc[cc];
     }
     __syncthreads();
   }
   // backward: M^T x = u
   for (int k0 = ((n - 1) / 8) * 8; k0 >= 0; k0 -= 8) {
     const int nb = min(8, n - k0);
-    double    x[8][NC];
+    IDX       base[8];
+    base[0] = static_cast<IDX>(k0) * n - static_cast<IDX>(k0) * (k0 - 1) / 2 - k0;
+#pragma unroll
+    for (int q = 1; q < 8; ++q)
+      base[q] = base[q - 1] + (n - (k0 + q - 1) - 1);
+    double x[8][NC];
 #pragma unroll
     for (int q = 7; q >= 0; --q) {
       if (q < nb) {
@@ -80,50 +130,50 @@ __device__ __forceinline__ void blockedSolve(const double *mp, int n, double *b,
         double    u[NC];
 #pragma unroll
         for (int cc = 0; cc < NC; ++cc)
-          u[cc] = b[cc * ldb + k];
+          u[cc] = v[k * LDV + cc];
 #pragma unroll
         for (int q2 = 7; q2 >= 0; --q2)
           if (q2 > q && q2 < nb) {
-            const double mik = mp[colStart(k, n) + (q2 - q)]; // M(k0+q2, k)
+            const double mik = mp[base[q] + k0 + q2]; // M(k0+q2, k)
 #pragma unroll
             for (int cc = 0; cc < NC; ++cc)
               u[cc] = fma(-mik, x[q2][cc], u[cc]);
           }
-        const double rd = mp[colStart(k, n)];
+        const double rd = mp[base[q] + k];
 #pragma unroll
         for (int cc = 0; cc < NC; ++cc)
           x[q][cc] = u[cc] * rd;
       }
     }
     __syncthreads(); // everyone has read b[k0..k0+nb) before the owners overwrite it
-    for (int q = 0; q < nb; ++q)
-      if (tid == (k0 + q) % nThreads) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (q < nb && tid == (k0 + q) % nThreads) {
 #pragma unroll
         for (int cc = 0; cc < NC; ++cc)
-          b[cc * ldb + k0 + q] = x[q][cc];
+          v[(k0 + q) * LDV + cc] = x[q][cc];
       }
     for (int i = tid; i < k0; i += nThreads) {
-      double          acc[NC];
-      const long long ci = colStart(i, n);
+      double    acc[NC];
+      const IDX bi = static_cast<IDX>(i) * n - static_cast<IDX>(i) * (i - 1) / 2 - i; // M(k, i) = mp[bi + k]
 #pragma unroll
       for (int cc = 0; cc < NC; ++cc)
-        acc[cc] = b[cc * ldb + i];
+        acc[cc] = v[i * LDV + cc];
 #pragma unroll
       for (int q = 0; q < 8; ++q)
         if (q < nb) {
-          const double mki = mp[ci + (k0 + q - i)]; // M(k0+q, i)
+          const double mki = mp[bi + k0 + q];
 #pragma unroll
           for (int cc = 0; cc < NC; ++cc)
             acc[cc] = fma(-mki, x[q][cc], acc[cc]);
         }
 #pragma unroll
       for (int cc = 0; cc < NC; ++cc)
-        b[cc * ldb + i] = acc[cc];
+        v[i * LDV + cc] = acc[cc];
     }
     __syncthreads();
   }
 }
-
 
 template <typename K>
 inline void allowSmem(K kernel, size_t bytes)
@@ -131,8 +181,5 @@ inline void allowSmem(K kernel, size_t bytes)
   if (bytes > 48 * 1024)
     RBF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
 }
-
-// threads per CTA of the map kernels for a bucket, and whether the packed factor is staged in shared memory
-inline int mapThreads(int bucket) { return bucket < 8 ? 64 : (bucket < 12 ? 128 : 256); }
 
 } // namespace rbfmap

@@ -3,7 +3,7 @@
 //
 // Replaces, per cluster, SphericalVertexCluster::mapConservative (impl/SphericalVertexCluster.hpp:201-240) with
 // RadialBasisFctSolver::solveConservative (RadialBasisFctSolver.hpp:413-438) and the evaluation matrix of buildMatrixA
-// (:209-242), which is never stored: A(i,j) = phi(|out_i - in_j|) is re-evaluated from the vertex tile in shared memory.
+// (:209-242), which is never stored: A(i,j) = phi(|out_i - in_j|) is re-evaluated from the vertex tiles in shared memory.
 // (The reference has no device path for this direction: PartitionOfUnityMapping.hpp:354-355.)
 #include "pum_map.cuh"
 
@@ -14,54 +14,53 @@ template <int KIND, int NC, int NT, bool STAGE_M, bool DIM3>
 __global__ void __launch_bounds__(NT) pumMapConservativeKernel(PumSolveArgs args, const int *__restrict__ list, const double *__restrict__ in, int dims, int c0,
                                                                double *__restrict__ out)
 {
+  constexpr int LDV = TileLd<NC>::value;
   extern __shared__ __align__(16) double dyn[];
-  const int       c    = list[blockIdx.x];
-  const int       n    = args.nIn[c];
-  const int       m    = args.nOut[c];
-  const int       tid  = threadIdx.x;
+  __shared__ __align__(8) unsigned long long mbar;
+
+  const int c   = list[blockIdx.x];
+  const int n   = args.nIn[c];
+  const int m   = args.nOut[c];
+  const int tid = threadIdx.x;
+  if (m == 0)
+    return;
   const int      *ids  = args.inIds + args.inOff[c];
   const int      *oids = args.outIds + args.outOff[c];
   const double   *mg   = args.mat + args.matOff[c];
   const RbfParams rbf  = args.rbf;
-  const PolyRec   rec  = args.poly[c];
   const double    cx = args.centers[3 * c], cy = args.centers[3 * c + 1], cz = args.centers[3 * c + 2];
   const double    rinv = 1.0 / args.radius;
-  const long long tri  = static_cast<long long>(n) * (n + 1) / 2;
+  const int       triPad = STAGE_M ? static_cast<int>(paddedTri(n)) : 0;
 
   double *ms  = dyn;
-  double *sx  = STAGE_M ? dyn + tri : dyn;
-  double *sy  = sx + n;
-  double *sz  = sy + n;
-  double *b   = sz + n;
-  double *red = b + NC * n;
-  double *ox  = red + 16 * (NT / 32);
-  double *oy  = ox + NT;
-  double *oz  = oy + NT;
-  double *ou  = oz + NT; // NC * NT
+  double *vt  = dyn + triPad;       // in-vertices: x, y, z, Au / mu
+  double *ot  = vt + n * LDV;       // chunk of out-vertices: x, y, z, w*u   (NT rows)
+  double *red = ot + NT * LDV;
 
-  if (m == 0)
-    return;
-  if (STAGE_M)
-    for (long long e = tid; e < tri; e += NT)
-      ms[e] = mg[e];
+  if (STAGE_M) {
+    if (tid == 0)
+      mbarInit(&mbar, 1);
+    __syncthreads();
+    if (tid == 0)
+      bulkLoad(ms, mg, static_cast<unsigned>(triPad) * 8u, &mbar);
+  }
   for (int i = tid; i < n; i += NT) {
     const double *p = args.inXyz + 3 * static_cast<long long>(ids[i]);
-    sx[i]           = p[0];
-    sy[i]           = p[1];
-    sz[i]           = p[2];
+    vt[i * LDV]     = p[0];
+    vt[i * LDV + 1] = p[1];
+    vt[i * LDV + 2] = p[2];
+#pragma unroll
+    for (int cc = 0; cc < NC; ++cc)
+      vt[i * LDV + 3 + cc] = 0.0;
   }
-  const double *mp = STAGE_M ? ms : mg;
+  const int polyMode = args.poly[c].mode, polyMask = args.poly[c].mask, polyRefine = args.poly[c].pad;
 
   // ---- Au = A^T (w .* u), epsilon = V^T (w .* u) (RadialBasisFctSolver.hpp:420, :428) ----
   double eps[4 * NC];
 #pragma unroll
   for (int e = 0; e < 4 * NC; ++e)
     eps[e] = 0.0;
-  const int rowsPerThread = (n + NT - 1) / NT; // 1 for the register-tiled classes
-  for (int i = tid; i < n; i += NT)
-#pragma unroll
-    for (int cc = 0; cc < NC; ++cc)
-      b[cc * n + i] = 0.0;
+  const int rowsPerThread = (n + NT - 1) / NT; // 1 for the register-tiled buckets
   for (int o0 = 0; o0 < m; o0 += NT) {
     __syncthreads();
     const int o = o0 + tid;
@@ -69,19 +68,19 @@ __global__ void __launch_bounds__(NT) pumMapConservativeKernel(PumSolveArgs args
       const long long gid = oids[o];
       const double   *p   = args.outXyz + 3 * gid;
       const double    x = p[0], y = p[1], z = p[2];
-      ox[tid] = x;
-      oy[tid] = y;
-      oz[tid] = z;
+      ot[tid * LDV]     = x;
+      ot[tid * LDV + 1] = y;
+      ot[tid * LDV + 2] = z;
       // SphericalVertexCluster.hpp:219-227: in(i,c) = data * normalizedWeight
       const double w = normalizedWeight(x, y, z, cx, cy, cz, rinv, args.wsum[gid], args.wcount[gid]);
       double       q[4];
-      if (rec.mode != 0)
-        polyRow(rec.mode, rec.mask, x, y, z, cx, cy, cz, rinv, q);
+      if (polyMode != 0)
+        polyRow(polyMode, polyMask, x, y, z, cx, cy, cz, rinv, q);
 #pragma unroll
       for (int cc = 0; cc < NC; ++cc) {
-        const double u   = in[gid * dims + c0 + cc] * w;
-        ou[cc * NT + tid] = u;
-        if (rec.mode != 0) {
+        const double u          = in[gid * dims + c0 + cc] * w;
+        ot[tid * LDV + 3 + cc] = u;
+        if (polyMode != 0) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             eps[k * NC + cc] += q[k] * u;
@@ -96,27 +95,40 @@ __global__ void __launch_bounds__(NT) pumMapConservativeKernel(PumSolveArgs args
         double acc[NC];
 #pragma unroll
         for (int cc = 0; cc < NC; ++cc)
-          acc[cc] = b[cc * n + j];
-        const double xj = sx[j], yj = sy[j], zj = sz[j];
-        for (int oo = 0; oo < chunk; ++oo) {
-          const double d2  = sqDistD<DIM3>(ox[oo], oy[oo], oz[oo], xj, yj, zj);
-          const double phi = evalBasisK<KIND>(distSqrt(d2), rbf);
-#pragma unroll
-          for (int cc = 0; cc < NC; ++cc)
-            acc[cc] = fma(phi, ou[cc * NT + oo], acc[cc]);
+          acc[cc] = vt[j * LDV + 3 + cc];
+        const double  xj = vt[j * LDV], yj = vt[j * LDV + 1], zj = vt[j * LDV + 2];
+        const double *op = ot;
+#pragma unroll 2
+        for (int oo = 0; oo < chunk; ++oo, op += LDV) {
+          const double2 xy  = *reinterpret_cast<const double2 *>(op);
+          const double2 zu  = *reinterpret_cast<const double2 *>(op + 2);
+          const double  d2  = sqDistD<DIM3>(xy.x, xy.y, zu.x, xj, yj, zj);
+          const double  phi = evalBasisK<KIND>(distSqrt(d2), rbf);
+          acc[0]            = fma(phi, zu.y, acc[0]);
+          if (NC > 1) {
+            const double2 u12 = *reinterpret_cast<const double2 *>(op + 4);
+            acc[1]            = fma(phi, u12.x, acc[1]);
+            if (NC > 2)
+              acc[2] = fma(phi, u12.y, acc[2]);
+          }
         }
 #pragma unroll
         for (int cc = 0; cc < NC; ++cc)
-          b[cc * n + j] = acc[cc];
+          vt[j * LDV + 3 + cc] = acc[cc];
       }
     }
   }
-  if (rec.mode != 0)
+  if (polyMode != 0)
     blockReduceSum<4 * NC>(eps, red, NT);
   __syncthreads();
 
   // ---- mu = C^-1 Au ----
-  blockedSolve<NC>(mp, n, b, n, tid, NT);
+  if (STAGE_M) {
+    mbarWait(&mbar, 0);
+    blockedSolve<NC, LDV, int>(ms, n, vt + 3, tid, NT);
+  } else {
+    blockedSolve<NC, LDV, long long>(mg, n, vt + 3, tid, NT);
+  }
 
   // ---- out = mu + Q (Q^T Q)^-1 (epsilon - Q^T mu)  (RadialBasisFctSolver.hpp:427-436) ----
   double gamma[4][NC];
@@ -125,9 +137,10 @@ __global__ void __launch_bounds__(NT) pumMapConservativeKernel(PumSolveArgs args
 #pragma unroll
     for (int cc = 0; cc < NC; ++cc)
       gamma[k][cc] = 0.0;
-  if (rec.mode == 1) {
+  const double *G = args.poly[c].G;
+  if (polyMode == 1) {
 #pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
+    for (int pass = 0; pass <= polyRefine; ++pass) {
       // tau = epsilon - Q^T (mu + Q gamma)
       double t[4 * NC];
 #pragma unroll
@@ -135,10 +148,10 @@ __global__ void __launch_bounds__(NT) pumMapConservativeKernel(PumSolveArgs args
         t[e] = 0.0;
       for (int i = tid; i < n; i += NT) {
         double q[4];
-        polyRow(rec.mode, rec.mask, sx[i], sy[i], sz[i], cx, cy, cz, rinv, q);
+        polyRow(1, polyMask, vt[i * LDV], vt[i * LDV + 1], vt[i * LDV + 2], cx, cy, cz, rinv, q);
 #pragma unroll
         for (int cc = 0; cc < NC; ++cc) {
-          double v = b[cc * n + i];
+          double v = vt[i * LDV + 3 + cc];
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             v += q[k] * gamma[k][cc];
@@ -155,7 +168,7 @@ __global__ void __launch_bounds__(NT) pumMapConservativeKernel(PumSolveArgs args
           double s = 0.0;
 #pragma unroll
           for (int l = 0; l < 4; ++l)
-            s += rec.G[4 * k + l] * (eps[l * NC + cc] - t[l * NC + cc]);
+            s += G[4 * k + l] * (eps[l * NC + cc] - t[l * NC + cc]);
           gamma[k][cc] += s;
         }
     }
@@ -165,16 +178,16 @@ __global__ void __launch_bounds__(NT) pumMapConservativeKernel(PumSolveArgs args
     double          res[NC];
 #pragma unroll
     for (int cc = 0; cc < NC; ++cc)
-      res[cc] = b[cc * n + i];
-    if (rec.mode == 1) {
+      res[cc] = vt[i * LDV + 3 + cc];
+    if (polyMode == 1) {
       double q[4];
-      polyRow(rec.mode, rec.mask, sx[i], sy[i], sz[i], cx, cy, cz, rinv, q);
+      polyRow(1, polyMask, vt[i * LDV], vt[i * LDV + 1], vt[i * LDV + 2], cx, cy, cz, rinv, q);
 #pragma unroll
       for (int cc = 0; cc < NC; ++cc)
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           res[cc] += q[k] * gamma[k][cc];
-    } else if (rec.mode == 2) {
+    } else if (polyMode == 2) {
       // y = S^T (epsilon - Q^T mu) with the raw basis; n <= 3 rows
 #pragma unroll
       for (int cc = 0; cc < NC; ++cc) {
@@ -184,15 +197,15 @@ __global__ void __launch_bounds__(NT) pumMapConservativeKernel(PumSolveArgs args
           tau[k] = eps[k * NC + cc];
         for (int r = 0; r < n && r < 3; ++r) {
           double q[4];
-          polyRow(rec.mode, rec.mask, sx[r], sy[r], sz[r], cx, cy, cz, rinv, q);
+          polyRow(2, polyMask, vt[r * LDV], vt[r * LDV + 1], vt[r * LDV + 2], cx, cy, cz, rinv, q);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            tau[k] -= q[k] * b[cc * n + r];
+            tau[k] -= q[k] * vt[r * LDV + 3 + cc];
         }
         double yv = 0.0;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          yv += rec.G[4 * k + i] * tau[k];
+          yv += G[4 * k + i] * tau[k];
         res[cc] += yv;
       }
     }
@@ -203,12 +216,11 @@ __global__ void __launch_bounds__(NT) pumMapConservativeKernel(PumSolveArgs args
   }
 }
 
-
 template <int KIND, int NC, int NT, bool STAGE_M>
 void launchConservative(const PumSolveArgs &a, const int *list, int64_t count, int maxN, const double *in, int dims, int c0, double *out, cudaStream_t s)
 {
-  const size_t tri = STAGE_M ? static_cast<size_t>(maxN) * (maxN + 1) / 2 : 0;
-  const size_t sm  = (tri + (3 + NC) * static_cast<size_t>(maxN) + 16 * (NT / 32) + (3 + NC) * NT) * sizeof(double);
+  const size_t tri = STAGE_M ? static_cast<size_t>(paddedTri(maxN)) : 0;
+  const size_t sm  = (tri + static_cast<size_t>(TileLd<NC>::value) * (maxN + NT) + 16 * (NT / 32)) * sizeof(double);
   if (sm > kPumMaxSmem)
     throw MapError(RBFMAP_ERR_UNSUPPORTED, "rbf-pum-direct: a cluster with " + std::to_string(maxN) + " vertices exceeds the supported cluster size.");
   if (a.dim == 3) {
@@ -240,7 +252,7 @@ void dispatchConservative(const PumSolveArgs &a, const PumBuckets &bk, const dou
     if (count <= 0)
       continue;
     const int *list = bk.order.p + bk.start[b];
-    for (int c0 = 0; c0 < dims;) { // components are processed in groups of up to 3 per launch
+    for (int c0 = 0; c0 < dims;) {
       const int nc = std::min(3, dims - c0);
       if (nc == 1)
         bucketConservative<KIND, 1>(a, b, list, count, bk.maxN[b], in, dims, c0, out, s);

@@ -10,75 +10,76 @@
 namespace rbfmap {
 namespace {
 
-// Shared-memory layout of the map kernels (doubles):
-//   mp   : n(n+1)/2   packed factor (only when it fits, STAGE_M)
-//   sx,sy,sz : n each
-//   b    : NC * n      right-hand sides / coefficients
-//   red  : 16 * nWarps reduction scratch
-//   (conservative) ox,oy,oz,ou[NC] : chunk of out-vertices, NT each
 template <int KIND, int NC, int NT, bool STAGE_M, bool DIM3>
 __global__ void __launch_bounds__(NT) pumMapConsistentKernel(PumSolveArgs args, const int *__restrict__ list, const double *__restrict__ in, int dims, int c0,
                                                              double *__restrict__ out)
 {
+  constexpr int LDV = TileLd<NC>::value;
   extern __shared__ __align__(16) double dyn[];
+  __shared__ __align__(8) unsigned long long mbar;
+
   const int       c    = list[blockIdx.x];
   const int       n    = args.nIn[c];
   const int       m    = args.nOut[c];
   const int       tid  = threadIdx.x;
+  if (m == 0)
+    return; // nothing to evaluate (uniform per CTA)
   const int      *ids  = args.inIds + args.inOff[c];
   const int      *oids = args.outIds + args.outOff[c];
   const double   *mg   = args.mat + args.matOff[c];
   const RbfParams rbf  = args.rbf;
-  const PolyRec   rec  = args.poly[c];
   const double    cx = args.centers[3 * c], cy = args.centers[3 * c + 1], cz = args.centers[3 * c + 2];
   const double    rinv = 1.0 / args.radius;
-  const long long tri  = static_cast<long long>(n) * (n + 1) / 2;
+  const int       triPad = STAGE_M ? static_cast<int>(paddedTri(n)) : 0;
 
   double *ms  = dyn;
-  double *sx  = STAGE_M ? dyn + tri : dyn;
-  double *sy  = sx + n;
-  double *sz  = sy + n;
-  double *b   = sz + n;
-  double *red = b + NC * n;
+  double *vt  = dyn + triPad;
+  double *red = vt + n * LDV;
 
-  if (m == 0)
-    return; // nothing to evaluate (uniform per CTA)
-  if (STAGE_M)
-    for (long long e = tid; e < tri; e += NT)
-      ms[e] = mg[e];
+  // ---- stage the packed factor with one TMA bulk copy; it lands while the tile is gathered and the polynomial fitted ----
+  if (STAGE_M) {
+    if (tid == 0)
+      mbarInit(&mbar, 1);
+    __syncthreads();
+    if (tid == 0)
+      bulkLoad(ms, mg, static_cast<unsigned>(triPad) * 8u, &mbar);
+  }
+
+  // ---- gather (SphericalVertexCluster.hpp:312-320) ----
   for (int i = tid; i < n; i += NT) {
     const long long id = ids[i];
     const double   *p  = args.inXyz + 3 * id;
-    sx[i]              = p[0];
-    sy[i]              = p[1];
-    sz[i]              = p[2];
+    vt[i * LDV]        = p[0];
+    vt[i * LDV + 1]    = p[1];
+    vt[i * LDV + 2]    = p[2];
 #pragma unroll
     for (int cc = 0; cc < NC; ++cc)
-      b[cc * n + i] = in[id * dims + c0 + cc]; // SphericalVertexCluster.hpp:312-320
+      vt[i * LDV + 3 + cc] = in[id * dims + c0 + cc];
   }
   __syncthreads();
-  const double *mp = STAGE_M ? ms : mg;
 
   // ---- separated polynomial: beta = lstsq(Q, f); f <- f - Q beta (RadialBasisFctSolver.hpp:446-449) ----
-  double beta[4][NC];
+  const int polyMode = args.poly[c].mode, polyMask = args.poly[c].mask, polyRefine = args.poly[c].pad;
+  double    beta[4][NC];
 #pragma unroll
   for (int q = 0; q < 4; ++q)
 #pragma unroll
     for (int cc = 0; cc < NC; ++cc)
       beta[q][cc] = 0.0;
-  if (rec.mode == 1) {
+  if (polyMode == 1) {
+    const double *G = args.poly[c].G;
 #pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) { // normal equations + one refinement step on the residual
+    for (int pass = 0; pass <= polyRefine; ++pass) { // normal equations (+ one refinement step on the residual)
       double t[4 * NC];
 #pragma unroll
       for (int e = 0; e < 4 * NC; ++e)
         t[e] = 0.0;
       for (int i = tid; i < n; i += NT) {
         double q[4];
-        polyRow(rec.mode, rec.mask, sx[i], sy[i], sz[i], cx, cy, cz, rinv, q);
+        polyRow(1, polyMask, vt[i * LDV], vt[i * LDV + 1], vt[i * LDV + 2], cx, cy, cz, rinv, q);
 #pragma unroll
         for (int cc = 0; cc < NC; ++cc) {
-          double r = b[cc * n + i];
+          double r = vt[i * LDV + 3 + cc];
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             r -= q[k] * beta[k][cc];
@@ -95,40 +96,46 @@ __global__ void __launch_bounds__(NT) pumMapConsistentKernel(PumSolveArgs args, 
           double s = 0.0;
 #pragma unroll
           for (int l = 0; l < 4; ++l)
-            s += rec.G[4 * k + l] * t[l * NC + cc];
+            s += G[4 * k + l] * t[l * NC + cc];
           beta[k][cc] += s;
         }
     }
-  } else if (rec.mode == 2) {
+  } else if (polyMode == 2) {
+    const double *G = args.poly[c].G;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
 #pragma unroll
       for (int cc = 0; cc < NC; ++cc) {
         double s = 0.0;
         for (int i = 0; i < n && i < 3; ++i)
-          s += rec.G[4 * k + i] * b[cc * n + i];
+          s += G[4 * k + i] * vt[i * LDV + 3 + cc];
         beta[k][cc] = s;
       }
   }
-  if (rec.mode != 0) {
+  if (polyMode != 0) {
     __syncthreads();
     for (int i = tid; i < n; i += NT) {
       double q[4];
-      polyRow(rec.mode, rec.mask, sx[i], sy[i], sz[i], cx, cy, cz, rinv, q);
+      polyRow(polyMode, polyMask, vt[i * LDV], vt[i * LDV + 1], vt[i * LDV + 2], cx, cy, cz, rinv, q);
 #pragma unroll
       for (int cc = 0; cc < NC; ++cc) {
-        double r = b[cc * n + i];
+        double r = vt[i * LDV + 3 + cc];
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           r -= q[k] * beta[k][cc];
-        b[cc * n + i] = r;
+        vt[i * LDV + 3 + cc] = r;
       }
     }
     __syncthreads();
   }
 
   // ---- lambda = C^-1 f ----
-  blockedSolve<NC>(mp, n, b, n, tid, NT);
+  if (STAGE_M) {
+    mbarWait(&mbar, 0);
+    blockedSolve<NC, LDV, int>(ms, n, vt + 3, tid, NT);
+  } else {
+    blockedSolve<NC, LDV, long long>(mg, n, vt + 3, tid, NT);
+  }
 
   // ---- out = A lambda + V beta, weighted accumulation (SphericalVertexCluster.hpp:322-334) ----
   for (int o = tid; o < m; o += NT) {
@@ -139,16 +146,24 @@ __global__ void __launch_bounds__(NT) pumMapConsistentKernel(PumSolveArgs args, 
 #pragma unroll
     for (int cc = 0; cc < NC; ++cc)
       acc[cc] = 0.0;
-    for (int j = 0; j < n; ++j) {
-      const double d2  = sqDistD<DIM3>(x, y, z, sx[j], sy[j], sz[j]);
-      const double phi = evalBasisK<KIND>(distSqrt(d2), rbf);
-#pragma unroll
-      for (int cc = 0; cc < NC; ++cc)
-        acc[cc] = fma(phi, b[cc * n + j], acc[cc]);
+    const double *vp = vt;
+#pragma unroll 2
+    for (int j = 0; j < n; ++j, vp += LDV) {
+      const double2 xy = *reinterpret_cast<const double2 *>(vp);
+      const double2 zb = *reinterpret_cast<const double2 *>(vp + 2);
+      const double  d2  = sqDistD<DIM3>(x, y, z, xy.x, xy.y, zb.x);
+      const double  phi = evalBasisK<KIND>(distSqrt(d2), rbf);
+      acc[0]            = fma(phi, zb.y, acc[0]);
+      if (NC > 1) {
+        const double2 b12 = *reinterpret_cast<const double2 *>(vp + 4);
+        acc[1]            = fma(phi, b12.x, acc[1]);
+        if (NC > 2)
+          acc[2] = fma(phi, b12.y, acc[2]);
+      }
     }
-    if (rec.mode != 0) {
+    if (polyMode != 0) {
       double q[4];
-      polyRow(rec.mode, rec.mask, x, y, z, cx, cy, cz, rinv, q);
+      polyRow(polyMode, polyMask, x, y, z, cx, cy, cz, rinv, q);
 #pragma unroll
       for (int cc = 0; cc < NC; ++cc)
 #pragma unroll
@@ -162,12 +177,11 @@ __global__ void __launch_bounds__(NT) pumMapConsistentKernel(PumSolveArgs args, 
   }
 }
 
-
 template <int KIND, int NC, int NT, bool STAGE_M>
 void launchConsistent(const PumSolveArgs &a, const int *list, int64_t count, int maxN, const double *in, int dims, int c0, double *out, cudaStream_t s)
 {
-  const size_t tri = STAGE_M ? static_cast<size_t>(maxN) * (maxN + 1) / 2 : 0;
-  const size_t sm  = (tri + (3 + NC) * static_cast<size_t>(maxN) + 16 * (NT / 32) + 0) * sizeof(double);
+  const size_t tri = STAGE_M ? static_cast<size_t>(paddedTri(maxN)) : 0;
+  const size_t sm  = (tri + static_cast<size_t>(TileLd<NC>::value) * maxN + 16 * (NT / 32)) * sizeof(double);
   if (sm > kPumMaxSmem)
     throw MapError(RBFMAP_ERR_UNSUPPORTED, "rbf-pum-direct: a cluster with " + std::to_string(maxN) + " vertices exceeds the supported cluster size.");
   if (a.dim == 3) {

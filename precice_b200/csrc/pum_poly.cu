@@ -326,6 +326,10 @@ __global__ void polySetupKernel(PumSolveArgs a, int64_t nClusters)
     for (int r = 0; r < 4; ++r)
       if (r >= p)
         g[r][r] = 1.0;
+    double normG = 0.0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      normG = fmax(normG, fabs(g[r][0]) + fabs(g[r][1]) + fabs(g[r][2]) + fabs(g[r][3]));
     // Gauss-Jordan inverse of the SPD 4x4 (no pivoting needed)
     double inv[4][4];
 #pragma unroll
@@ -352,6 +356,13 @@ __global__ void polySetupKernel(PumSolveArgs a, int64_t nClusters)
           }
         }
     }
+double normI = 0.0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      normI = fmax(normI, fabs(inv[r][0]) + fabs(inv[r][1]) + fabs(inv[r][2]) + fabs(inv[r][3]));
+    // the map kernels add one refinement step to the normal-equation solve when the centred Gram matrix is not
+    // well conditioned (nearly degenerate clusters that just passed the 1e5 test above)
+    rec.pad = (normG * normI > 1.0e3) ? 1 : 0;
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
