@@ -1,0 +1,86 @@
+"""`-m "not gpu"`: the C-ABI library loads, exports every symbol include/rbfmap.h declares, validates configurations
+on the host, and fails loudly (no CPU fallback) when there is no CUDA device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "rbfmap.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rbfmap_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    from precice_b200 import _lib
+    assert sorted(_lib.EXPORTS) == _declared_symbols()
+
+
+def test_library_exports_every_declared_symbol():
+    from precice_b200 import _lib
+    L = _lib.lib()
+    for name in _declared_symbols():
+        assert hasattr(L, name), name
+
+
+def test_struct_layouts_match_header():
+    from precice_b200 import _lib
+    cfg = _lib.Config()
+    _lib.lib().rbfmap_default_config(C.byref(cfg))
+    # XML defaults: MappingConfiguration.cpp:227-248
+    assert cfg.polynomial == _lib.POLYNOMIAL["separate"]
+    assert cfg.vertices_per_cluster == 50
+    assert cfg.relative_overlap == 0.15
+    assert cfg.project_to_input == 1
+    assert cfg.solver_rtol == 1e-9
+    assert cfg.device_id == -1
+    assert C.sizeof(_lib.Config) == 88
+    assert C.sizeof(_lib.Stats) == 120
+
+
+def test_enum_values_follow_reference():
+    from precice_b200 import _lib
+    # mapping/config/MappingConfigurationTypes.hpp:11-30, mapping/Mapping.hpp:30-35
+    assert _lib.POLYNOMIAL == {"on": 0, "off": 1, "separate": 2}
+    assert _lib.BASIS["compact-polynomial-c0"] == 0 and _lib.BASIS["compact-polynomial-c8"] == 4
+    assert _lib.BASIS["thin-plate-splines"] == 5 and _lib.BASIS["compact-tps-c2"] == 10
+    assert _lib.CONSTRAINT == {"consistent": 0, "conservative": 1, "scaled-consistent-surface": 2, "scaled-consistent-volume": 3}
+
+
+def test_no_cpu_fallback():
+    import precice_b200 as pb
+    if pb.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(pb.MappingError) as e:
+        pb.PartitionOfUnityMapping("consistent", 3, "compact-polynomial-c6", 1.0)
+    assert e.value.status == "CUDA"
+    assert "no CPU fallback" in str(e.value)
+    with pytest.raises(pb.MappingError):
+        pb.eval_basis("compact-polynomial-c6", 1.0, np.array([0.5]))
+
+
+def test_constructor_argument_checks_run_on_host():
+    """Invalid configurations are rejected with the reference's messages before any device is touched."""
+    import precice_b200 as pb
+    with pytest.raises(pb.MappingError) as e:  # BasisFunctions.hpp:519-523
+        pb.PartitionOfUnityMapping("consistent", 3, "compact-polynomial-c6", 0.0)
+    assert e.value.status == "INVALID" and "has to be larger than zero" in str(e.value)
+    with pytest.raises(pb.MappingError) as e:  # BasisFunctions.hpp:233-236
+        pb.PartitionOfUnityMapping("consistent", 3, "gaussian", -1.0)
+    assert "Shape parameter for radial-basis-function gaussian" in str(e.value)
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under precice_b200/ may reference it."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "precice_b200")):
+        if "_obj" in dirpath:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "rbf_oracle" not in text, os.path.join(dirpath, f)
