@@ -5,53 +5,13 @@
 // then the decomposition used by solveConsistent / solveConservative (:409, :427-436, :446-449).
 // (Kokkos prior art: do_batched_qr, device/KokkosPUMKernels_Impl.hpp:177-276.)
 #include "pum_device.cuh"
+#include "small_dense.cuh"
 
 #include <algorithm>
 #include <climits>
 
 namespace rbfmap {
 namespace {
-// eigenvalues of a symmetric 4x4 matrix (cyclic Jacobi, everything in registers)
-__device__ void jacobiEigenvalues4(double a[4][4], double &evMin, double &evMax)
-{
-#pragma unroll 1
-  for (int sweep = 0; sweep < 16; ++sweep) {
-    double off = 0.0;
-#pragma unroll
-    for (int p = 0; p < 3; ++p)
-#pragma unroll
-      for (int q = p + 1; q < 4; ++q)
-        off += a[p][q] * a[p][q];
-    if (off == 0.0)
-      break;
-#pragma unroll
-    for (int p = 0; p < 3; ++p)
-#pragma unroll
-      for (int q = p + 1; q < 4; ++q) {
-        const double apq = a[p][q];
-        if (fabs(apq) > 1e-300) {
-          const double theta = (a[q][q] - a[p][p]) / (2.0 * apq);
-          const double t     = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-          const double c     = 1.0 / sqrt(t * t + 1.0);
-          const double s     = t * c;
-          a[p][p] -= t * apq;
-          a[q][q] += t * apq;
-          a[p][q] = 0.0;
-          a[q][p] = 0.0;
-#pragma unroll
-          for (int r = 0; r < 4; ++r)
-            if (r != p && r != q) {
-              const double arp = a[r][p], arq = a[r][q];
-              a[r][p] = a[p][r] = c * arp - s * arq;
-              a[r][q] = a[q][r] = s * arp + c * arq;
-            }
-        }
-      }
-  }
-  evMin = fmin(fmin(a[0][0], a[1][1]), fmin(a[2][2], a[3][3]));
-  evMax = fmax(fmax(a[0][0], a[1][1]), fmax(a[2][2], a[3][3]));
-}
-
 // Column-pivoted Householder QR of a tiny rows x cols matrix (rows <= 3, cols <= 4), same pivoting and
 // rank rules as Eigen::ColPivHouseholderQR, condensed into the operator S (cols x rows) with
 // solve(b) = S b  and  transpose().solve(c) = S^T c. Only used for clusters with fewer vertices than

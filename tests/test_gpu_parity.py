@@ -341,3 +341,85 @@ def test_device_resident_path(pb, orc):
     g2 = pb.PartitionOfUnityMapping("consistent", 3, "compact-polynomial-c6", 0.3, "separate", 30)
     g2.compute_mapping(inp, out)
     assert np.array_equal(np.sort(r_dev), np.sort(g2.map(vals, 1))) or refcases.rel_l2(r_dev, g2.map(vals, 1)) <= 1e-14
+
+
+# ============================================================================================== rbf-global-direct
+SPD_GLOBAL = [(b, p, poly) for b, p, polys in refcases.GLOBAL_BASES for poly in polys
+              if b not in ("thin-plate-splines", "multiquadrics", "volume-splines")]
+GLOBAL_GPU = [(b, p, poly, c) for b, p, poly in SPD_GLOBAL for c in refcases.global_cases(b, p, poly)]
+
+
+@pytest.mark.parametrize("basis,param,poly,case", GLOBAL_GPU, ids=[f"{b}-{poly}-{c['name']}" for b, p, poly, c in GLOBAL_GPU])
+def test_global_reference_cases(pb, basis, param, poly, case):
+    """RadialBasisFctMappingTest.cpp:1295-1412 through the device backend (strictly positive definite functions)."""
+    refcases.run_global_case(case, lambda **kw: pb.RadialBasisFctMapping(**kw))
+
+
+@pytest.mark.parametrize("constraint", ["consistent", "conservative"])
+@pytest.mark.parametrize("basis,param,polynomial", [("compact-polynomial-c2", 0.5, "separate"), ("compact-polynomial-c6", 0.8, "off"),
+                                                    ("gaussian", 6.0, "separate"), ("inverse-multiquadrics", 0.3, "separate"),
+                                                    ("compact-polynomial-c0", 0.4, "separate"), ("compact-tps-c2", 0.6, "off")])
+def test_global_direct_vs_oracle(pb, orc, basis, param, polynomial, constraint):
+    n, m = 1500, 1300
+    inp = refcases.halton(n, (2, 3, 5))
+    out = refcases.halton(m, (7, 11, 13))
+    a, b = (inp, out) if constraint == "consistent" else (out, inp)
+    vals = refcases.field(a)
+    g = pb.RadialBasisFctMapping(constraint, 3, basis, param, polynomial=polynomial)
+    o = orc.GlobalMapping(constraint, 3, basis, param, polynomial=polynomial)
+    g.compute_mapping(a, b)
+    o.compute_mapping(a, b)
+    rg, ro = g.map(vals, 1), o.map(vals, 1)
+    # dense global systems are far worse conditioned than the PUM clusters: gaussian / inverse multiquadrics reach
+    # cond ~1e12+; the tolerance scales accordingly (north_star: 1e-10 for the well-conditioned compact functions)
+    tol = 1e-10 if basis.startswith("compact-polynomial") else 1e-6
+    assert refcases.rel_l2(rg, ro) <= tol, refcases.rel_l2(rg, ro)
+    v3 = np.stack([vals, 2 * vals + 1, -vals], axis=1).reshape(-1)
+    assert refcases.rel_l2(g.map(v3, 3), o.map(v3, 3)) <= tol
+    if constraint == "conservative" and polynomial != "off":  # the constant is reproduced only with a polynomial
+        assert refcases.close(rg.sum(), vals.sum(), 1e-8)
+
+
+def test_global_direct_dead_axis(pb, orc):
+    n = 700
+    inp = refcases.halton(n, (2, 3, 5))
+    out = refcases.halton(n, (7, 11, 13))
+    vals = refcases.field(inp)
+    for dead in ((False, True, False), (False, False, True)):
+        g = pb.RadialBasisFctMapping("consistent", 3, "compact-polynomial-c2", 0.6, dead_axis=dead, polynomial="separate")
+        o = orc.GlobalMapping("consistent", 3, "compact-polynomial-c2", 0.6, dead_axis=dead, polynomial="separate")
+        # with a dead axis the projected vertices nearly coincide -> use a mesh that stays unisolvent in the projection
+        inp2 = inp.copy()
+        inp2[:, [i for i, d in enumerate(dead) if d][0]] *= 1e-3
+        g.compute_mapping(inp2, out)
+        o.compute_mapping(inp2, out)
+        assert refcases.rel_l2(g.map(vals, 1), o.map(vals, 1)) <= 1e-7
+
+
+def test_global_direct_2d(pb, orc):
+    n = 900
+    inp = refcases.halton(n, (2, 3))
+    out = refcases.halton(n, (7, 11))
+    vals = refcases.field(inp)
+    for constraint in ("consistent", "conservative"):
+        g = pb.RadialBasisFctMapping(constraint, 2, "compact-polynomial-c4", 0.5, polynomial="separate")
+        o = orc.GlobalMapping(constraint, 2, "compact-polynomial-c4", 0.5, polynomial="separate")
+        a, b = (inp, out) if constraint == "consistent" else (out, inp)
+        g.compute_mapping(a, b)
+        o.compute_mapping(a, b)
+        v = refcases.field(a)
+        assert refcases.rel_l2(g.map(v, 1), o.map(v, 1)) <= 1e-9
+
+
+def test_global_direct_errors(pb):
+    with pytest.raises(pb.MappingError) as e:  # RadialBasisFctMapping.hpp:90
+        pb.RadialBasisFctMapping("consistent", 3, "compact-polynomial-c2", 0.5, polynomial="on")
+    assert "integrated polynomial" in str(e.value)
+    with pytest.raises(pb.MappingError):  # RadialBasisFctBaseMapping.hpp:100-108
+        pb.RadialBasisFctMapping("consistent", 2, "compact-polynomial-c2", 0.5, dead_axis=(True, True, False))
+    inp = refcases.halton(300, (2, 3, 5))
+    dup = np.concatenate([inp, inp[:5]])
+    g = pb.RadialBasisFctMapping("consistent", 3, "compact-polynomial-c2", 0.5)
+    with pytest.raises(pb.MappingError) as e:  # RadialBasisFctSolver.hpp:360-365
+        g.compute_mapping(dup, inp)
+    assert e.value.status == "SINGULAR" and "is not invertable" in str(e.value)
