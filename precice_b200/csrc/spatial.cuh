@@ -56,20 +56,20 @@ __device__ __forceinline__ int cellCoordUnclamped(double p, double o, double ih,
   return static_cast<int>(t);
 }
 
-// Calls f(pos, valid) for every binned point in the 3x3x3 cell neighbourhood of (cx,cy,cz), warp-cooperatively:
+// Calls f(pos, valid) for every binned point in the (2H+1)^3 cell neighbourhood of (cx,cy,cz), warp-cooperatively:
 // all 32 lanes call f together (valid == false on padding lanes) so f may use warp collectives.
 // f returns true to stop early (must be warp-uniform).
-template <typename F>
+template <int H = 1, typename F>
 __device__ __forceinline__ void forNeighbourhoodWarp(const BinGridView &g, double cx, double cy, double cz, int lane, F &&f)
 {
   const int ix = cellCoordUnclamped(cx, g.ox, g.ihx, g.nx);
   const int iy = cellCoordUnclamped(cy, g.oy, g.ihy, g.ny);
   const int iz = cellCoordUnclamped(cz, g.oz, g.ihz, g.nz);
-  const int z0 = max(iz - 1, 0), z1 = min(iz + 1, g.nz - 1);
+  const int z0 = max(iz - H, 0), z1 = min(iz + H, g.nz - 1);
   if (z0 > z1)
     return;
-  for (int x = max(ix - 1, 0); x <= min(ix + 1, g.nx - 1); ++x)
-    for (int y = max(iy - 1, 0); y <= min(iy + 1, g.ny - 1); ++y) {
+  for (int x = max(ix - H, 0); x <= min(ix + H, g.nx - 1); ++x)
+    for (int y = max(iy - H, 0); y <= min(iy + H, g.ny - 1); ++y) {
       const int row = (x * g.ny + y) * g.nz;
       const int beg = g.cellStart[row + z0], end = g.cellStart[row + z1 + 1];
       for (int base = beg; base < end; base += 32) {

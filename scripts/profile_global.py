@@ -34,7 +34,7 @@ for constraint, dims in (("consistent", 1), ("conservative", 3)):
         st = m.stats()
         n3 = (a.n ** 3) / 3.0
         print(f"{constraint} dims={dims} step {s}: compute {1e3*(t1-t0):.1f} ms (factor+assembly {st['ms_assembly_factor']:.1f} ms = "
-              f"{n3/ (st['ms_assembly_factor']*1e-3)/1e12:.2f} TFLOP/s Cholesky-equivalent) map {1e3*(t2-t1):.1f} ms launches {st['kernel_launches']} "
+              f"{n3/ (max(st['ms_assembly_factor'],1e-9)*1e-3)/1e12:.2f} TFLOP/s Cholesky-equivalent) map {1e3*(t2-t1):.1f} ms launches {st['kernel_launches']} "
               f"iters {st['iterations']} res {st['residual']:.2e}", flush=True)
     if constraint == "consistent":
         # interpolation sanity: mapped field vs the analytic field at the output vertices

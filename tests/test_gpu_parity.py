@@ -423,3 +423,51 @@ def test_global_direct_errors(pb):
     with pytest.raises(pb.MappingError) as e:  # RadialBasisFctSolver.hpp:360-365
         g.compute_mapping(dup, inp)
     assert e.value.status == "SINGULAR" and "is not invertable" in str(e.value)
+
+
+# ============================================================================================== rbf-global-iterative
+@pytest.mark.parametrize("constraint", ["consistent", "conservative"])
+@pytest.mark.parametrize("basis,param,polynomial", [("compact-polynomial-c2", 0.25, "separate"), ("compact-polynomial-c6", 0.3, "off"),
+                                                    ("gaussian", 30.0, "separate"), ("compact-polynomial-c0", 0.2, "separate")])
+def test_global_iterative_vs_direct_oracle(pb, orc, basis, param, polynomial, constraint):
+    """Matrix-free CG against the oracle's direct solve: agreement to solver tolerance (north_star), here
+    rtol 1e-12 so that cond * rtol stays below the asserted 1e-7."""
+    n, m = 2500, 2200
+    inp = refcases.halton(n, (2, 3, 5))
+    out = refcases.halton(m, (7, 11, 13))
+    a, b = (inp, out) if constraint == "consistent" else (out, inp)
+    vals = refcases.field(a)
+    g = pb.RadialBasisFctMapping(constraint, 3, basis, param, polynomial=polynomial, solver="iterative", solver_rtol=1e-12)
+    o = orc.GlobalMapping(constraint, 3, basis, param, polynomial=polynomial)
+    g.compute_mapping(a, b)
+    o.compute_mapping(a, b)
+    rg, ro = g.map(vals, 1), o.map(vals, 1)
+    st = g.stats()
+    assert 0 < st["iterations"] < 5000 and st["residual"] <= 1e-12
+    assert refcases.rel_l2(rg, ro) <= 1e-7, refcases.rel_l2(rg, ro)
+    v3 = np.stack([vals, 2 * vals + 1, -vals], axis=1).reshape(-1)
+    assert refcases.rel_l2(g.map(v3, 3), o.map(v3, 3)) <= 1e-7
+    # warm start (GinkgoRadialBasisFctSolver.hpp:218-221, 437): mapping the same data again converges immediately
+    g.map(v3, 3)
+    assert g.stats()["iterations"] <= 2
+
+
+def test_global_iterative_matches_device_direct(pb):
+    n = 3000
+    inp = refcases.halton(n, (2, 3, 5))
+    out = refcases.halton(n, (7, 11, 13))
+    vals = refcases.field(inp)
+    d = pb.RadialBasisFctMapping("consistent", 3, "compact-polynomial-c4", 0.25, polynomial="separate")
+    i = pb.RadialBasisFctMapping("consistent", 3, "compact-polynomial-c4", 0.25, polynomial="separate", solver="iterative", solver_rtol=1e-11)
+    d.compute_mapping(inp, out)
+    i.compute_mapping(inp, out)
+    assert refcases.rel_l2(i.map(vals, 1), d.map(vals, 1)) <= 1e-7
+
+
+def test_global_iterative_not_converged_error(pb):
+    inp = refcases.halton(2000, (2, 3, 5))
+    g = pb.RadialBasisFctMapping("consistent", 3, "compact-polynomial-c6", 0.4, solver="iterative", solver_rtol=1e-14, max_iterations=3)
+    g.compute_mapping(inp, inp)
+    with pytest.raises(pb.MappingError) as e:
+        g.map(refcases.field(inp), 1)
+    assert e.value.status == "NOT_CONVERGED"
