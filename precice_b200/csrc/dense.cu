@@ -698,6 +698,27 @@ bool denseCholesky(double *dC, int64_t np, double *dInvDiag, cudaStream_t s)
   return failed == INT_MAX;
 }
 
+// C(rows x cols) -= A(rows x K) * B(cols x K)^T ; rows, cols multiples of 64, K multiple of 32
+void denseGemmNtSubtract(const double *A, int64_t lda, const double *B, int64_t ldb, double *C, int64_t ldc, int64_t rows, int64_t cols, int K, cudaStream_t s)
+{
+  GemmArgs g{};
+  g.A = A;
+  g.lda = lda;
+  g.B = B;
+  g.ldb = ldb;
+  g.C = C;
+  g.ldc = ldc;
+  g.K = K;
+  g.tilesM = divUp(rows, 128);
+  g.tilesN = static_cast<int>(cols / 64);
+  g.rowOrigin = 0;
+  g.colOrigin = 0;
+  g.lower = 0;
+  g.subtract = 1;
+  g.validRows = rows;
+  launchGemm<64>(g, s);
+}
+
 void denseCholeskySolve(const double *dL, int64_t np, const double *dInvDiag, double *dB, int64_t ldb, int nrhs, cudaStream_t s)
 {
   for (int c0 = 0; c0 < nrhs;) {

@@ -31,6 +31,11 @@ bool denseCholesky(double *dC, int64_t np, double *dInvDiag, cudaStream_t s);
 // Solves L L^T X = B in place for nrhs right-hand sides stored as separate vectors B[c*ldb + i] (ldb >= np).
 void denseCholeskySolve(const double *dL, int64_t np, const double *dInvDiag, double *dB, int64_t ldb, int nrhs, cudaStream_t s);
 
+// General (not positive definite) systems: in-place LU with partial pivoting of the np x np matrix (np multiple of 256),
+// dPiv receives np row interchanges; returns false if numerically singular. Solve works on planar right-hand sides.
+bool denseLu(double *dA, int64_t np, int *dPiv, cudaStream_t s);
+void denseLuSolve(const double *dLU, int64_t np, const int *dPiv, double *dB, int64_t ldb, int nrhs, cudaStream_t s);
+
 // rowOut[c*ldo + i] (=|+=) sum_j phi(|row_i - col_j|) colVals[c*ldv + j]  for i < nRows, j < nCols, c < nrhs
 void denseEvaluate(const RbfParams &rbf, const AxisMask &mask, const double *dRowXyz, int64_t nRows, const double *dColXyz, int64_t nCols,
                    const double *dColVals, int64_t ldv, double *dRowOut, int64_t ldo, int nrhs, bool accumulate, cudaStream_t s);

@@ -127,14 +127,16 @@ __global__ void centredGramKernel(const double *__restrict__ xyz, long long n, P
 
 // t[k * nrhs + c] += sum_i Q(i,k) (vals[c*ld + i] + sgn * (Q beta)(i, c))
 __global__ void polyProjectKernel(const double *__restrict__ xyz, long long n, PolyGlobal pg, const double *__restrict__ vals, long long ld, int nrhs,
-                                  const double *__restrict__ beta, double sgn, double *__restrict__ t)
+                                  const double *__restrict__ beta, double sgn, double *__restrict__ t, long long tk = -1, long long tc = 1)
 {
+  if (tk < 0)
+    tk = nrhs; // default layout t[k * nrhs + c]
   for (int c = 0; c < nrhs; ++c) {
     double acc[4] = {0, 0, 0, 0};
     double b[4]   = {0, 0, 0, 0};
     if (beta)
       for (int k = 0; k < 4; ++k)
-        b[k] = beta[k * nrhs + c];
+        b[k] = k < pg.p ? beta[k * nrhs + c] : 0.0;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
       double q[4];
       polyRowG(pg, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], q);
@@ -151,7 +153,8 @@ __global__ void polyProjectKernel(const double *__restrict__ xyz, long long n, P
     if ((threadIdx.x & 31) == 0)
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        atomicAdd(&t[k * nrhs + c], acc[k]);
+        if (k < pg.p)
+          atomicAdd(&t[k * tk + c * tc], acc[k]);
   }
 }
 
@@ -174,8 +177,10 @@ __global__ void polySolveKernel(PolyGlobal pg, const double *__restrict__ a, con
 
 // vals[c*ld + i] += sgn * (Q beta)(i, c)
 __global__ void polyApplyKernel(const double *__restrict__ xyz, long long n, PolyGlobal pg, const double *__restrict__ beta, int nrhs, double sgn,
-                                double *__restrict__ vals, long long ld)
+                                double *__restrict__ vals, long long ld, long long bk = -1, long long bc = 1)
 {
+  if (bk < 0)
+    bk = nrhs; // default layout beta[k * nrhs + c]
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= n)
     return;
@@ -185,9 +190,27 @@ __global__ void polyApplyKernel(const double *__restrict__ xyz, long long n, Pol
     double s = 0.0;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      s += q[k] * beta[k * nrhs + c];
+      if (k < pg.p)
+        s += q[k] * beta[k * bk + c * bc];
     vals[c * ld + i] += sgn * s;
   }
+}
+
+// integrated polynomial (RadialBasisFctSolver.hpp:140-162): C(i, n+q) = C(n+q, i) = P(i, q), zero p x p block
+__global__ void polyBlockKernel(const double *__restrict__ xyz, long long n, PolyGlobal pg, double *__restrict__ C, long long ld)
+{
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i < n) {
+    double q[4];
+    polyRowG(pg, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], q);
+    for (int k = 0; k < pg.p; ++k) {
+      C[i + (n + k) * ld] = q[k];
+      C[(n + k) + i * ld] = q[k];
+    }
+  }
+  if (i < pg.p)
+    for (int k = 0; k < pg.p; ++k)
+      C[(n + i) + (n + k) * ld] = 0.0;
 }
 
 inline int reduceGrid(int64_t n) { return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, static_cast<int64_t>(smCount()) * 8))); }
@@ -208,8 +231,7 @@ public:
     if (!anyAlive)
       throw MapError(RBFMAP_ERR_INVALID, "You cannot set all axes to dead for an RBF mapping. Please remove one of the respective mapping's "
                                          "\"x-dead\", \"y-dead\", or \"z-dead\" attributes.");
-    if (!basisIsSpd(cfg.basis))
-      throw MapError(RBFMAP_ERR_UNSUPPORTED, "rbf-global-direct on the device currently requires a strictly positive definite basis function.");
+    _spd = basisIsSpd(cfg.basis);
     for (int d = 0; d < 3; ++d)
       _active[d] = d < cfg.dimensions && cfg.dead_axis[d] == 0;
   }
@@ -225,6 +247,7 @@ public:
     _outXyz.release();
     _C.release();
     _invDiag.release();
+    _piv.release();
     _computed = false;
     stats     = rbfmap_stats{};
   }
@@ -233,18 +256,31 @@ private:
   void     setupPolynomial();
   AxisMask mask() const { return AxisMask{_active[0] ? 1.0 : 0.0, _active[1] ? 1.0 : 0.0, _active[2] ? 1.0 : 0.0}; }
 
+  void solveSystem(double *dB, int nrhs)
+  {
+    if (_spd)
+      denseCholeskySolve(_C.p, _np, _invDiag.p, dB, _np, nrhs, _stream);
+    else
+      denseLuSolve(_C.p, _np, _piv.p, dB, _np, nrhs, _stream);
+  }
+
+  bool           _spd       = true;
   bool           _active[3] = {true, true, true};
   DevBuf<double> _inXyz, _outXyz;
   int64_t        _nIn = 0, _nOut = 0, _np = 0;
   DevBuf<double> _C, _invDiag;
-  PolyGlobal     _poly{};
+  DevBuf<int>    _piv;
+  PolyGlobal     _poly{};   // separated polynomial
+  PolyGlobal     _polyOn{}; // integrated polynomial (mode 0 = none)
 };
 
 void GlobalDirectMapping::setupPolynomial()
 {
-  _poly      = PolyGlobal{};
-  _poly.mode = 0;
-  if (_cfg.polynomial != RBFMAP_POLYNOMIAL_SEPARATE)
+  _poly        = PolyGlobal{};
+  _poly.mode   = 0;
+  _polyOn      = PolyGlobal{};
+  _polyOn.mode = 0;
+  if (_cfg.polynomial == RBFMAP_POLYNOMIAL_OFF)
     return;
   DevBuf<double>             m16;
   DevBuf<unsigned long long> ext;
@@ -265,8 +301,25 @@ void GlobalDirectMapping::setupPolynomial()
     lo[d] = decodeOrdered(he[d]);
     hi[d] = decodeOrdered(he[3 + d]);
   }
-  // RadialBasisFctSolver.hpp:383-402: drop the active axis with the smallest extent while cond(Q) > 1e5
   int mask = (_active[0] ? 1 : 0) | (_active[1] ? 2 : 0) | (_active[2] ? 4 : 0);
+  if (_cfg.polynomial == RBFMAP_POLYNOMIAL_ON) {
+    // integrated polynomial over all active axes (no axis dropping, RadialBasisFctSolver.hpp:140-162). The columns are
+    // written in the centred / scaled basis: it spans the same space as [1, x_active...], so the interpolant is the
+    // same function, while the augmented matrix is far better scaled.
+    _polyOn.mode = 1;
+    _polyOn.mask = mask;
+    _polyOn.p    = 1 + ((mask & 1) ? 1 : 0) + ((mask & 2) ? 1 : 0) + ((mask & 4) ? 1 : 0);
+    _polyOn.cx   = 0.5 * (lo[0] + hi[0]);
+    _polyOn.cy   = 0.5 * (lo[1] + hi[1]);
+    _polyOn.cz   = 0.5 * (lo[2] + hi[2]);
+    double sp    = 0.0;
+    for (int d = 0; d < 3; ++d)
+      if (mask & (1 << d))
+        sp = std::max(sp, hi[d] - lo[d]);
+    _polyOn.scale = sp > 0.0 ? 2.0 / sp : 1.0;
+    return;
+  }
+  // RadialBasisFctSolver.hpp:383-402: drop the active axis with the smallest extent while cond(Q) > 1e5
   int p    = 1;
   while (true) {
     p = 1 + ((mask & 1) ? 1 : 0) + ((mask & 2) ? 1 : 0) + ((mask & 4) ? 1 : 0);
@@ -356,17 +409,34 @@ void GlobalDirectMapping::computeMapping(const double *dInputXyz, int64_t nInput
   }
   if (_nIn > 200000)
     throw MapError(RBFMAP_ERR_UNSUPPORTED, "rbf-global-direct: the dense system does not fit one device (use rbf-pum-direct or rbf-global-iterative).");
-  _np = padTo(_nIn, kPanelNb);
+  setupPolynomial();
+  trace.phase("polynomial");
+  const int64_t nSys = _nIn + (_polyOn.mode ? _polyOn.p : 0);
+  if (_polyOn.mode && _nIn < _polyOn.p) // PRECICE_ASSERT(inputSize >= 1 + polyparams), RadialBasisFctSolver.hpp:180
+    throw MapError(RBFMAP_ERR_INVALID, "The integrated polynomial needs at least as many vertices as polynomial parameters.");
+  _np = padTo(nSys, kPanelNb);
   _C.alloc(static_cast<size_t>(_np) * _np + 256);
-  _invDiag.alloc(static_cast<size_t>(_np / kDiagNb) * kDiagNb * kDiagNb);
   trace.phase("copy + alloc");
   EventTimer tf(_stream);
   tf.start();
-  denseAssemble(_rbf, mask(), _inXyz.p, _nIn, _C.p, _np, true, _stream);
-  trace.phase("assemble C");
-  const bool ok = denseCholesky(_C.p, _np, _invDiag.p, _stream);
+  bool ok;
+  if (_spd) {
+    _invDiag.alloc(static_cast<size_t>(_np / kDiagNb) * kDiagNb * kDiagNb);
+    denseAssemble(_rbf, mask(), _inXyz.p, _nIn, _C.p, _np, true, _stream);
+    trace.phase("assemble C");
+    ok = denseCholesky(_C.p, _np, _invDiag.p, _stream);
+  } else {
+    _piv.alloc(_np);
+    denseAssemble(_rbf, mask(), _inXyz.p, _nIn, _C.p, _np, false, _stream);
+    if (_polyOn.mode) {
+      polyBlockKernel<<<divUp(_nIn, 256), 256, 0, _stream>>>(_inXyz.p, _nIn, _polyOn, _C.p, _np);
+      RBF_LAUNCHED();
+    }
+    trace.phase("assemble C");
+    ok = denseLu(_C.p, _np, _piv.p, _stream);
+  }
   stats.ms_assembly_factor = tf.stop();
-  trace.phase("cholesky");
+  trace.phase("factorisation");
   if (!ok) {
     // RadialBasisFctSolver.hpp:360-365
     const char *inName = cons ? "output" : "input", *outName = cons ? "input" : "output";
@@ -375,8 +445,6 @@ void GlobalDirectMapping::computeMapping(const double *dInputXyz, int64_t nInput
                                             "Please check if your coupling meshes are correct (e.g. no vertices are duplicated) or reconfigure "
                                             "your basis-function (e.g. reduce the support-radius).");
   }
-  setupPolynomial();
-  trace.phase("polynomial");
   stats.device_bytes       = static_cast<int64_t>(_C.bytes() + _invDiag.bytes() + _inXyz.bytes() + _outXyz.bytes());
   stats.ms_compute_kernels = whole.stop();
   stats.kernel_launches    = g_launches;
@@ -413,8 +481,12 @@ void GlobalDirectMapping::mapConsistent(const double *dIn, int dims, double *dOu
       polyApplyKernel<<<divUp(_nIn, 256), 256, 0, _stream>>>(_inXyz.p, _nIn, _poly, beta.p, dims, -1.0, f.p, _np);
       RBF_LAUNCHED();
     }
-    denseCholeskySolve(_C.p, _np, _invDiag.p, f.p, _np, dims, _stream);
+    solveSystem(f.p, dims);
     denseEvaluate(_rbf, mask(), _outXyz.p, _nOut, _inXyz.p, _nIn, f.p, _np, o.p, _nOut, dims, false, _stream);
+    if (_polyOn.mode) { // out += P_out lambda_poly (the last p rows of the solution, RadialBasisFctSolver.hpp:238-240)
+      polyApplyKernel<<<divUp(_nOut, 256), 256, 0, _stream>>>(_outXyz.p, _nOut, _polyOn, f.p + _nIn, dims, 1.0, o.p, _nOut, 1, _np);
+      RBF_LAUNCHED();
+    }
     if (_poly.mode == 1) {
       polyApplyKernel<<<divUp(_nOut, 256), 256, 0, _stream>>>(_outXyz.p, _nOut, _poly, beta.p, dims, 1.0, o.p, _nOut);
       RBF_LAUNCHED();
@@ -446,7 +518,11 @@ void GlobalDirectMapping::mapConservative(const double *dIn, int dims, double *d
     RBF_CUDA(cudaMemsetAsync(mu.p, 0, static_cast<size_t>(_np) * dims * sizeof(double), _stream));
     // Au = A^T u
     denseEvaluate(_rbf, mask(), _inXyz.p, _nIn, _outXyz.p, _nOut, u.p, _nOut, mu.p, _np, dims, false, _stream);
-    denseCholeskySolve(_C.p, _np, _invDiag.p, mu.p, _np, dims, _stream);
+    if (_polyOn.mode) { // the polynomial rows of A^T u: P_out^T u
+      polyProjectKernel<<<reduceGrid(_nOut), 256, 0, _stream>>>(_outXyz.p, _nOut, _polyOn, u.p, _nOut, dims, nullptr, 0.0, mu.p + _nIn, 1, _np);
+      RBF_LAUNCHED();
+    }
+    solveSystem(mu.p, dims);
     if (_poly.mode == 1) {
       eps.alloc(4 * dims);
       tt.alloc(4 * dims);

@@ -344,14 +344,13 @@ def test_device_resident_path(pb, orc):
 
 
 # ============================================================================================== rbf-global-direct
-SPD_GLOBAL = [(b, p, poly) for b, p, polys in refcases.GLOBAL_BASES for poly in polys
-              if b not in ("thin-plate-splines", "multiquadrics", "volume-splines")]
-GLOBAL_GPU = [(b, p, poly, c) for b, p, poly in SPD_GLOBAL for c in refcases.global_cases(b, p, poly)]
+GLOBAL_GPU = [(b, p, poly, c) for b, p, polys in refcases.GLOBAL_BASES for poly in polys for c in refcases.global_cases(b, p, poly)]
 
 
 @pytest.mark.parametrize("basis,param,poly,case", GLOBAL_GPU, ids=[f"{b}-{poly}-{c['name']}" for b, p, poly, c in GLOBAL_GPU])
 def test_global_reference_cases(pb, basis, param, poly, case):
-    """RadialBasisFctMappingTest.cpp:1295-1412 through the device backend (strictly positive definite functions)."""
+    """RadialBasisFctMappingTest.cpp:1295-1412 through the device backend: all eleven basis functions, integrated and
+    separated polynomial."""
     refcases.run_global_case(case, lambda **kw: pb.RadialBasisFctMapping(**kw))
 
 
@@ -471,3 +470,34 @@ def test_global_iterative_not_converged_error(pb):
     with pytest.raises(pb.MappingError) as e:
         g.map(refcases.field(inp), 1)
     assert e.value.status == "NOT_CONVERGED"
+
+
+DEAD_GPU = refcases.dead_axis_cases()
+
+
+@pytest.mark.parametrize("case", DEAD_GPU, ids=[c["name"] for c in DEAD_GPU])
+def test_global_dead_axis_goldens(pb, case):
+    """RadialBasisFctMappingTest.cpp:1416-1546: thin-plate splines (not positive definite -> LU path), y axis dead,
+    polynomial on / off / separate, golden literals."""
+    refcases.run_global_case(case, lambda **kw: pb.RadialBasisFctMapping(**kw))
+
+
+@pytest.mark.parametrize("constraint", ["consistent", "conservative"])
+@pytest.mark.parametrize("basis,param,polynomial", [("thin-plate-splines", 0.0, "on"), ("thin-plate-splines", 0.0, "separate"),
+                                                    ("multiquadrics", 0.1, "on"), ("volume-splines", 0.0, "separate")])
+def test_global_direct_nonspd_vs_oracle(pb, orc, basis, param, polynomial, constraint):
+    """BASELINE.json configs[0] family: rbf-global-direct thin-plate-splines on 2-D non-matching Halton meshes (and the
+    other functions without positive definiteness), LU on the device against the oracle's pivoted QR."""
+    n, m = 1100, 1000
+    inp = refcases.halton(n, (2, 3))
+    out = refcases.halton(m, (7, 11))
+    a, b = (inp, out) if constraint == "consistent" else (out, inp)
+    vals = refcases.field(a)
+    g = pb.RadialBasisFctMapping(constraint, 2, basis, param, polynomial=polynomial)
+    o = orc.GlobalMapping(constraint, 2, basis, param, polynomial=polynomial)
+    g.compute_mapping(a, b)
+    o.compute_mapping(a, b)
+    rg, ro = g.map(vals, 1), o.map(vals, 1)
+    assert refcases.rel_l2(rg, ro) <= 1e-7, refcases.rel_l2(rg, ro)  # cond(C) ~ 1e8..1e10 for these global functions
+    if constraint == "conservative":
+        assert refcases.close(rg.sum(), vals.sum(), 1e-7)
