@@ -118,6 +118,19 @@ int rbfmap_map_conservative(rbfmap_handle *h, const double *in, int dims, double
 int rbfmap_compute_mapping_device(rbfmap_handle *h, const double *d_input_xyz, int64_t n_input, const double *d_output_xyz, int64_t n_output);
 int rbfmap_map_device(rbfmap_handle *h, const double *d_in, int dims, double *d_out);
 
+/* Multi-GPU, one process per GPU. rbf-pum-direct shards by mesh partition (one mapping per rank, no
+ * communication, exactly the reference's parallel PUM: BatchedRBFSolver.hpp:29-31) and rbf-global-direct stays on one
+ * device, so neither needs these calls. rbf-global-iterative shards the rows of its matrix-free CG operator: every rank
+ * is given the same (replicated) meshes and values, owns a contiguous slice of the cell-ordered rows, and the library
+ * all-gathers the direction vector and all-reduces the dot products with NCCL over NVLink (the role of PETSc's
+ * distributed KSP in PetRadialBasisFctMapping.hpp:246-263, 629-633). Rank 0 obtains the 128-byte NCCL id, the host
+ * application broadcasts it (MPI / sockets / torch.distributed), then every rank calls rbfmap_distributed_init before
+ * computeMapping. All ranks must make the same sequence of calls. */
+int rbfmap_nccl_unique_id(char id[128]);
+int rbfmap_distributed_init(rbfmap_handle *h, const char id[128], int rank, int world);
+/* The contiguous slice [*begin, *end) of n rows owned by `rank` (host-side helper, no device needed). */
+int rbfmap_partition_rows(int64_t n, int world, int rank, int64_t *begin, int64_t *end);
+
 /* Mapping::clear() (Mapping.hpp:134), Mapping::hasComputedMapping(), destructor, Mapping::getName(). */
 int         rbfmap_clear(rbfmap_handle *h);
 int         rbfmap_has_computed_mapping(const rbfmap_handle *h);

@@ -31,7 +31,8 @@ EXPORTS = [
     "rbfmap_map_conservative", "rbfmap_compute_mapping_device", "rbfmap_map_device", "rbfmap_clear",
     "rbfmap_has_computed_mapping", "rbfmap_destroy", "rbfmap_get_name", "rbfmap_last_error", "rbfmap_get_stats",
     "rbfmap_pum_get_clusters", "rbfmap_pum_get_cluster_ids", "rbfmap_eval_basis", "rbfmap_device_count",
-    "rbfmap_device_info", "rbfmap_measure_fp64_peak", "rbfmap_debug_dist_sqrt",
+    "rbfmap_device_info", "rbfmap_measure_fp64_peak", "rbfmap_debug_dist_sqrt", "rbfmap_nccl_unique_id", "rbfmap_distributed_init",
+    "rbfmap_partition_rows",
 ]
 
 
@@ -99,5 +100,8 @@ def lib():
         L.rbfmap_device_info.argtypes = [C.c_int, ip, ip, ip, C.POINTER(C.c_int64)]
         L.rbfmap_measure_fp64_peak.argtypes = [dp, dp]
         L.rbfmap_debug_dist_sqrt.argtypes = [dp, C.c_int64, dp]
+        L.rbfmap_nccl_unique_id.argtypes = [C.c_char_p]
+        L.rbfmap_distributed_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int]
+        L.rbfmap_partition_rows.argtypes = [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         _lib = L
     return _lib

@@ -1,5 +1,6 @@
 // capi.cu — the extern "C" boundary declared in include/rbfmap.h.
 #include "mapping.cuh"
+#include "nccl_dyn.cuh"
 #include "pum.cuh"
 
 #include <cmath>
@@ -310,6 +311,32 @@ int rbfmap_map_device(rbfmap_handle *h, const double *d_in, int dims, double *d_
       throw MapError(RBFMAP_ERR_STATE, "The mapping has not been computed; call computeMapping() first.");
     mapDeviceImpl(h, 0, d_in, dims, d_out);
   });
+}
+
+int rbfmap_nccl_unique_id(char id[128])
+{
+  return guarded(nullptr, [&] {
+    ncclUniqueId u;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    RBF_NCCL(ncclApi().GetUniqueId(&u));
+    std::memcpy(id, &u, sizeof(u));
+  });
+}
+
+int rbfmap_distributed_init(rbfmap_handle *h, const char id[128], int rank, int world)
+{
+  if (!h)
+    return RBFMAP_ERR_INVALID;
+  return guarded(h, [&] { h->impl->distributedInit(id, rank, world); });
+}
+
+int rbfmap_partition_rows(int64_t n, int world, int rank, int64_t *begin, int64_t *end)
+{
+  if (n < 0 || world < 1 || rank < 0 || rank >= world || !begin || !end)
+    return RBFMAP_ERR_INVALID;
+  int64_t slice;
+  partitionRows(n, world, rank, *begin, *end, slice);
+  return RBFMAP_OK;
 }
 
 int rbfmap_clear(rbfmap_handle *h)

@@ -11,6 +11,7 @@
 // Functions without compact support fall back to the dense matrix-free product of dense.cu.
 #include "dense.cuh"
 #include "mapping.cuh"
+#include "nccl_dyn.cuh"
 #include "pum_device.cuh"
 #include "small_dense.cuh"
 #include "spatial.cuh"
@@ -18,6 +19,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstddef>
+#include <cstring>
 
 namespace rbfmap {
 namespace {
@@ -31,12 +33,12 @@ struct CgScalars {
 
 // y[c][r] = sum_j phi(|row_r - col_j|) x[c][j] over the (2H+1)^3 cell neighbourhood; rows and columns in cell order
 template <int KIND, int NC, int H>
-__global__ void __launch_bounds__(256) sparseApplyKernel(RbfParams rbf, double support2, BinGridView rows, long long nRows, BinGridView cols,
+__global__ void __launch_bounds__(256) sparseApplyKernel(RbfParams rbf, double support2, BinGridView rows, long long rowBegin, long long nRows, BinGridView cols,
                                                         const double *__restrict__ x, long long ldx, double *__restrict__ y, long long ldy,
                                                         const double *__restrict__ dotWith, long long ldd, double *__restrict__ dotOut)
 {
   __shared__ double dots[NC][8];
-  const long long r    = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long r    = rowBegin + ((blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5);
   const int       lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const bool      live = r < nRows;
   const long long rr   = live ? r : nRows - 1;
@@ -412,6 +414,27 @@ public:
   void computeMapping(const double *dInputXyz, int64_t nInput, const double *dOutputXyz, int64_t nOutput) override;
   void mapConsistent(const double *dIn, int dims, double *dOut) override { map(false, dIn, dims, dOut); }
   void mapConservative(const double *dIn, int dims, double *dOut) override { map(true, dIn, dims, dOut); }
+  ~GlobalIterativeMapping() override
+  {
+    if (_comm)
+      ncclApi().CommDestroy(_comm);
+  }
+  void distributedInit(const char *uniqueId, int rank, int world) override
+  {
+    if (world < 1 || rank < 0 || rank >= world)
+      throw MapError(RBFMAP_ERR_INVALID, "invalid rank / world size");
+    if (_comm) {
+      ncclApi().CommDestroy(_comm);
+      _comm = nullptr;
+    }
+    _rank  = rank;
+    _world = world;
+    if (world > 1) {
+      ncclUniqueId id;
+      std::memcpy(&id, uniqueId, sizeof(id));
+      RBF_NCCL(ncclApi().CommInitRank(&_comm, world, id, rank));
+    }
+  }
   void clear() override
   {
     _inGrid  = BinGrid();
@@ -425,11 +448,18 @@ public:
 private:
   void map(bool conservative, const double *dIn, int dims, double *dOut);
   // y (rows of `rows`) = Phi(rows, cols) x (cols); optional fused dot product with `dotWith`
-  void apply(const BinGrid &rows, const BinGrid &cols, const double *x, int64_t ldx, double *y, int64_t ldy, int nc, const double *dotWith, int64_t ldd,
-             double *dotOut);
+  // rows [rb, re) only (this rank's slice); y and dotWith are indexed by the global row
+  void apply(const BinGrid &rows, int64_t rb, int64_t re, const BinGrid &cols, const double *x, int64_t ldx, double *y, int64_t ldy, int nc,
+             const double *dotWith, int64_t ldd, double *dotOut);
+  // all ranks contribute their slice [rank * slice, ...) of every component; buffers are padded to world * slice
+  void allGatherSlices(double *v, int64_t ld, int nc, int64_t slice);
+  void allReduceScalars(double *d, int count);
   void cg(double *b /*in: rhs, out: destroyed*/, double *x /*in: guess, out: solution*/, int nc);
   void setupPolynomial();
 
+  ncclComm_t     _comm  = nullptr;
+  int            _rank = 0, _world = 1;
+  int64_t        _ldIn = 0; // leading dimension of the in-mesh vectors: world * slice
   int            _dead = 0;
   int64_t        _nIn = 0, _nOut = 0;
   bool           _sparse = true;
@@ -440,28 +470,46 @@ private:
   int            _guessDims = 0;
 };
 
-void GlobalIterativeMapping::apply(const BinGrid &rows, const BinGrid &cols, const double *x, int64_t ldx, double *y, int64_t ldy, int nc,
-                                   const double *dotWith, int64_t ldd, double *dotOut)
+void GlobalIterativeMapping::apply(const BinGrid &rows, int64_t rb, int64_t re, const BinGrid &cols, const double *x, int64_t ldx, double *y, int64_t ldy,
+                                   int nc, const double *dotWith, int64_t ldd, double *dotOut)
 {
-  if (rows.n <= 0)
+  if (re <= rb)
     return;
   if (!_sparse) {
     AxisMask all{1.0, 1.0, 1.0};
-    denseEvaluate(_rbf, all, rows.xyz.p, rows.n, cols.xyz.p, cols.n, x, ldx, y, ldy, nc, false, _stream);
+    denseEvaluate(_rbf, all, rows.xyz.p + 3 * rb, re - rb, cols.xyz.p, cols.n, x, ldx, y + rb, ldy, nc, false, _stream);
     return;
   }
-  const int    grid = divUp(rows.n * 32, 256);
+  const int    grid = divUp((re - rb) * 32, 256);
   const double s2   = _support * _support * (1.0 + 1e-12);
   RBF_DISPATCH_HOT_BASIS(_rbf.kind, {
     if (nc == 1)
-      sparseApplyKernel<KIND, 1, 2><<<grid, 256, 0, _stream>>>(_rbf, s2, rows.view(), rows.n, cols.view(), x, ldx, y, ldy, dotWith, ldd, dotOut);
+      sparseApplyKernel<KIND, 1, 2><<<grid, 256, 0, _stream>>>(_rbf, s2, rows.view(), rb, re, cols.view(), x, ldx, y, ldy, dotWith, ldd, dotOut);
     else if (nc == 2)
-      sparseApplyKernel<KIND, 2, 2><<<grid, 256, 0, _stream>>>(_rbf, s2, rows.view(), rows.n, cols.view(), x, ldx, y, ldy, dotWith, ldd, dotOut);
+      sparseApplyKernel<KIND, 2, 2><<<grid, 256, 0, _stream>>>(_rbf, s2, rows.view(), rb, re, cols.view(), x, ldx, y, ldy, dotWith, ldd, dotOut);
     else
-      sparseApplyKernel<KIND, 3, 2><<<grid, 256, 0, _stream>>>(_rbf, s2, rows.view(), rows.n, cols.view(), x, ldx, y, ldy, dotWith, ldd, dotOut);
+      sparseApplyKernel<KIND, 3, 2><<<grid, 256, 0, _stream>>>(_rbf, s2, rows.view(), rb, re, cols.view(), x, ldx, y, ldy, dotWith, ldd, dotOut);
   });
   RBF_LAUNCHED();
   RBF_CUDA(cudaGetLastError());
+}
+
+void GlobalIterativeMapping::allGatherSlices(double *v, int64_t ld, int nc, int64_t slice)
+{
+  if (_world == 1)
+    return;
+  const NcclApi &n = ncclApi();
+  RBF_NCCL(n.GroupStart());
+  for (int c = 0; c < nc; ++c)
+    RBF_NCCL(n.AllGather(v + c * ld + _rank * slice, v + c * ld, static_cast<size_t>(slice), ncclDouble, _comm, _stream));
+  RBF_NCCL(n.GroupEnd());
+}
+
+void GlobalIterativeMapping::allReduceScalars(double *d, int count)
+{
+  if (_world == 1)
+    return;
+  RBF_NCCL(ncclApi().AllReduce(d, d, static_cast<size_t>(count), ncclDouble, ncclSum, _comm, _stream));
 }
 
 void GlobalIterativeMapping::setupPolynomial()
@@ -595,47 +643,61 @@ void GlobalIterativeMapping::computeMapping(const double *dInputXyz, int64_t nIn
   _computed                = true;
 }
 
-// conjugate gradients for nc right-hand sides in lockstep; b is overwritten by the residual
+// Conjugate gradients for nc right-hand sides in lockstep. Vectors are planar with leading dimension _ldIn (padded to
+// world * slice). With several ranks every rank owns the cell-ordered row slice [rb, re): it applies the operator to its
+// rows (needs the full direction vector -> all-gather per iteration) and contributes partial dot products
+// (-> all-reduce of 3 doubles). b: only the slice must be valid on entry; it is overwritten by the residual.
+// x: full initial guess on entry (identical on all ranks), full solution on exit.
 void GlobalIterativeMapping::cg(double *b, double *x, int nc)
 {
-  const int64_t  n = _nIn;
-  DevBuf<double> p, Ap;
+  const int64_t n = _nIn, ld = _ldIn;
+  int64_t       rb, re, slice;
+  partitionRows(n, _world, _rank, rb, re, slice);
+  const int64_t     m = re - rb;
+  DevBuf<double>    p, Ap;
   DevBuf<CgScalars> sc;
-  p.alloc(static_cast<size_t>(n) * nc);
-  Ap.alloc(static_cast<size_t>(n) * nc);
+  p.alloc(static_cast<size_t>(ld) * nc);
+  Ap.alloc(static_cast<size_t>(ld) * nc);
   sc.alloc(1);
   RBF_CUDA(cudaMemsetAsync(sc.p, 0, sizeof(CgScalars), _stream));
-  // r = b - A x0
-  apply(_inGrid, _inGrid, x, n, Ap.p, n, nc, nullptr, 0, nullptr);
-  const int rg = reduceGrid(n);
+  RBF_CUDA(cudaMemsetAsync(p.p, 0, static_cast<size_t>(ld) * nc * sizeof(double), _stream));
+  double *scD = reinterpret_cast<double *>(sc.p); // rr[3] pAp[3] rrNew[3] r0[3] bb[3]
+  // r = b - A x0 on the slice
+  apply(_inGrid, rb, re, _inGrid, x, ld, Ap.p, ld, nc, nullptr, 0, nullptr);
+  const int rg       = reduceGrid(std::max<int64_t>(m, 1));
   auto      launchNc = [&](auto fn) {
     if (nc == 1) fn(std::integral_constant<int, 1>{});
     else if (nc == 2) fn(std::integral_constant<int, 2>{});
     else fn(std::integral_constant<int, 3>{});
   };
-  launchNc([&](auto NC) { cgInitKernel<decltype(NC)::value><<<rg, 256, 0, _stream>>>(b, Ap.p, b, p.p, n, n, sc.p); });
+  launchNc([&](auto NC) { cgInitKernel<decltype(NC)::value><<<rg, 256, 0, _stream>>>(b + rb, Ap.p + rb, b + rb, p.p + rb, m, ld, sc.p); });
+  RBF_LAUNCHED();
+  allReduceScalars(scD, 5 * kMaxNc);
   cgStartKernel<<<1, 32, 0, _stream>>>(sc.p, nc, _cfg.solver_rtol);
   RBF_LAUNCHED();
-  RBF_LAUNCHED();
+  allGatherSlices(p.p, ld, nc, slice);
   CgScalars h{};
   RBF_CUDA(cudaMemcpyAsync(&h, sc.p, sizeof(h), cudaMemcpyDeviceToHost, _stream));
   RBF_CUDA(cudaStreamSynchronize(_stream));
-  double *r       = b;
-  int     it      = 0;
+  double *r         = b;
+  int     it        = 0;
   bool    anyActive = false;
   for (int c = 0; c < nc; ++c)
     anyActive |= h.active[c] != 0;
-  const int maxIt = _cfg.max_iterations > 0 ? _cfg.max_iterations : 1000000;
+  const int  maxIt  = _cfg.max_iterations > 0 ? _cfg.max_iterations : 1000000;
   const bool fused  = _sparse;
-  double    *pApDev = reinterpret_cast<double *>(reinterpret_cast<char *>(sc.p) + offsetof(CgScalars, pAp));
+  double    *pApDev = scD + kMaxNc, *rrNewDev = scD + 2 * kMaxNc;
   while (anyActive && it < maxIt) {
-    apply(_inGrid, _inGrid, p.p, n, Ap.p, n, nc, fused ? p.p : nullptr, n, fused ? pApDev : nullptr);
-    if (!fused) { // dense operator: separate dot product p . (A p)
-      launchNc([&](auto NC) { cgDotKernel<decltype(NC)::value><<<rg, 256, 0, _stream>>>(p.p, Ap.p, n, n, pApDev); });
+    apply(_inGrid, rb, re, _inGrid, p.p, ld, Ap.p, ld, nc, fused ? p.p : nullptr, ld, fused ? pApDev : nullptr);
+    if (!fused && m > 0) { // dense operator: separate dot product p . (A p)
+      launchNc([&](auto NC) { cgDotKernel<decltype(NC)::value><<<rg, 256, 0, _stream>>>(p.p + rb, Ap.p + rb, m, ld, pApDev); });
       RBF_LAUNCHED();
     }
-    launchNc([&](auto NC) { cgUpdateKernel<decltype(NC)::value><<<rg, 256, 0, _stream>>>(x, r, p.p, Ap.p, n, n, sc.p); });
-    launchNc([&](auto NC) { cgDirectionKernel<decltype(NC)::value><<<rg, 256, 0, _stream>>>(p.p, r, n, n, sc.p); });
+    allReduceScalars(pApDev, kMaxNc);
+    launchNc([&](auto NC) { cgUpdateKernel<decltype(NC)::value><<<rg, 256, 0, _stream>>>(x + rb, r + rb, p.p + rb, Ap.p + rb, m, ld, sc.p); });
+    allReduceScalars(rrNewDev, kMaxNc);
+    launchNc([&](auto NC) { cgDirectionKernel<decltype(NC)::value><<<rg, 256, 0, _stream>>>(p.p + rb, r + rb, m, ld, sc.p); });
+    allGatherSlices(p.p, ld, nc, slice);
     cgRollKernel<<<1, 32, 0, _stream>>>(sc.p, nc, _cfg.solver_rtol);
     RBF_LAUNCHED();
     RBF_LAUNCHED();
@@ -649,6 +711,7 @@ void GlobalIterativeMapping::cg(double *b, double *x, int nc)
         anyActive |= h.active[c] != 0;
     }
   }
+  allGatherSlices(x, ld, nc, slice);
   RBF_CUDA(cudaMemcpyAsync(&h, sc.p, sizeof(h), cudaMemcpyDeviceToHost, _stream));
   RBF_CUDA(cudaStreamSynchronize(_stream));
   stats.iterations = std::max(stats.iterations, it);
@@ -674,18 +737,23 @@ void GlobalIterativeMapping::map(bool conservative, const double *dIn, int dims,
   if (nRes > 0)
     RBF_CUDA(cudaMemsetAsync(dOut, 0, static_cast<size_t>(nRes) * dims * sizeof(double), _stream));
   if (_nIn > 0 && _nOut > 0) {
+    int64_t ib, ie, islice, ob, oe, oslice;
+    partitionRows(_nIn, _world, _rank, ib, ie, islice);
+    partitionRows(_nOut, _world, _rank, ob, oe, oslice);
+    _ldIn              = islice * _world;
+    const int64_t ldOut = oslice * _world;
     if (_guessDims != dims) { // initial guess: zero on first use, kept per component afterwards
-      _guess.alloc(static_cast<size_t>(_nIn) * dims);
-      RBF_CUDA(cudaMemsetAsync(_guess.p, 0, static_cast<size_t>(_nIn) * dims * sizeof(double), _stream));
+      _guess.alloc(static_cast<size_t>(_ldIn) * dims);
+      RBF_CUDA(cudaMemsetAsync(_guess.p, 0, static_cast<size_t>(_ldIn) * dims * sizeof(double), _stream));
       _guessDims = dims;
     }
     for (int c0 = 0; c0 < dims; c0 += kMaxNc) {
       const int      nc = std::min(kMaxNc, dims - c0);
-      double        *x  = _guess.p + static_cast<size_t>(c0) * _nIn;
+      double        *x  = _guess.p + static_cast<size_t>(c0) * _ldIn;
       DevBuf<double> b, o, beta, tt, eps, u;
-      b.alloc(static_cast<size_t>(_nIn) * nc);
+      b.alloc(static_cast<size_t>(_ldIn) * nc);
       if (!conservative) {
-        gatherPlanarKernel<<<divUp(_nIn, 256), 256, 0, _stream>>>(dIn, dims, c0, nc, _inGrid.ids.p, _nIn, b.p, _nIn);
+        gatherPlanarKernel<<<divUp(_nIn, 256), 256, 0, _stream>>>(dIn, dims, c0, nc, _inGrid.ids.p, _nIn, b.p, _ldIn);
         RBF_LAUNCHED();
         if (_poly.mode == 1) {
           beta.alloc(4 * nc);
@@ -693,31 +761,32 @@ void GlobalIterativeMapping::map(bool conservative, const double *dIn, int dims,
           RBF_CUDA(cudaMemsetAsync(beta.p, 0, 4 * nc * sizeof(double), _stream));
           for (int pass = 0; pass < 2; ++pass) {
             RBF_CUDA(cudaMemsetAsync(tt.p, 0, 4 * nc * sizeof(double), _stream));
-            projectItKernel<<<reduceGrid(_nIn), 256, 0, _stream>>>(_inGrid.xyz.p, _nIn, _poly, b.p, _nIn, nc, beta.p, -1.0, tt.p);
+            projectItKernel<<<reduceGrid(_nIn), 256, 0, _stream>>>(_inGrid.xyz.p, _nIn, _poly, b.p, _ldIn, nc, beta.p, -1.0, tt.p);
             solveItKernel<<<1, 32, 0, _stream>>>(_poly, tt.p, nullptr, nc, beta.p);
             RBF_LAUNCHED();
             RBF_LAUNCHED();
           }
-          applyItKernel<<<divUp(_nIn, 256), 256, 0, _stream>>>(_inGrid.xyz.p, _nIn, _poly, beta.p, nc, -1.0, b.p, _nIn);
+          applyItKernel<<<divUp(_nIn, 256), 256, 0, _stream>>>(_inGrid.xyz.p, _nIn, _poly, beta.p, nc, -1.0, b.p, _ldIn);
           RBF_LAUNCHED();
         }
         cg(b.p, x, nc);
-        o.alloc(static_cast<size_t>(_nOut) * nc);
-        apply(_outGrid, _inGrid, x, _nIn, o.p, _nOut, nc, nullptr, 0, nullptr);
+        o.alloc(static_cast<size_t>(ldOut) * nc);
+        apply(_outGrid, ob, oe, _inGrid, x, _ldIn, o.p, ldOut, nc, nullptr, 0, nullptr); // this rank's evaluation rows
+        allGatherSlices(o.p, ldOut, nc, oslice);
         if (_poly.mode == 1) {
-          applyItKernel<<<divUp(_nOut, 256), 256, 0, _stream>>>(_outGrid.xyz.p, _nOut, _poly, beta.p, nc, 1.0, o.p, _nOut);
+          applyItKernel<<<divUp(_nOut, 256), 256, 0, _stream>>>(_outGrid.xyz.p, _nOut, _poly, beta.p, nc, 1.0, o.p, ldOut);
           RBF_LAUNCHED();
         }
-        scatterInterleavedKernel<<<divUp(_nOut, 256), 256, 0, _stream>>>(o.p, _nOut, nc, _outGrid.ids.p, _nOut, dims, c0, dOut);
+        scatterInterleavedKernel<<<divUp(_nOut, 256), 256, 0, _stream>>>(o.p, ldOut, nc, _outGrid.ids.p, _nOut, dims, c0, dOut);
         RBF_LAUNCHED();
       } else {
         u.alloc(static_cast<size_t>(_nOut) * nc);
         gatherPlanarKernel<<<divUp(_nOut, 256), 256, 0, _stream>>>(dIn, dims, c0, nc, _outGrid.ids.p, _nOut, u.p, _nOut);
         RBF_LAUNCHED();
-        apply(_inGrid, _outGrid, u.p, _nOut, b.p, _nIn, nc, nullptr, 0, nullptr); // Au = A^T u
+        apply(_inGrid, ib, ie, _outGrid, u.p, _nOut, b.p, _ldIn, nc, nullptr, 0, nullptr); // slice of Au = A^T u
         cg(b.p, x, nc);
-        o.alloc(static_cast<size_t>(_nIn) * nc);
-        RBF_CUDA(cudaMemcpyAsync(o.p, x, static_cast<size_t>(_nIn) * nc * sizeof(double), cudaMemcpyDeviceToDevice, _stream));
+        o.alloc(static_cast<size_t>(_ldIn) * nc);
+        RBF_CUDA(cudaMemcpyAsync(o.p, x, static_cast<size_t>(_ldIn) * nc * sizeof(double), cudaMemcpyDeviceToDevice, _stream));
         if (_poly.mode == 1) {
           eps.alloc(4 * nc);
           tt.alloc(4 * nc);
@@ -728,15 +797,15 @@ void GlobalIterativeMapping::map(bool conservative, const double *dIn, int dims,
           RBF_LAUNCHED();
           for (int pass = 0; pass < 2; ++pass) {
             RBF_CUDA(cudaMemsetAsync(tt.p, 0, 4 * nc * sizeof(double), _stream));
-            projectItKernel<<<reduceGrid(_nIn), 256, 0, _stream>>>(_inGrid.xyz.p, _nIn, _poly, o.p, _nIn, nc, beta.p, 1.0, tt.p);
+            projectItKernel<<<reduceGrid(_nIn), 256, 0, _stream>>>(_inGrid.xyz.p, _nIn, _poly, o.p, _ldIn, nc, beta.p, 1.0, tt.p);
             solveItKernel<<<1, 32, 0, _stream>>>(_poly, eps.p, tt.p, nc, beta.p);
             RBF_LAUNCHED();
             RBF_LAUNCHED();
           }
-          applyItKernel<<<divUp(_nIn, 256), 256, 0, _stream>>>(_inGrid.xyz.p, _nIn, _poly, beta.p, nc, 1.0, o.p, _nIn);
+          applyItKernel<<<divUp(_nIn, 256), 256, 0, _stream>>>(_inGrid.xyz.p, _nIn, _poly, beta.p, nc, 1.0, o.p, _ldIn);
           RBF_LAUNCHED();
         }
-        scatterInterleavedKernel<<<divUp(_nIn, 256), 256, 0, _stream>>>(o.p, _nIn, nc, _inGrid.ids.p, _nIn, dims, c0, dOut);
+        scatterInterleavedKernel<<<divUp(_nIn, 256), 256, 0, _stream>>>(o.p, _ldIn, nc, _inGrid.ids.p, _nIn, dims, c0, dOut);
         RBF_LAUNCHED();
       }
     }

@@ -22,6 +22,13 @@ public:
   virtual void        mapConservative(const double *dIn, int dims, double *dOut)                                       = 0;
   virtual void        clear()                                                                                          = 0;
   virtual std::string name() const                                                                                     = 0;
+  // joins a group of `world` processes (one GPU each) that execute the same calls on replicated inputs and shard the work;
+  // only rbf-global-iterative shards inside one mapping (rows of the CG operator), see global_iterative.cu
+  virtual void distributedInit(const char * /*ncclUniqueId, 128 bytes*/, int /*rank*/, int /*world*/)
+  {
+    throw MapError(RBFMAP_ERR_UNSUPPORTED, "this mapping variant does not shard across devices: rbf-pum-direct shards by mesh partition "
+                                           "(one mapping per rank, no communication), rbf-global-direct stays on one device");
+  }
 
   bool                 hasComputedMapping() const { return _computed; }
   bool                 isConservative() const { return _cfg.constraint == RBFMAP_CONSERVATIVE; }

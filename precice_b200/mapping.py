@@ -126,6 +126,11 @@ class _Mapping:
     def getName(self) -> str:
         return self._L.rbfmap_get_name(self._h).decode()
 
+    # -- multi-GPU (rbf-global-iterative only, see include/rbfmap.h)
+    def distributedInit(self, unique_id: bytes, rank: int, world: int):
+        assert len(unique_id) == 128
+        self._check(self._L.rbfmap_distributed_init(self._h, unique_id, rank, world))
+
     # -- extras
     def stats(self) -> dict:
         s = Stats()
@@ -213,6 +218,25 @@ def eval_basis(basis: str, param: float, radii, gauss_support=None) -> np.ndarra
     if rc != 0:
         raise MappingError(rc, L.rbfmap_last_error(None).decode())
     return out
+
+
+def nccl_unique_id() -> bytes:
+    """128-byte NCCL id created on the calling rank; broadcast it to the other ranks before distributedInit."""
+    L = _lib.lib()
+    buf = C.create_string_buffer(128)
+    rc = L.rbfmap_nccl_unique_id(buf)
+    if rc != 0:
+        raise MappingError(rc, L.rbfmap_last_error(None).decode())
+    return buf.raw
+
+
+def partition_rows(n: int, world: int, rank: int):
+    """Row slice [begin, end) of `rank` in the sharded CG (host-side helper)."""
+    b, e = C.c_int64(0), C.c_int64(0)
+    rc = _lib.lib().rbfmap_partition_rows(n, world, rank, C.byref(b), C.byref(e))
+    if rc != 0:
+        raise MappingError(rc, "invalid partition request")
+    return b.value, e.value
 
 
 def device_count() -> int:

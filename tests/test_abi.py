@@ -84,3 +84,14 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "rbf_oracle" not in text, os.path.join(dirpath, f)
+
+
+def test_partition_rows_host_helper():
+    """Row slices of the sharded CG: contiguous, equal length except the tail, cover [0, n)."""
+    import precice_b200 as pb
+    for n, world in ((10, 3), (5, 8), (500000, 8), (7, 1), (0, 4)):
+        parts = [pb.partition_rows(n, world, r) for r in range(world)]
+        assert parts[0][0] == 0 and parts[-1][1] == n
+        for (b0, e0), (b1, e1) in zip(parts, parts[1:]):
+            assert e0 == b1 and e0 - b0 >= e1 - b1
+        assert max(e - b for b, e in parts) == -(-n // world)
