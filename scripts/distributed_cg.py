@@ -10,7 +10,7 @@ import bench
 import precice_b200 as pb
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--n", type=int, default=500000)
+ap.add_argument("--vertices", dest="n", type=int, default=500000)
 ap.add_argument("--basis", default="gaussian")
 ap.add_argument("--param", type=float, default=91.05)
 ap.add_argument("--rtol", type=float, default=1e-9)
@@ -37,13 +37,23 @@ def run(sharded):
         m.distributedInit(ident[0], rank, world)
     m.computeMapping(inp, out)
     torch.cuda.synchronize()
-    if world > 1:
+    if sharded and world > 1:
         dist.barrier()
+    t0 = time.perf_counter()
+    r = m.map(vals, a.dims)  # first call: includes NCCL channel set-up when sharded
+    if a.dims >= 1:
+        m.clear()
+        m.computeMapping(inp, out)  # resets the warm start, so that the second call solves from zero again
+        torch.cuda.synchronize()
+        if sharded and world > 1:
+            dist.barrier()
     t0 = time.perf_counter()
     r = m.map(vals, a.dims)
     torch.cuda.synchronize()
     t = time.perf_counter() - t0
-    return r, t, m.stats()
+    st = m.stats()
+    del m
+    return r, t, st
 
 r_sh, t_sh, st = run(True)
 tt = torch.tensor([t_sh], device=dev, dtype=torch.float64)

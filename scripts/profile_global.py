@@ -8,7 +8,7 @@ import bench, refcases
 import precice_b200 as pb
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--n", type=int, default=50000)
+ap.add_argument("--vertices", dest="n", type=int, default=50000)
 ap.add_argument("--support", type=float, default=0.2)
 ap.add_argument("--basis", default="compact-polynomial-c2")
 ap.add_argument("--steps", type=int, default=2)

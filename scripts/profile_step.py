@@ -8,7 +8,7 @@ import bench
 import precice_b200 as pb
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--n", type=int, default=1_000_000)
+ap.add_argument("--vertices", dest="n", type=int, default=1_000_000)
 ap.add_argument("--steps", type=int, default=1)
 ap.add_argument("--constraint", default="consistent")
 ap.add_argument("--dims", type=int, default=1)

@@ -501,3 +501,19 @@ def test_global_direct_nonspd_vs_oracle(pb, orc, basis, param, polynomial, const
     assert refcases.rel_l2(rg, ro) <= 1e-7, refcases.rel_l2(rg, ro)  # cond(C) ~ 1e8..1e10 for these global functions
     if constraint == "conservative":
         assert refcases.close(rg.sum(), vals.sum(), 1e-7)
+
+
+def test_global_iterative_sharded_two_gpus(pb):
+    """the CG rows sharded over 2 GPUs (NCCL all-gather + all-reduce) give the single-GPU result."""
+    torch = pytest.importorskip("torch")
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run with `gpurun --gpus 2`)")
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "scripts", "distributed_cg.py"), "--vertices", "60000", "--param", "45"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "rel.L2 sharded vs single" in out.stdout
