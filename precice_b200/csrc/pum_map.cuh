@@ -175,6 +175,89 @@ __device__ __forceinline__ void blockedSolve(const double *__restrict__ mp, int 
   }
 }
 
+// Warp-level variant for factors staged in shared memory (n <= 32 * RPL): ONE warp performs both substitutions, lane l
+// owns rows l, l + 32, ...; the solved entry of each step is broadcast with a shuffle, so no block barrier and no
+// redundant diagonal solves are needed (about a quarter of the instructions of blockedSolve for n ~ 50).
+// Forward: column access M(i, k) = mp[base_k + i] (contiguous over lanes); backward: row access M(k, i) = mp[base_i + k].
+// Must be called by all 32 lanes of one warp; the other warps of the CTA wait at the caller's barrier.
+template <int NC, int LDV, int RPL>
+__device__ __forceinline__ void warpSolve(const double *__restrict__ mp, int n, double *v, int lane)
+{
+  double u[RPL][NC];
+  int    bi[RPL]; // base of the column of each owned row: M(k, i) = mp[bi + k]
+#pragma unroll
+  for (int r = 0; r < RPL; ++r) {
+    const int i = lane + 32 * r;
+    bi[r]       = i * n - (i * (i - 1)) / 2 - i;
+#pragma unroll
+    for (int cc = 0; cc < NC; ++cc)
+      u[r][cc] = i < n ? v[i * LDV + cc] : 0.0;
+  }
+  // ---- forward: M y = b; afterwards u holds the numerators D y ----
+  int base = 0; // base_k = colStart(k) - k
+#pragma unroll
+  for (int r0 = 0; r0 < RPL; ++r0) {
+    const int kEnd = min(32, n - 32 * r0);
+    for (int kk = 0; kk < kEnd; ++kk) {
+      const int    k  = 32 * r0 + kk;
+      const double rd = mp[base + k];
+      double       y[NC];
+#pragma unroll
+      for (int cc = 0; cc < NC; ++cc)
+        y[cc] = __shfl_sync(0xffffffffu, u[r0][cc], kk) * rd;
+#pragma unroll
+      for (int r = r0; r < RPL; ++r) {
+        const int i = lane + 32 * r;
+        if (i > k && i < n) {
+          const double mik = mp[base + i];
+#pragma unroll
+          for (int cc = 0; cc < NC; ++cc)
+            u[r][cc] = fma(-mik, y[cc], u[r][cc]);
+        }
+      }
+      base += n - k - 1;
+    }
+  }
+  // ---- backward: M^T x = u ----
+#pragma unroll
+  for (int r0 = RPL - 1; r0 >= 0; --r0) {
+    const int kEnd = min(32, n - 32 * r0);
+    for (int kk = kEnd - 1; kk >= 0; --kk) {
+      const int k = 32 * r0 + kk;
+      base -= n - k - 1; // back to base_k
+      const double rd = mp[base + k];
+      double       x[NC];
+#pragma unroll
+      for (int cc = 0; cc < NC; ++cc)
+        x[cc] = __shfl_sync(0xffffffffu, u[r0][cc], kk) * rd;
+      if (lane == kk) {
+#pragma unroll
+        for (int cc = 0; cc < NC; ++cc)
+          u[r0][cc] = x[cc]; // the owner keeps the solution entry
+      }
+#pragma unroll
+      for (int r = 0; r <= r0; ++r) {
+        const int i = lane + 32 * r;
+        if (i < k) {
+          const double mki = mp[bi[r] + k];
+#pragma unroll
+          for (int cc = 0; cc < NC; ++cc)
+            u[r][cc] = fma(-mki, x[cc], u[r][cc]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RPL; ++r) {
+    const int i = lane + 32 * r;
+    if (i < n) {
+#pragma unroll
+      for (int cc = 0; cc < NC; ++cc)
+        v[i * LDV + cc] = u[r][cc];
+    }
+  }
+}
+
 template <typename K>
 inline void allowSmem(K kernel, size_t bytes)
 {

@@ -124,8 +124,11 @@ __global__ void __launch_bounds__(NT) pumMapConservativeKernel(PumSolveArgs args
 
   // ---- mu = C^-1 Au ----
   if (STAGE_M) {
-    mbarWait(&mbar, 0);
-    blockedSolve<NC, LDV, int>(ms, n, vt + 3, tid, NT);
+    if (tid < 32) { // one warp solves; the others wait at the barrier
+      mbarWait(&mbar, 0);
+      warpSolve<NC, LDV, NT / 32>(ms, n, vt + 3, tid);
+    }
+    __syncthreads();
   } else {
     blockedSolve<NC, LDV, long long>(mg, n, vt + 3, tid, NT);
   }

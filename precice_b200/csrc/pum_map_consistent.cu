@@ -131,8 +131,11 @@ __global__ void __launch_bounds__(NT) pumMapConsistentKernel(PumSolveArgs args, 
 
   // ---- lambda = C^-1 f ----
   if (STAGE_M) {
-    mbarWait(&mbar, 0);
-    blockedSolve<NC, LDV, int>(ms, n, vt + 3, tid, NT);
+    if (tid < 32) { // one warp solves; the others wait at the barrier
+      mbarWait(&mbar, 0);
+      warpSolve<NC, LDV, NT / 32>(ms, n, vt + 3, tid);
+    }
+    __syncthreads();
   } else {
     blockedSolve<NC, LDV, long long>(mg, n, vt + 3, tid, NT);
   }
