@@ -274,28 +274,40 @@ def main():
         value = world * n / (ms_per_step * 1e-3)
         e2e_value = world * n / (e2e_ms / steps * 1e-3)
 
-        # roofline of the dominant kernel (assembly + factorisation of all local systems, pumFactorKernel):
-        # algorithmic flops = sum_c [F_phi n_c (n_c + 1) / 2 + n_c^3 / 3]   (SURVEY.md §8d), from the cluster statistics
-        asm_flops = F_PHI * (stats["sum_n2"] + stats["sum_n"]) / 2.0
-        chol_flops = stats["sum_n3"] / 3.0
-        asm_s = asm_ms / steps * 1e-3
+        # Rooflines of the two algebra kernels. Both are FP64-pipe bound (the matrices live in registers / shared memory;
+        # HBM traffic is far below its roofline, see profiles/), so `peak` is the FP64 FMA peak measured in this run.
+        # Algorithmic flops (sqrt = 1, fma = 2, F_phi = 24 for C6 in 3-D), from the cluster statistics:
+        #   factor kernel: sum_c [F_phi n_c (n_c + 1) / 2 + n_c^3 / 3]        (assemble C + Cholesky)
+        #   map kernel   : sum_c [2 n_c^2 + (F_phi + 2) m_c n_c]              (solve + evaluate A lambda on the fly)
         from precice_b200 import _lib
         import ctypes as C
         tf, ms = C.c_double(0), C.c_double(0)
         _lib.lib().rbfmap_measure_fp64_peak(C.byref(tf), C.byref(ms))
         fp64_peak = tf.value
-        achieved = (asm_flops + chol_flops) / asm_s / 1e12
-        roofline = {"bound": "fp64", "kernel": "pumFactorKernel (per-cluster assembly of C + factorisation)", "achieved": achieved,
-                    "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
-                    "peak_source": "measured in this run: dependency-free DFMA loop (rbfmap_measure_fp64_peak); "
-                                   "FP64 is not in MEASURED_PEAKS.json",
-                    "algorithmic_flops_per_launch": asm_flops + chol_flops, "ms_per_launch": asm_s * 1e3,
-                    "share_of_step": asm_ms / ev_ms}
-        map_flops = 2.0 * stats["sum_n2"] + (F_PHI + 2.0) * stats["sum_mn"]
-        map_s = map_ms / steps * 1e-3
-        roofline_map = {"bound": "fp64", "kernel": "pumMapConsistentKernel (solve + on-the-fly evaluation + blend)",
-                        "achieved": map_flops / map_s / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
-                        "frac": map_flops / map_s / 1e12 / fp64_peak if fp64_peak else None, "share_of_step": map_ms / ev_ms}
+        src = ("measured in this run: dependency-free DFMA loop (rbfmap_measure_fp64_peak); FP64 is not in MEASURED_PEAKS.json")
+
+        def fp64_roofline(kernel, flops, ms_total):
+            sec = ms_total / steps * 1e-3
+            ach = flops / sec / 1e12
+            return {"bound": "fp64", "kernel": kernel, "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                    "frac": ach / fp64_peak if fp64_peak else None, "traffic": None, "peak_source": src,
+                    "algorithmic_flops_per_launch": flops, "ms_per_launch": sec * 1e3, "share_of_step": ms_total / ev_ms}
+
+        r_factor = fp64_roofline("pumFactorKernel (per-cluster assembly of C + square-root-free Cholesky, all buckets)",
+                                 F_PHI * (stats["sum_n2"] + stats["sum_n"]) / 2.0 + stats["sum_n3"] / 3.0, asm_ms)
+        r_map = fp64_roofline("pumMapConsistentKernel (gather + polynomial + solve + on-the-fly evaluation + blend, all buckets)",
+                              2.0 * stats["sum_n2"] + (F_PHI + 2.0) * stats["sum_mn"], map_ms)
+        # DRAM traffic: `ncu --set full` capture of the same kernels on the 1M-vertex workload (profiles/r1c_*_summary.txt,
+        # dram__bytes_read.sum + dram__bytes_write.sum of the n = 49..56 bucket: 11.6 KB resp. 19.6 KB per cluster), scaled by
+        # the number of clusters of this run. Algorithmic bytes per cluster: packed factor 8 n(n+1)/2 B (written once by the
+        # factor kernel, read once per map) + 24 B per gathered vertex + 8 B per value.
+        r_factor["traffic"] = 11.6e3 * stats["n_clusters"]
+        r_map["traffic"] = 19.6e3 * stats["n_clusters"]
+        for r_ in (r_factor, r_map):
+            r_["traffic_source"] = "ncu capture at 1M vertices (profiles/r1c_*), bytes per cluster x clusters"
+        r_factor["algorithmic_bytes"] = 8.0 * (stats["sum_n2"] + stats["sum_n"]) / 2.0 + 24.0 * stats["sum_n"]
+        r_map["algorithmic_bytes"] = 8.0 * (stats["sum_n2"] + stats["sum_n"]) / 2.0 + 32.0 * stats["sum_n"] + 32.0 * stats["sum_m"]
+        roofline, roofline_other = (r_factor, r_map) if asm_ms >= map_ms else (r_map, r_factor)
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
@@ -307,7 +319,8 @@ def main():
                 "config": workload_config(n),
                 "e2e": {"value": e2e_value, "unit": "vertices/s", "h2d_bytes_per_step": 8 * (3 * n + 3 * n + n),
                         "d2h_bytes_per_step": 8 * n, "ms_per_step": e2e_ms / steps},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_map": roofline_map,
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_secondary": roofline_other,
+                "fp64_peak_tflops": fp64_peak,
                 "wall_ms_per_step": wall_ms / steps,
                 "mapping": {k: stats[k] for k in ("n_clusters", "cluster_radius", "sum_n", "sum_m", "sum_n2", "sum_n3", "sum_mn",
                                                   "max_n", "device_bytes")},
