@@ -95,6 +95,7 @@ void pumClassify(const PumMembership &m, int64_t nClusters, PumBuckets &b, rbfma
 void pumPolySetup(const PumSolveArgs &a, int64_t nClusters, int polynomial, cudaStream_t s);
 // fail = device int (lowest failing cluster index or INT_MAX)
 void pumFactor(const PumSolveArgs &a, const PumBuckets &b, int *fail, cudaStream_t s);
+void pumFactorWarp(const PumSolveArgs &a, int bucket, const int *list, int64_t count, int *fail, cudaStream_t s);
 void pumMapConsistent(const PumSolveArgs &a, const PumBuckets &b, const double *in, int dims, double *out, cudaStream_t s);
 void pumMapConservative(const PumSolveArgs &a, const PumBuckets &b, const double *in, int dims, double *out, cudaStream_t s);
 

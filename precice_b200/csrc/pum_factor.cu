@@ -14,6 +14,7 @@
 #include "pum_device.cuh"
 
 #include <climits>
+#include <cstdlib>
 
 namespace rbfmap {
 namespace {
@@ -23,19 +24,20 @@ namespace {
 constexpr int kColLd = 10;
 
 template <int KIND, int TG, int NB, bool DIM3>
-__global__ void __launch_bounds__(TG *TG) pumFactorKernel(PumSolveArgs args, const int *__restrict__ list, int *__restrict__ fail)
+__global__ void __launch_bounds__(TG *TG, TG == 8 ? (NB <= 7 ? 10 : 8) : 2) pumFactorKernel(PumSolveArgs args, const int *__restrict__ list, int *__restrict__ fail)
 {
   constexpr int NT   = TG * TG;
   constexpr int NMAX = NB * TG;
   __shared__ double sx[NMAX], sy[NMAX], sz[NMAX];
-  __shared__ __align__(16) double colBuf[2][TG * kColLd];
+  __shared__ __align__(16) double colBuf[2][2][TG * kColLd]; // [parity][unscaled | scaled by 1/d_k]
 
   const int c   = list[blockIdx.x];
   const int n   = args.nIn[c];
   const int tid = threadIdx.x;
   const int tr = tid % TG, tc = tid / TG;
   const int      *ids = args.inIds + args.inOff[c];
-  const RbfParams rbf = args.rbf;
+  const RbfParams rbf   = args.rbf;
+  const double    invR2 = rbf.p1 * rbf.p1;
 
   for (int i = tid; i < NMAX; i += NT) {
     double x = paddingCoordinate(i), y = 0.0, z = 0.0;
@@ -67,56 +69,107 @@ __global__ void __launch_bounds__(TG *TG) pumFactorKernel(PumSolveArgs args, con
 #pragma unroll
       for (int b = 0; b <= a; ++b) {
         // RadialBasisFctSolver.hpp:191-192
-        const double d2 = sqDistD<DIM3>(xj[b], yj[b], zj[b], xi, yi, zi);
-        A[a][b]         = evalBasisK<KIND>(distSqrt(d2), rbf);
+        A[a][b] = pairBasis<KIND, DIM3>(xj[b], yj[b], zj[b], xi, yi, zi, rbf, invR2);
       }
     }
   }
 
-  // ---- right-looking factorisation, one column per step ----
-  bool ok = true;
+  // ---- right-looking factorisation, one column per step, one barrier per step ----
+  // Column k is published in shared memory twice: unscaled (row operand M(i,k)) and scaled by 1/d_k (column operand).
+  // Look-ahead: in step k every thread first updates its entries of the block column that holds column k+1; the warp that
+  // owns column k+1 (its TG owners are consecutive lanes of one warp) then fetches the new pivot from the diagonal thread
+  // with a shuffle, inverts it and publishes column k+1 into the other buffer while all warps finish the trailing update.
+  // All NB*TG columns are processed: the padding vertices form an identity block that costs a few cheap steps and
+  // removes every size-dependent branch from the loop. Pivot test: the smallest high word of the pivots is tracked and
+  // checked once at the end (d <= 0 <=> high word <= 0, the criterion of Eigen::LLT; NaNs pass there as well).
+  constexpr int kParity = 2 * TG * kColLd; // doubles between the two buffer pairs
+  constexpr int kScaled = TG * kColLd;
+  double       *rowP    = &colBuf[0][0][0] + tr * kColLd; // row operand of this thread / publishing slot of an owner
+  const double *colP    = &colBuf[0][1][0] + tc * kColLd; // column operand
+  const int     warp    = tid >> 5;
+  int           minHi   = 0x7ff00000;
+
+  auto publish = [&](const int KB, const int kk2) { // warp-uniform: executed by all lanes of the warp that owns column kk2
+    const int    lane0 = (kk2 * TG) & 31;
+    const double d     = __shfl_sync(0xffffffffu, A[KB][KB], lane0 + kk2);
+    minHi              = min(minHi, __double2hiint(d));
+    const double rd    = pivotReciprocal(d);
+    if (tc == kk2) {
+      double *dst = rowP + (kk2 & 1) * kParity;
+#pragma unroll
+      for (int a2 = (KB & ~1); a2 < NB; a2 += 2) {
+        const double v0 = a2 >= KB ? A[a2 >= KB ? a2 : KB][KB] : 0.0;
+        const double v1 = a2 + 1 < NB ? A[a2 + 1 < NB ? a2 + 1 : KB][KB] : 0.0;
+        *reinterpret_cast<double2 *>(dst + a2)           = make_double2(v0, v1);
+        *reinterpret_cast<double2 *>(dst + kScaled + a2) = make_double2(v0 * rd, v1 * rd);
+      }
+      if (tr == kk2)
+        A[KB][KB] = rd; // the packed factor stores 1/d_k; this entry is final
+    }
+  };
+
+  if (warp == 0)
+    publish(0, 0);
 #pragma unroll
   for (int kb = 0; kb < NB; ++kb) {
-    const int kend = min(TG, n - kb * TG);
-    if (ok) {
+    // steps 0 .. TG-2 of the block: the next column lies in the same block column
 #pragma unroll 1
-      for (int kk = 0; kk < kend; ++kk) {
-        double *buf = colBuf[kk & 1];
-        if (tc == kk) {
+    for (int kk = 0; kk < TG - 1; ++kk) {
+      const int par = (kk & 1) * kParity;
+      __syncthreads();
+      double li[NB + 1], lj[NB + 1];
 #pragma unroll
-          for (int a = kb; a < NB; ++a)
-            buf[tr * kColLd + a] = A[a][kb];
-        }
-        __syncthreads();
-        const double d = buf[kk * kColLd + kb];
-        if (!(d > 0.0)) { // same pivot test as Eigen::LLT (x <= 0 -> NumericalIssue); uniform over the CTA
-          ok = false;
-          break;
-        }
-        const double rd = 1.0 / d;
-        double       li[NB + 1], lj[NB + 1];
+      for (int a2 = (kb & ~1); a2 < NB; a2 += 2) {
+        const double2 u = *reinterpret_cast<const double2 *>(rowP + par + a2);
+        const double2 v = *reinterpret_cast<const double2 *>(colP + par + a2);
+        li[a2]     = u.x;
+        li[a2 + 1] = u.y;
+        lj[a2]     = v.x;
+        lj[a2 + 1] = v.y;
+      }
+      const double ljk = tc > kk ? lj[kb] : 0.0; // columns j <= k of block column kb are final
 #pragma unroll
-        for (int a2 = (kb & ~1); a2 < NB; a2 += 2) {
-          const double2 u = *reinterpret_cast<const double2 *>(&buf[tr * kColLd + a2]);
-          const double2 v = *reinterpret_cast<const double2 *>(&buf[tc * kColLd + a2]);
-          li[a2]     = u.x;
-          li[a2 + 1] = u.y;
-          lj[a2]     = v.x * rd;
-          lj[a2 + 1] = v.y * rd;
-        }
-        const bool colActive = tc > kk; // columns j <= k of block column kb are final
+      for (int a = kb; a < NB; ++a)
+        A[a][kb] = fma(-li[a], ljk, A[a][kb]);
+      if (warp == ((kk + 1) * TG) >> 5)
+        publish(kb, kk + 1);
 #pragma unroll
-        for (int a = kb; a < NB; ++a) {
-          if (colActive)
-            A[a][kb] = fma(-li[a], lj[kb], A[a][kb]);
+      for (int a = kb + 1; a < NB; ++a) {
 #pragma unroll
-          for (int b = kb + 1; b <= a; ++b)
+        for (int b = kb + 1; b <= a; ++b)
+          A[a][b] = fma(-li[a], lj[b], A[a][b]);
+      }
+    }
+    // last step of the block: block column kb is final, the next column is the first one of block column kb + 1
+    {
+      constexpr int par = ((TG - 1) & 1) * kParity;
+      __syncthreads();
+      double li[NB + 1], lj[NB + 1];
+#pragma unroll
+      for (int a2 = (kb & ~1); a2 < NB; a2 += 2) {
+        const double2 u = *reinterpret_cast<const double2 *>(rowP + par + a2);
+        const double2 v = *reinterpret_cast<const double2 *>(colP + par + a2);
+        li[a2]     = u.x;
+        li[a2 + 1] = u.y;
+        lj[a2]     = v.x;
+        lj[a2 + 1] = v.y;
+      }
+      if (kb + 1 < NB) {
+#pragma unroll
+        for (int a = kb + 1; a < NB; ++a)
+          A[a][kb + 1] = fma(-li[a], lj[kb + 1], A[a][kb + 1]);
+        if (warp == 0)
+          publish(kb + 1, 0);
+#pragma unroll
+        for (int a = kb + 2; a < NB; ++a) {
+#pragma unroll
+          for (int b = kb + 2; b <= a; ++b)
             A[a][b] = fma(-li[a], lj[b], A[a][b]);
         }
       }
     }
   }
-  if (!ok) {
+  if (__syncthreads_or(minHi <= 0)) {
     if (tid == 0)
       atomicMin(fail, c);
     return;
@@ -133,7 +186,7 @@ __global__ void __launch_bounds__(TG *TG) pumFactorKernel(PumSolveArgs args, con
       for (int a = b; a < NB; ++a) {
         const int i = a * TG + tr;
         if (i < n && i >= j)
-          colp[i] = (i == j) ? 1.0 / A[a][b] : A[a][b];
+          colp[i] = A[a][b]; // the diagonal already holds 1/d_j
       }
     }
   }
@@ -149,6 +202,7 @@ __global__ void __launch_bounds__(256) pumFactorGenericKernel(PumSolveArgs args,
   const int      *ids = args.inIds + args.inOff[c];
   double         *mp  = args.mat + args.matOff[c];
   const RbfParams rbf = args.rbf;
+  const double    invR2 = rbf.p1 * rbf.p1;
   double         *sx = dyn, *sy = dyn + n, *sz = dyn + 2 * n, *col = dyn + 3 * n;
   __shared__ int  bad;
   if (threadIdx.x == 0)
@@ -164,8 +218,8 @@ __global__ void __launch_bounds__(256) pumFactorGenericKernel(PumSolveArgs args,
   for (int j = 0; j < n; ++j) {
     const long long cs = colStart(j, n);
     for (int i = j + threadIdx.x; i < n; i += blockDim.x) {
-      const double d2 = dim3 ? sqDistD<true>(sx[j], sy[j], sz[j], sx[i], sy[i], sz[i]) : sqDistD<false>(sx[j], sy[j], sz[j], sx[i], sy[i], sz[i]);
-      mp[cs + i - j]  = evalBasisK<KIND>(distSqrt(d2), rbf);
+      mp[cs + i - j] = dim3 ? pairBasis<KIND, true>(sx[j], sy[j], sz[j], sx[i], sy[i], sz[i], rbf, invR2)
+                            : pairBasis<KIND, false>(sx[j], sy[j], sz[j], sx[i], sy[i], sz[i], rbf, invR2);
     }
   }
   __syncthreads();
@@ -237,6 +291,9 @@ void factorBucket(const PumSolveArgs &a, int bucket, const int *list, int64_t co
 
 } // namespace
 
+// RBFMAP_TILED_FACTOR=1 keeps the column-by-column kernel for all sizes (A/B comparison and tests)
+static const bool g_pumForceTiledFactor = [] { const char *e = std::getenv("RBFMAP_TILED_FACTOR"); return e && e[0] == '1'; }();
+
 void pumFactor(const PumSolveArgs &a, const PumBuckets &bk, int *fail, cudaStream_t s)
 {
   for (int b = 0; b < kNumBuckets; ++b) {
@@ -244,6 +301,10 @@ void pumFactor(const PumSolveArgs &a, const PumBuckets &bk, int *fail, cudaStrea
     if (count <= 0)
       continue;
     const int *list = bk.order.p + bk.start[b];
+    if (b < 8 && !g_pumForceTiledFactor) { // clusters of up to 64 vertices: one warp per cluster on DMMA (pum_factor_warp.cu)
+      pumFactorWarp(a, b, list, count, fail, s);
+      continue;
+    }
     RBF_DISPATCH_HOT_BASIS(a.rbf.kind, factorBucket<KIND>(a, b, list, count, bk.maxN[b], fail, s));
   }
   RBF_CUDA(cudaGetLastError());

@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(NT) pumMapConservativeKernel(PumSolveArgs args
   const RbfParams rbf  = args.rbf;
   const double    cx = args.centers[3 * c], cy = args.centers[3 * c + 1], cz = args.centers[3 * c + 2];
   const double    rinv = 1.0 / args.radius;
+  const double    invR2 = rbf.p1 * rbf.p1;
   const int       triPad = STAGE_M ? static_cast<int>(paddedTri(n)) : 0;
 
   double *ms  = dyn;
@@ -102,8 +103,7 @@ __global__ void __launch_bounds__(NT) pumMapConservativeKernel(PumSolveArgs args
         for (int oo = 0; oo < chunk; ++oo, op += LDV) {
           const double2 xy  = *reinterpret_cast<const double2 *>(op);
           const double2 zu  = *reinterpret_cast<const double2 *>(op + 2);
-          const double  d2  = sqDistD<DIM3>(xy.x, xy.y, zu.x, xj, yj, zj);
-          const double  phi = evalBasisK<KIND>(distSqrt(d2), rbf);
+          const double  phi = pairBasis<KIND, DIM3>(xy.x, xy.y, zu.x, xj, yj, zj, rbf, invR2);
           acc[0]            = fma(phi, zu.y, acc[0]);
           if (NC > 1) {
             const double2 u12 = *reinterpret_cast<const double2 *>(op + 4);

@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(NT) pumMapConsistentKernel(PumSolveArgs args, 
   const RbfParams rbf  = args.rbf;
   const double    cx = args.centers[3 * c], cy = args.centers[3 * c + 1], cz = args.centers[3 * c + 2];
   const double    rinv = 1.0 / args.radius;
+  const double    invR2 = rbf.p1 * rbf.p1;
   const int       triPad = STAGE_M ? static_cast<int>(paddedTri(n)) : 0;
 
   double *ms  = dyn;
@@ -154,8 +155,7 @@ __global__ void __launch_bounds__(NT) pumMapConsistentKernel(PumSolveArgs args, 
     for (int j = 0; j < n; ++j, vp += LDV) {
       const double2 xy = *reinterpret_cast<const double2 *>(vp);
       const double2 zb = *reinterpret_cast<const double2 *>(vp + 2);
-      const double  d2  = sqDistD<DIM3>(x, y, z, xy.x, xy.y, zb.x);
-      const double  phi = evalBasisK<KIND>(distSqrt(d2), rbf);
+      const double  phi = pairBasis<KIND, DIM3>(x, y, z, xy.x, xy.y, zb.x, rbf, invR2);
       acc[0]            = fma(phi, zb.y, acc[0]);
       if (NC > 1) {
         const double2 b12 = *reinterpret_cast<const double2 *>(vp + 4);
