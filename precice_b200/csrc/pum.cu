@@ -89,6 +89,7 @@ private:
   int64_t         _nClusters = 0;
   DevBuf<double>  _centers;
   PumMembership   _mem;
+  PumScratch      _scratch; // survives clear(), see pum.cuh
   DevBuf<double>  _mat;
   DevBuf<PolyRec> _poly;
   DevBuf<double>  _wsum;
@@ -310,7 +311,7 @@ void PumMapping::computeMapping(const double *dInputXyz, int64_t nInput, const d
   stats.cluster_radius = _radius;
 
   // per-cluster vertex sets (SphericalVertexCluster.hpp:153-162)
-  pumBuildMembership(_centers.p, _nClusters, inGrid, outGrid, _radius, _mem, _stream);
+  pumBuildMembership(_centers.p, _nClusters, inGrid, outGrid, _radius, _mem, _scratch, _stream);
   trace.phase("membership");
 
   // partition-of-unity weight sums (PartitionOfUnityMapping.hpp:263-276, 290-341)

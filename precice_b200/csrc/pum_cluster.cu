@@ -28,7 +28,7 @@ __global__ void tagEmptyKernel(const double *__restrict__ centers, int *__restri
     return;
   const double cx = centers[3 * c], cy = centers[3 * c + 1], cz = centers[3 * c + 2];
   bool         found = false;
-  forNeighbourhoodWarp(g, cx, cy, cz, lane, [&](int pos, bool valid) {
+  forCandidatesWarp(g, cx, cy, cz, lane, [&](int pos, bool valid) {
     bool hit = false;
     if (valid)
       hit = __dsqrt_rn(sqDist3(cx, cy, cz, g.xyz[3 * pos], g.xyz[3 * pos + 1], g.xyz[3 * pos + 2])) < radius;
@@ -52,7 +52,7 @@ __global__ void projectKernel(double *__restrict__ centers, const int *__restric
   const double cx = centers[3 * c], cy = centers[3 * c + 1], cz = centers[3 * c + 2];
   double       best = 1.7976931348623157e308;
   int          bestId = 0x7fffffff, bestPos = -1;
-  forNeighbourhoodWarp(g, cx, cy, cz, lane, [&](int pos, bool valid) {
+  forCandidatesWarp(g, cx, cy, cz, lane, [&](int pos, bool valid) {
     if (valid) {
       const double d2 = sqDist3(cx, cy, cz, g.xyz[3 * pos], g.xyz[3 * pos + 1], g.xyz[3 * pos + 2]);
       const int    id = g.ids[pos];
@@ -162,37 +162,6 @@ __global__ void compactKernel(int64_t total, const int *__restrict__ tag, const 
 }
 
 // ---- cluster membership: one warp per cluster ------------------------------------------------
-__global__ void memberCountKernel(const double *__restrict__ centers, int64_t nClusters, BinGridView gin, BinGridView gout, double rIn, double rOut,
-                                  int *__restrict__ nIn, int *__restrict__ nOut, long long *__restrict__ tri)
-{
-  const int64_t c    = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
-  const int     lane = threadIdx.x & 31;
-  if (c >= nClusters)
-    return;
-  const double cx = centers[3 * c], cy = centers[3 * c + 1], cz = centers[3 * c + 2];
-  int          ci = 0, co = 0;
-  forNeighbourhoodWarp(gin, cx, cy, cz, lane, [&](int pos, bool valid) {
-    if (valid && __dsqrt_rn(sqDist3(cx, cy, cz, gin.xyz[3 * pos], gin.xyz[3 * pos + 1], gin.xyz[3 * pos + 2])) < rIn)
-      ++ci;
-    return false;
-  });
-  forNeighbourhoodWarp(gout, cx, cy, cz, lane, [&](int pos, bool valid) {
-    if (valid && __dsqrt_rn(sqDist3(cx, cy, cz, gout.xyz[3 * pos], gout.xyz[3 * pos + 1], gout.xyz[3 * pos + 2])) < rOut)
-      ++co;
-    return false;
-  });
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    ci += __shfl_xor_sync(0xffffffffu, ci, o);
-    co += __shfl_xor_sync(0xffffffffu, co, o);
-  }
-  if (lane == 0) {
-    nIn[c]  = ci;
-    nOut[c] = co;
-    tri[c]  = (static_cast<long long>(ci) * (ci + 1) / 2 + 1) & ~1LL; // even count: 16-byte aligned factors for the TMA bulk copy
-  }
-}
-
 // warp-cooperative ascending sort of seg[0..n) (global memory) through a shared staging buffer
 __device__ void warpSortSegment(int *seg, int n, int *stage, int stageCap, int lane)
 {
@@ -243,7 +212,7 @@ constexpr int kSortCap = 1024; // ints staged per warp
 __device__ void gatherMembers(const BinGridView &g, double cx, double cy, double cz, double r, int *seg, int lane)
 {
   int base = 0;
-  forNeighbourhoodWarp(g, cx, cy, cz, lane, [&](int pos, bool valid) {
+  forCandidatesWarp(g, cx, cy, cz, lane, [&](int pos, bool valid) {
     const bool     hit = valid && __dsqrt_rn(sqDist3(cx, cy, cz, g.xyz[3 * pos], g.xyz[3 * pos + 1], g.xyz[3 * pos + 2])) < r;
     const unsigned m   = __ballot_sync(0xffffffffu, hit);
     if (hit)
@@ -252,6 +221,88 @@ __device__ void gatherMembers(const BinGridView &g, double cx, double cy, double
     return false;
   });
   __syncwarp();
+}
+
+// ---- single-pass membership: candidates are visited once; the sorted vertex sets go to fixed-size slots, sizes are
+// scanned, and a copy kernel packs the slots into the CSR arrays. Clusters that do not fit a slot raise `overflow`;
+// the host then falls back to the two-pass fill above (the sizes are exact in either case). ----
+constexpr int kSlotCap = 128;
+
+// ids of the vertices of grid g within radius r of the centre -> stage (unsorted, first kSlotCap hits); returns the count
+__device__ __forceinline__ int gatherToShared(const BinGridView &g, double cx, double cy, double cz, double r, int *stage, int lane)
+{
+  int base = 0;
+  forCandidatesWarp(g, cx, cy, cz, lane, [&](int pos, bool valid) {
+    const bool     hit = valid && __dsqrt_rn(sqDist3(cx, cy, cz, g.xyz[3 * pos], g.xyz[3 * pos + 1], g.xyz[3 * pos + 2])) < r;
+    const unsigned m   = __ballot_sync(0xffffffffu, hit);
+    const int      at  = base + __popc(m & ((1u << lane) - 1u));
+    if (hit && at < kSlotCap)
+      stage[at] = g.ids[pos];
+    base += __popc(m);
+    return false;
+  });
+  __syncwarp();
+  return base;
+}
+
+// ascending rank sort of the n <= kSlotCap distinct ids in stage -> dst[0..n)
+__device__ __forceinline__ void rankSortToGlobal(const int *stage, int n, int *__restrict__ dst, int lane)
+{
+  for (int i = lane; i < n; i += 32) {
+    const int v = stage[i];
+    int       rank = 0;
+    int       j = 0;
+    for (; j + 4 <= n; j += 4) {
+      const int4 q = *reinterpret_cast<const int4 *>(stage + j);
+      rank += (q.x < v) + (q.y < v) + (q.z < v) + (q.w < v);
+    }
+    for (; j < n; ++j)
+      rank += stage[j] < v;
+    dst[rank] = v;
+  }
+}
+
+__global__ void memberGatherKernel(const double *__restrict__ centers, int64_t nClusters, BinGridView gin, BinGridView gout, double rIn, double rOut,
+                                   int *__restrict__ nIn, int *__restrict__ nOut, long long *__restrict__ tri, int *__restrict__ slotIn,
+                                   int *__restrict__ slotOut, int *__restrict__ overflow)
+{
+  __shared__ __align__(16) int stage[kWarpsPerBlock][kSlotCap];
+  const int64_t c    = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int     lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (c >= nClusters)
+    return;
+  const double cx = centers[3 * c], cy = centers[3 * c + 1], cz = centers[3 * c + 2];
+  const int    ci = gatherToShared(gin, cx, cy, cz, rIn, stage[w], lane);
+  if (ci <= kSlotCap)
+    rankSortToGlobal(stage[w], ci, slotIn + c * kSlotCap, lane);
+  __syncwarp();
+  const int co = gatherToShared(gout, cx, cy, cz, rOut, stage[w], lane);
+  if (co <= kSlotCap)
+    rankSortToGlobal(stage[w], co, slotOut + c * kSlotCap, lane);
+  if (lane == 0) {
+    nIn[c]  = ci;
+    nOut[c] = co;
+    tri[c]  = (static_cast<long long>(ci) * (ci + 1) / 2 + 1) & ~1LL; // even count: 16-byte aligned factors for the TMA bulk copy
+    if (ci > kSlotCap || co > kSlotCap)
+      atomicOr(overflow, 1);
+  }
+}
+
+__global__ void memberPackKernel(int64_t nClusters, const int *__restrict__ nIn, const int *__restrict__ nOut, const long long *__restrict__ inOff,
+                                 const long long *__restrict__ outOff, const int *__restrict__ slotIn, const int *__restrict__ slotOut,
+                                 int *__restrict__ inIds, int *__restrict__ outIds)
+{
+  const int64_t c    = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int     lane = threadIdx.x & 31;
+  if (c >= nClusters)
+    return;
+  const int  ni = nIn[c], no = nOut[c];
+  int       *di = inIds + inOff[c], *dO = outIds + outOff[c];
+  const int *si = slotIn + c * kSlotCap, *so = slotOut + c * kSlotCap;
+  for (int i = lane; i < ni; i += 32)
+    di[i] = si[i];
+  for (int i = lane; i < no; i += 32)
+    dO[i] = so[i];
 }
 
 __global__ void memberFillKernel(const double *__restrict__ centers, int64_t nClusters, BinGridView gin, BinGridView gout, double rIn, double rOut,
@@ -416,7 +467,8 @@ int64_t PumClustering::compact(DevBuf<double> &out, cudaStream_t s)
   return count;
 }
 
-void pumBuildMembership(const double *dCenters, int64_t nClusters, const BinGrid &inMesh, const BinGrid &outMesh, double radius, PumMembership &m, cudaStream_t s)
+void pumBuildMembership(const double *dCenters, int64_t nClusters, const BinGrid &inMesh, const BinGrid &outMesh, double radius, PumMembership &m,
+                        PumScratch &scratch, cudaStream_t s)
 {
   const double rOut = radius - kZeroDiff; // SphericalVertexCluster.hpp:155
   DevBuf<int>  nIn, nOut;
@@ -428,25 +480,40 @@ void pumBuildMembership(const double *dCenters, int64_t nClusters, const BinGrid
   m.matOff.alloc(nClusters + 1);
   m.nIn.alloc(nClusters);
   m.nOut.alloc(nClusters);
-  memberCountKernel<<<warpGrid(nClusters), kBlockThreads, 0, s>>>(dCenters, nClusters, inMesh.view(), outMesh.view(), radius, rOut, m.nIn.p, m.nOut.p,
-                                                                 reinterpret_cast<long long *>(m.tri.p));
+  DevBuf<int> &slotIn = scratch.slotIn, &slotOut = scratch.slotOut;
+  const size_t slots  = static_cast<size_t>(std::max<int64_t>(nClusters, 1)) * kSlotCap;
+  if (slotIn.n < slots) { // grow only
+    slotIn.alloc(slots + slots / 8);
+    slotOut.alloc(slots + slots / 8);
+  }
+  DevBuf<int> overflow;
+  overflow.alloc(1);
+  RBF_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), s));
+  memberGatherKernel<<<warpGrid(nClusters), kBlockThreads, 0, s>>>(dCenters, nClusters, inMesh.view(), outMesh.view(), radius, rOut, m.nIn.p, m.nOut.p,
+                                                                  reinterpret_cast<long long *>(m.tri.p), slotIn.p, slotOut.p, overflow.p);
   RBF_LAUNCHED();
   exclusiveScan(m.nIn.p, m.inOff.p, nClusters, s);
   exclusiveScan(m.nOut.p, m.outOff.p, nClusters, s);
   exclusiveScan(m.tri.p, m.matOff.p, nClusters, s);
   int64_t totals[3];
+  int     over = 0;
   RBF_CUDA(cudaMemcpyAsync(&totals[0], m.inOff.p + nClusters, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
   RBF_CUDA(cudaMemcpyAsync(&totals[1], m.outOff.p + nClusters, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
   RBF_CUDA(cudaMemcpyAsync(&totals[2], m.matOff.p + nClusters, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  RBF_CUDA(cudaMemcpyAsync(&over, overflow.p, sizeof(int), cudaMemcpyDeviceToHost, s));
   RBF_CUDA(cudaStreamSynchronize(s));
   m.sumIn  = totals[0];
   m.sumOut = totals[1];
   m.sumTri = totals[2];
   m.inIds.alloc(std::max<int64_t>(m.sumIn, 1));
   m.outIds.alloc(std::max<int64_t>(m.sumOut, 1));
-  memberFillKernel<<<warpGrid(nClusters), kBlockThreads, 0, s>>>(dCenters, nClusters, inMesh.view(), outMesh.view(), radius, rOut,
-                                                                reinterpret_cast<const long long *>(m.inOff.p), reinterpret_cast<const long long *>(m.outOff.p),
-                                                                m.inIds.p, m.outIds.p);
+  if (!over)
+    memberPackKernel<<<warpGrid(nClusters), kBlockThreads, 0, s>>>(nClusters, m.nIn.p, m.nOut.p, reinterpret_cast<const long long *>(m.inOff.p),
+                                                                  reinterpret_cast<const long long *>(m.outOff.p), slotIn.p, slotOut.p, m.inIds.p, m.outIds.p);
+  else // clusters beyond the slot size: two-pass fill with the (exact) sizes counted above
+    memberFillKernel<<<warpGrid(nClusters), kBlockThreads, 0, s>>>(dCenters, nClusters, inMesh.view(), outMesh.view(), radius, rOut,
+                                                                  reinterpret_cast<const long long *>(m.inOff.p), reinterpret_cast<const long long *>(m.outOff.p),
+                                                                  m.inIds.p, m.outIds.p);
   RBF_LAUNCHED();
   RBF_CUDA(cudaGetLastError());
 }

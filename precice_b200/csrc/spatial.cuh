@@ -80,6 +80,55 @@ __device__ __forceinline__ void forNeighbourhoodWarp(const BinGridView &g, doubl
     }
 }
 
+// Same candidates, flattened: the (2H+1)^2 z-runs of the neighbourhood are looked up by (2H+1)^2 lanes at once (one
+// memory latency instead of one per run), their lengths are prefix-summed across the warp, and the concatenated
+// candidate list is walked 32 at a time, so every lane has work in every iteration (a run holds ~35 points at 50
+// vertices per cluster: run-by-run the second iteration of each run is almost empty).
+// f(pos, valid) is called by all 32 lanes; it returns true (warp-uniform) to stop early.
+template <int H = 1, typename F>
+__device__ __forceinline__ void forCandidatesWarp(const BinGridView &g, double cx, double cy, double cz, int lane, F &&f)
+{
+  constexpr int      W = 2 * H + 1, R = W * W;
+  constexpr unsigned kFull = 0xffffffffu;
+  static_assert(R <= 32, "one lane per z-run");
+  const int ix = cellCoordUnclamped(cx, g.ox, g.ihx, g.nx);
+  const int iy = cellCoordUnclamped(cy, g.oy, g.ihy, g.ny);
+  const int iz = cellCoordUnclamped(cz, g.oz, g.ihz, g.nz);
+  const int z0 = max(iz - H, 0), z1 = min(iz + H, g.nz - 1);
+  int       beg = 0, len = 0;
+  if (lane < R && z0 <= z1) {
+    const int x = ix + lane / W - H, y = iy + lane % W - H;
+    if (x >= 0 && x < g.nx && y >= 0 && y < g.ny) {
+      const int row = (x * g.ny + y) * g.nz;
+      beg           = g.cellStart[row + z0];
+      len           = g.cellStart[row + z1 + 1] - beg;
+    }
+  }
+  int incl = len;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(kFull, incl, o);
+    if (lane >= o)
+      incl += t;
+  }
+  const int total = __shfl_sync(kFull, incl, 31);
+  const int excl  = incl - len;
+  for (int base = 0; base < total; base += 32) {
+    const int t = base + lane;
+    int       r = 0; // number of runs that end at or before candidate t (binary search over the inclusive sums)
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+      const int v = __shfl_sync(kFull, incl, r + step - 1);
+      if (v <= t)
+        r += step;
+    }
+    r             = min(r, 31);
+    const int pos = __shfl_sync(kFull, beg, r) + (t - __shfl_sync(kFull, excl, r));
+    if (f(pos, t < total))
+      return;
+  }
+}
+
 // single-thread variant: f(pos) for every binned point of the neighbourhood
 template <typename F>
 __device__ __forceinline__ void forNeighbourhoodThread(const BinGridView &g, double cx, double cy, double cz, F &&f)
