@@ -122,6 +122,106 @@ __device__ __forceinline__ double pairBasis(double ax, double ay, double az, dou
   }
 }
 
+// N independent pair evaluations written stage by stage. A warp issues in order and a dependent FP64 operation waits
+// ~16-20 cycles for its operand, so a single evaluation (a chain of ~20 dependent operations) uses a twentieth of the
+// pipe; ptxas does not interleave unrolled iterations by itself, but it keeps this order. All N pairs share the point a.
+template <int KIND, bool DIM3, int N>
+__device__ __forceinline__ void pairBasisBatch(double ax, double ay, double az, const double (&bx)[N], const double (&by)[N], const double (&bz)[N],
+                                               const RbfParams &f, double invR2, double (&out)[N])
+{
+  if (FastBasis<KIND>::value) {
+    double x[N], y[N], s[N], e[N], p[N], q[N], q2[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const double dx = ax - bx[i];
+      x[i]            = dx * dx;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const double dy = ay - by[i];
+      x[i]            = fma(dy, dy, x[i]);
+    }
+    if (DIM3) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const double dz = az - bz[i];
+        x[i]            = fma(dz, dz, x[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      x[i] = fma(x[i], invR2, 1.0e-300);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      if (__double2hiint(x[i]) >= 0x3ff00000)
+        x[i] = 1.0;
+      asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y[i]) : "d"(x[i]));
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      s[i] = x[i] * y[i];
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      e[i] = fma(-s[i], y[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      y[i] = fma(0.375, e[i], 0.5);
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      e[i] = e[i] * y[i];
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      p[i] = fma(s[i], e[i], s[i]);
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      q[i] = 1.0 - p[i];
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      q2[i] = q[i] * q[i];
+    if (KIND == RBFMAP_COMPACT_POLYNOMIAL_C0) {
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+        out[i] = q2[i];
+    } else if (KIND == RBFMAP_COMPACT_POLYNOMIAL_C2) {
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+        out[i] = (q2[i] * q2[i]) * fma(4.0, p[i], 1.0);
+    } else if (KIND == RBFMAP_COMPACT_POLYNOMIAL_C4) {
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+        out[i] = (q2[i] * q2[i] * q2[i]) * fma(fma(35.0, p[i], 18.0), p[i], 3.0);
+    } else if (KIND == RBFMAP_COMPACT_POLYNOMIAL_C6) {
+      double h[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        q2[i] = q2[i] * q2[i]; // q^4
+        h[i]  = fma(32.0, p[i], 25.0);
+      }
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        q2[i] = q2[i] * q2[i]; // q^8
+        h[i]  = fma(h[i], p[i], 8.0);
+      }
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+        h[i] = fma(h[i], p[i], 1.0);
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+        out[i] = q2[i] * h[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const double q4 = q2[i] * q2[i];
+        out[i]          = (q4 * q4 * q2[i]) * fma(fma(fma(fma(1287.0, p[i], 1350.0), p[i], 630.0), p[i], 150.0), p[i], 15.0);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      out[i] = evalBasisK<KIND>(distSqrt(sqDistD<DIM3>(ax, ay, az, bx[i], by[i], bz[i])), f);
+  }
+}
+
 // reciprocal of a positive pivot: MUFU.RCP64H seed + two Newton steps, no slow path (~1 ulp)
 __device__ __forceinline__ double pivotReciprocal(double d)
 {

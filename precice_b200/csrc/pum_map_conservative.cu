@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(NT) pumMapConservativeKernel(PumSolveArgs args
   if (STAGE_M) {
     if (tid < 32) { // one warp solves; the others wait at the barrier
       mbarWait(&mbar, 0);
-      warpSolve<NC, LDV, NT / 32>(ms, n, vt + 3, tid);
+      warpSolve<NC, LDV, (NT == 32 ? 2 : NT / 32)>(ms, n, vt + 3, tid);
     }
     __syncthreads();
   } else {

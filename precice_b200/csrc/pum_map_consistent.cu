@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(NT) pumMapConsistentKernel(PumSolveArgs args, 
   if (STAGE_M) {
     if (tid < 32) { // one warp solves; the others wait at the barrier
       mbarWait(&mbar, 0);
-      warpSolve<NC, LDV, NT / 32>(ms, n, vt + 3, tid);
+      warpSolve<NC, LDV, (NT == 32 ? 2 : NT / 32)>(ms, n, vt + 3, tid);
     }
     __syncthreads();
   } else {
@@ -142,41 +142,83 @@ __global__ void __launch_bounds__(NT) pumMapConsistentKernel(PumSolveArgs args, 
   }
 
   // ---- out = A lambda + V beta, weighted accumulation (SphericalVertexCluster.hpp:322-334) ----
-  for (int o = tid; o < m; o += NT) {
-    const long long gid = oids[o];
-    const double   *p   = args.outXyz + 3 * gid;
-    const double    x = p[0], y = p[1], z = p[2];
-    double          acc[NC];
+  // One out-vertex per lane and pass. When the last pass has 16 or fewer vertices left, 2 / 4 / 8 lanes share a vertex
+  // (each takes every 2nd / 4th / 8th in-vertex, partial sums are combined with shuffles) so that no lane idles.
+  for (int o0 = 0; o0 < m; o0 += NT) {
+    const int rem   = m - o0;
+    const int split = (NT == 32 && rem <= 16) ? (rem <= 4 ? 8 : rem <= 8 ? 4 : 2) : 1;
+    const int per   = NT / split;
+    const int ol = tid % per, sub = tid / per;
+    const bool have = ol < rem;
+    long long  gid = 0;
+    double     x = 0.0, y = 0.0, z = 0.0;
+    if (have) {
+      gid             = oids[o0 + ol];
+      const double *p = args.outXyz + 3 * gid;
+      x = p[0], y = p[1], z = p[2];
+    }
+    double acc[NC];
 #pragma unroll
     for (int cc = 0; cc < NC; ++cc)
       acc[cc] = 0.0;
-    const double *vp = vt;
-#pragma unroll 4
-    for (int j = 0; j < n; ++j, vp += LDV) {
-      const double2 xy = *reinterpret_cast<const double2 *>(vp);
-      const double2 zb = *reinterpret_cast<const double2 *>(vp + 2);
-      const double  phi = pairBasis<KIND, DIM3>(x, y, z, xy.x, xy.y, zb.x, rbf, invR2);
-      acc[0]            = fma(phi, zb.y, acc[0]);
-      if (NC > 1) {
-        const double2 b12 = *reinterpret_cast<const double2 *>(vp + 4);
-        acc[1]            = fma(phi, b12.x, acc[1]);
-        if (NC > 2)
-          acc[2] = fma(phi, b12.y, acc[2]);
+    if (have) {
+      const double *vp = vt + sub * LDV;
+      const int     stride = split * LDV;
+      int j = sub;
+      for (; j + 3 * split < n; j += 4 * split, vp += 4 * stride) { // four in-vertices side by side (see pairBasisBatch)
+        double bx[4], by[4], bz[4], cf[4][NC], phi[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const double2 xy = *reinterpret_cast<const double2 *>(vp + u * stride);
+          const double2 zb = *reinterpret_cast<const double2 *>(vp + u * stride + 2);
+          bx[u] = xy.x, by[u] = xy.y, bz[u] = zb.x, cf[u][0] = zb.y;
+          if (NC > 1) {
+            const double2 b12 = *reinterpret_cast<const double2 *>(vp + u * stride + 4);
+            cf[u][1]          = b12.x;
+            if (NC > 2)
+              cf[u][2] = b12.y;
+          }
+        }
+        pairBasisBatch<KIND, DIM3, 4>(x, y, z, bx, by, bz, rbf, invR2, phi);
+#pragma unroll
+        for (int cc = 0; cc < NC; ++cc)
+          acc[cc] += fma(phi[0], cf[0][cc], phi[1] * cf[1][cc]) + fma(phi[2], cf[2][cc], phi[3] * cf[3][cc]);
+      }
+      for (; j < n; j += split, vp += stride) {
+        const double2 xy  = *reinterpret_cast<const double2 *>(vp);
+        const double2 zb  = *reinterpret_cast<const double2 *>(vp + 2);
+        const double  phi = pairBasis<KIND, DIM3>(x, y, z, xy.x, xy.y, zb.x, rbf, invR2);
+        acc[0]            = fma(phi, zb.y, acc[0]);
+        if (NC > 1) {
+          const double2 b12 = *reinterpret_cast<const double2 *>(vp + 4);
+          acc[1]            = fma(phi, b12.x, acc[1]);
+          if (NC > 2)
+            acc[2] = fma(phi, b12.y, acc[2]);
+        }
       }
     }
-    if (polyMode != 0) {
-      double q[4];
-      polyRow(polyMode, polyMask, x, y, z, cx, cy, cz, rinv, q);
+    if (split > 1) { // warp-uniform
+      for (int o = per; o < 32; o <<= 1) {
+#pragma unroll
+        for (int cc = 0; cc < NC; ++cc)
+          acc[cc] += __shfl_xor_sync(0xffffffffu, acc[cc], o);
+      }
+    }
+    if (have && sub == 0) {
+      if (polyMode != 0) {
+        double q[4];
+        polyRow(polyMode, polyMask, x, y, z, cx, cy, cz, rinv, q);
+#pragma unroll
+        for (int cc = 0; cc < NC; ++cc)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            acc[cc] += q[k] * beta[k][cc];
+      }
+      const double w = normalizedWeight(x, y, z, cx, cy, cz, rinv, args.wsum[gid], args.wcount[gid]);
 #pragma unroll
       for (int cc = 0; cc < NC; ++cc)
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          acc[cc] += q[k] * beta[k][cc];
+        atomicAdd(&out[gid * dims + c0 + cc], acc[cc] * w);
     }
-    const double w = normalizedWeight(x, y, z, cx, cy, cz, rinv, args.wsum[gid], args.wcount[gid]);
-#pragma unroll
-    for (int cc = 0; cc < NC; ++cc)
-      atomicAdd(&out[gid * dims + c0 + cc], acc[cc] * w);
   }
 }
 
@@ -201,7 +243,7 @@ template <int KIND, int NC>
 void bucketConsistent(const PumSolveArgs &a, int bucket, const int *list, int64_t count, int maxN, const double *in, int dims, int c0, double *out, cudaStream_t s)
 {
   if (bucket < 8)
-    launchConsistent<KIND, NC, 64, true>(a, list, count, maxN, in, dims, c0, out, s);
+    launchConsistent<KIND, NC, 32, true>(a, list, count, maxN, in, dims, c0, out, s);
   else if (bucket < 12)
     launchConsistent<KIND, NC, 128, true>(a, list, count, maxN, in, dims, c0, out, s);
   else
