@@ -91,7 +91,23 @@ class ClockSampler(threading.Thread):
         except Exception:
             self.nv = None
 
+    # NVML queries take a driver lock; issued from a second thread they stall the CUDA API calls of the step that runs
+    # beside them (measured on this box: single steps of 33 - 234 ms instead of 20.6, worst with
+    # nvmlDeviceGetCurrentClocksThrottleReasons). The main thread therefore samples BETWEEN the timed steps - inside the
+    # timed region, GPU still at its load clocks, but never concurrently with a step: the SM clock after every step
+    # (poll_clock), the throttle reasons before the first and after the last step (poll_reasons).
     def run(self):
+        return
+
+    def poll_clock(self):
+        if self.nv is None:
+            return
+        try:
+            self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+        except Exception:
+            pass
+
+    def poll_reasons(self):
         if self.nv is None:
             return
         nv = self.nv
@@ -99,16 +115,13 @@ class ClockSampler(threading.Thread):
                  nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
                  nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
                  nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
-        while not self._stop_evt.is_set():
-            try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in names.items():
-                    if r & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
-            self._stop_evt.wait(0.05)
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, name in names.items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
 
     def stop(self):
         self._stop_evt.set()
@@ -228,12 +241,18 @@ def main():
     barrier()
     t0 = time.perf_counter()
     ev_ms, asm_ms, map_ms, launches = 0.0, 0.0, 0.0, 0
+    sampler.poll_reasons()
     for _ in range(args.steps):
         st = step_device()
         ev_ms += st["ms_compute_kernels"] + st["ms_map_kernels"]  # CUDA events on the library's stream, whole calls
         asm_ms += st["ms_assembly_factor"]
         map_ms += st["ms_map_kernels"]
         launches += st["kernel_launches"]
+        sampler.poll_clock()
+        if os.environ.get("BENCH_VERBOSE"):
+            print(f"[bench] step: compute {st['ms_compute_kernels']:.2f} ms (factor {st['ms_assembly_factor']:.2f}) map {st['ms_map_kernels']:.2f} ms",
+                  file=sys.stderr, flush=True)
+    sampler.poll_reasons()
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop()
