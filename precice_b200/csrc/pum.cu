@@ -311,18 +311,16 @@ void PumMapping::computeMapping(const double *dInputXyz, int64_t nInput, const d
   stats.cluster_radius = _radius;
 
   // per-cluster vertex sets (SphericalVertexCluster.hpp:153-162)
-  pumBuildMembership(_centers.p, _nClusters, inGrid, outGrid, _radius, _mem, _scratch, _stream);
+  _wsum.alloc(_nOut);
+  _wcount.alloc(_nOut);
+  RBF_CUDA(cudaMemsetAsync(_wsum.p, 0, _nOut * sizeof(double), _stream));
+  RBF_CUDA(cudaMemsetAsync(_wcount.p, 0, _nOut * sizeof(int), _stream));
+  pumBuildMembership(_centers.p, _nClusters, inGrid, outGrid, _radius, _mem, _scratch, _wsum.p, _wcount.p, _stream);
   trace.phase("membership");
 
   // partition-of-unity weight sums (PartitionOfUnityMapping.hpp:263-276, 290-341)
   {
-    double cMin[3], cMax[3];
-    computeBounds(_centers.p, _nClusters, cMin, cMax, _stream);
-    BinGrid centerGrid;
-    centerGrid.build(_centers.p, _nClusters, cMin, cMax, _radius, _stream);
-    _wsum.alloc(_nOut);
-    _wcount.alloc(_nOut);
-    const int64_t bad = pumWeightSums(_outXyz.p, _nOut, centerGrid, _radius, _wsum.p, _wcount.p, _stream);
+    const int64_t bad = pumFirstUnassigned(_wcount.p, _nOut, _stream);
     if (bad >= 0) {
       double v[3];
       RBF_CUDA(cudaMemcpy(v, _outXyz.p + 3 * bad, sizeof(v), cudaMemcpyDeviceToHost));

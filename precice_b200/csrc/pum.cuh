@@ -49,8 +49,8 @@ struct PumScratch {
 };
 
 void    pumBuildMembership(const double *dCenters, int64_t nClusters, const BinGrid &inMesh, const BinGrid &outMesh, double radius, PumMembership &m,
-                           PumScratch &scratch, cudaStream_t s);
-int64_t pumWeightSums(const double *dOutXyz, int64_t nOut, const BinGrid &centerGrid, double radius, double *wsum, int *wcount, cudaStream_t s);
+                           PumScratch &scratch, double *wsum, int *wcount, cudaStream_t s);
+int64_t pumFirstUnassigned(const int *wcount, int64_t nOut, cudaStream_t s); // -1: every out-vertex lies in a cluster
 
 // Per-cluster separated-polynomial record (RadialBasisFctSolver.hpp:377-410 condensed).
 //  mode 0: no polynomial

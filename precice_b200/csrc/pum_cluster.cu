@@ -6,7 +6,7 @@
 //   impl/CreateClustering.hpp:96-122, 173-195  getNeighborsWithinSphere / tagDuplicateCenters
 //   impl/CreateClustering.hpp:205-208  removeTaggedVertices
 //   impl/SphericalVertexCluster.hpp:153-162  per-cluster sphere queries + sorted ID sets
-//   PartitionOfUnityMapping.hpp:290-341  computeNormalizedWeight (the per-vertex weight sums)
+//   PartitionOfUnityMapping.hpp:290-341  computeNormalizedWeight (the per-vertex weight sums, accumulated from the cluster side)
 #include "pum.cuh"
 
 #include <algorithm>
@@ -228,16 +228,31 @@ __device__ void gatherMembers(const BinGridView &g, double cx, double cy, double
 // the host then falls back to the two-pass fill above (the sizes are exact in either case). ----
 constexpr int kSlotCap = 128;
 
-// ids of the vertices of grid g within radius r of the centre -> stage (unsorted, first kSlotCap hits); returns the count
-__device__ __forceinline__ int gatherToShared(const BinGridView &g, double cx, double cy, double cz, double r, int *stage, int lane)
+// ids of the vertices of grid g within radius r of the centre -> stage (unsorted, first kSlotCap hits); returns the count.
+// WEIGHTS (out-mesh pass): every vertex within rW of the centre also receives this cluster's partition-of-unity weight,
+// PartitionOfUnityMapping.hpp:306-333 seen from the cluster side: w_c = C2(|x - c| / r) is added to the weight sum of
+// the vertex and its cluster count is incremented (the reference loops over the clusters of a vertex instead).
+template <bool WEIGHTS>
+__device__ __forceinline__ int gatherToShared(const BinGridView &g, double cx, double cy, double cz, double r, int *stage, int lane, double rW = 0.0,
+                                              double rinv = 0.0, double *__restrict__ wsum = nullptr, int *__restrict__ wcount = nullptr)
 {
   int base = 0;
   forCandidatesWarp(g, cx, cy, cz, lane, [&](int pos, bool valid) {
-    const bool     hit = valid && __dsqrt_rn(sqDist3(cx, cy, cz, g.xyz[3 * pos], g.xyz[3 * pos + 1], g.xyz[3 * pos + 2])) < r;
+    double d = 1.7976931348623157e308;
+    if (valid) // computeWeight (SphericalVertexCluster.hpp:337-344): squared difference (centre, vertex)
+      d = __dsqrt_rn(sqDist3(cx, cy, cz, g.xyz[3 * pos], g.xyz[3 * pos + 1], g.xyz[3 * pos + 2]));
+    const bool     hit = d < r;
     const unsigned m   = __ballot_sync(0xffffffffu, hit);
     const int      at  = base + __popc(m & ((1u << lane) - 1u));
+    int            id  = 0;
+    if (hit || (WEIGHTS && d < rW))
+      id = g.ids[pos];
     if (hit && at < kSlotCap)
-      stage[at] = g.ids[pos];
+      stage[at] = id;
+    if (WEIGHTS && d < rW) {
+      atomicAdd(wsum + id, pumWeight(d, rinv));
+      atomicAdd(wcount + id, 1);
+    }
     base += __popc(m);
     return false;
   });
@@ -264,7 +279,7 @@ __device__ __forceinline__ void rankSortToGlobal(const int *stage, int n, int *_
 
 __global__ void memberGatherKernel(const double *__restrict__ centers, int64_t nClusters, BinGridView gin, BinGridView gout, double rIn, double rOut,
                                    int *__restrict__ nIn, int *__restrict__ nOut, long long *__restrict__ tri, int *__restrict__ slotIn,
-                                   int *__restrict__ slotOut, int *__restrict__ overflow)
+                                   int *__restrict__ slotOut, int *__restrict__ overflow, double *__restrict__ wsum, int *__restrict__ wcount)
 {
   __shared__ __align__(16) int stage[kWarpsPerBlock][kSlotCap];
   const int64_t c    = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
@@ -272,11 +287,11 @@ __global__ void memberGatherKernel(const double *__restrict__ centers, int64_t n
   if (c >= nClusters)
     return;
   const double cx = centers[3 * c], cy = centers[3 * c + 1], cz = centers[3 * c + 2];
-  const int    ci = gatherToShared(gin, cx, cy, cz, rIn, stage[w], lane);
+  const int    ci = gatherToShared<false>(gin, cx, cy, cz, rIn, stage[w], lane);
   if (ci <= kSlotCap)
     rankSortToGlobal(stage[w], ci, slotIn + c * kSlotCap, lane);
   __syncwarp();
-  const int co = gatherToShared(gout, cx, cy, cz, rOut, stage[w], lane);
+  const int co = gatherToShared<true>(gout, cx, cy, cz, rOut, stage[w], lane, rIn, 1.0 / rIn, wsum, wcount);
   if (co <= kSlotCap)
     rankSortToGlobal(stage[w], co, slotOut + c * kSlotCap, lane);
   if (lane == 0) {
@@ -322,28 +337,11 @@ __global__ void memberFillKernel(const double *__restrict__ centers, int64_t nCl
   warpSortSegment(segOut, no, stage[w], kSortCap, lane);
 }
 
-// ---- weight sums: one thread per out-vertex -------------------------------------------------
-// PartitionOfUnityMapping.hpp:306-333: clusters with |x - c| < r; w_c = C2(|x - c| / r); sum of w.
-__global__ void weightSumKernel(const double *__restrict__ outXyz, int64_t nOut, BinGridView gc, double radius, double rinv, double *__restrict__ wsum,
-                                int *__restrict__ wcount, int *__restrict__ firstUnassigned)
+// ---- out-vertices that no cluster covers (PartitionOfUnityMapping.hpp:312-320) ----
+__global__ void unassignedKernel(const int *__restrict__ wcount, int64_t nOut, int *__restrict__ firstUnassigned)
 {
   const int64_t v = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  if (v >= nOut)
-    return;
-  const double x = outXyz[3 * v], y = outXyz[3 * v + 1], z = outXyz[3 * v + 2];
-  double       sum = 0.0;
-  int          cnt = 0;
-  forNeighbourhoodThread(gc, x, y, z, [&](int pos) {
-    // computeWeight (SphericalVertexCluster.hpp:337-344): squared difference (centre, vertex)
-    const double d = __dsqrt_rn(sqDist3(gc.xyz[3 * pos], gc.xyz[3 * pos + 1], gc.xyz[3 * pos + 2], x, y, z));
-    if (d < radius) {
-      sum = __dadd_rn(sum, pumWeight(d, rinv));
-      ++cnt;
-    }
-  });
-  wsum[v]   = sum;
-  wcount[v] = cnt;
-  if (cnt == 0)
+  if (v < nOut && wcount[v] == 0)
     atomicMin(firstUnassigned, static_cast<int>(v));
 }
 
@@ -468,7 +466,7 @@ int64_t PumClustering::compact(DevBuf<double> &out, cudaStream_t s)
 }
 
 void pumBuildMembership(const double *dCenters, int64_t nClusters, const BinGrid &inMesh, const BinGrid &outMesh, double radius, PumMembership &m,
-                        PumScratch &scratch, cudaStream_t s)
+                        PumScratch &scratch, double *wsum, int *wcount, cudaStream_t s)
 {
   const double rOut = radius - kZeroDiff; // SphericalVertexCluster.hpp:155
   DevBuf<int>  nIn, nOut;
@@ -490,7 +488,7 @@ void pumBuildMembership(const double *dCenters, int64_t nClusters, const BinGrid
   overflow.alloc(1);
   RBF_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), s));
   memberGatherKernel<<<warpGrid(nClusters), kBlockThreads, 0, s>>>(dCenters, nClusters, inMesh.view(), outMesh.view(), radius, rOut, m.nIn.p, m.nOut.p,
-                                                                  reinterpret_cast<long long *>(m.tri.p), slotIn.p, slotOut.p, overflow.p);
+                                                                  reinterpret_cast<long long *>(m.tri.p), slotIn.p, slotOut.p, overflow.p, wsum, wcount);
   RBF_LAUNCHED();
   exclusiveScan(m.nIn.p, m.inOff.p, nClusters, s);
   exclusiveScan(m.nOut.p, m.outOff.p, nClusters, s);
@@ -518,13 +516,13 @@ void pumBuildMembership(const double *dCenters, int64_t nClusters, const BinGrid
   RBF_CUDA(cudaGetLastError());
 }
 
-int64_t pumWeightSums(const double *dOutXyz, int64_t nOut, const BinGrid &centerGrid, double radius, double *wsum, int *wcount, cudaStream_t s)
+int64_t pumFirstUnassigned(const int *wcount, int64_t nOut, cudaStream_t s)
 {
   DevBuf<int> first;
   first.alloc(1);
   RBF_CUDA(cudaMemsetAsync(first.p, 0x7f, sizeof(int), s));
   if (nOut > 0) {
-    weightSumKernel<<<divUp(nOut, 256), 256, 0, s>>>(dOutXyz, nOut, centerGrid.view(), radius, 1.0 / radius, wsum, wcount, first.p);
+    unassignedKernel<<<divUp(nOut, 256), 256, 0, s>>>(wcount, nOut, first.p);
     RBF_LAUNCHED();
   }
   int f = 0;
