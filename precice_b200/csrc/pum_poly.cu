@@ -168,9 +168,25 @@ __global__ void polySetupKernel(PumSolveArgs a, int64_t nClusters)
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       m[i][j] = 0.0;
+  // ... and of the centred/scaled basis [1, (x_a - c_a)/r] over all three axes: the Gram matrix of the axes that survive
+  // the condition test below is a sub-matrix of it, so the vertices are gathered only once
+  const double cx = a.centers[3 * c], cy = a.centers[3 * c + 1], cz = a.centers[3 * c + 2];
+  const double rinv = 1.0 / a.radius;
+  double       mc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      mc[i][j] = 0.0;
   for (int i = 0; i < n; ++i) {
     const double *x    = a.inXyz + 3 * static_cast<long long>(ids[i]);
     const double  q[4] = {1.0, x[0], x[1], x[2]};
+    const double  qc[4] = {1.0, (x[0] - cx) * rinv, (x[1] - cy) * rinv, (x[2] - cz) * rinv};
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int s2 = r; s2 < 4; ++s2)
+        mc[r][s2] += qc[r] * qc[s2];
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       lo[d] = fmin(lo[d], x[d]);
@@ -263,25 +279,37 @@ __global__ void polySetupKernel(PumSolveArgs a, int64_t nClusters)
 
   if (n >= p) {
     rec.mode = 1;
-    // Gram matrix of the centred/scaled basis [1, (x_a - c_a)/r] over the active axes, then its inverse
-    const double cx = a.centers[3 * c], cy = a.centers[3 * c + 1], cz = a.centers[3 * c + 2];
-    const double rinv = 1.0 / a.radius;
-    double       g[4][4];
+    // Gram matrix of the centred/scaled basis over the active axes (polyRow packs the active axes in increasing
+    // order into q[1..p-1]), then its inverse
+    int sel[4] = {0, 0, 0, 0}; // basis index -> slot of the full basis
+    {
+      int k = 1;
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+        if (mask & (1 << d)) {
+          if (k == 1) sel[1] = d + 1;
+          else if (k == 2) sel[2] = d + 1;
+          else sel[3] = d + 1;
+          ++k;
+        }
+    }
+    double g[4][4];
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
-      for (int s = 0; s < 4; ++s)
-        g[r][s] = 0.0;
-    for (int i = 0; i < n; ++i) {
-      const double *x = a.inXyz + 3 * static_cast<long long>(ids[i]);
-      double        q[4];
-      polyRow(1, mask, x[0], x[1], x[2], cx, cy, cz, rinv, q);
+      for (int s2 = 0; s2 < 4; ++s2) {
+        double v = 0.0;
+        if (r < p && s2 < p) {
+          const int fr = sel[r], fs = sel[s2];
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
+          for (int u = 0; u < 4; ++u)
 #pragma unroll
-        for (int s = 0; s < 4; ++s)
-          g[r][s] += q[r] * q[s];
-    }
+            for (int w = 0; w < 4; ++w)
+              if (u == (fr < fs ? fr : fs) && w == (fr < fs ? fs : fr))
+                v = mc[u][w];
+        }
+        g[r][s2] = v;
+      }
 #pragma unroll
     for (int r = 0; r < 4; ++r)
       if (r >= p)
