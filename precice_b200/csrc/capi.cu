@@ -244,6 +244,8 @@ int rbfmap_compute_mapping(rbfmap_handle *h, const double *input_xyz, int64_t n_
   return guarded(h, [&] {
     if (n_input < 0 || n_output < 0)
       throw MapError(RBFMAP_ERR_INVALID, "negative mesh size");
+    if (h->impl->computeMappingHost(input_xyz, n_input, output_xyz, n_output))
+      return;
     cudaStream_t     s = h->impl->stream();
     AllocStreamScope allocScope(s);
     h->dInXyz.alloc(3 * std::max<int64_t>(n_input, 1));

@@ -18,6 +18,10 @@ public:
 
   // input/output = Mapping::input()/output() coordinates on the device (AoS n x 3)
   virtual void        computeMapping(const double *dInputXyz, int64_t nInput, const double *dOutputXyz, int64_t nOutput) = 0;
+  // host-pointer variant behind rbfmap_compute_mapping; returns false if the variant has no own implementation (the
+  // caller then stages both meshes on the device and calls computeMapping). rbf-pum-direct overrides it to overlap the
+  // upload of the second mesh with the work that only needs the first one.
+  virtual bool computeMappingHost(const double * /*hInputXyz*/, int64_t /*nInput*/, const double * /*hOutputXyz*/, int64_t /*nOutput*/) { return false; }
   virtual void        mapConsistent(const double *dIn, int dims, double *dOut)                                         = 0;
   virtual void        mapConservative(const double *dIn, int dims, double *dOut)                                       = 0;
   virtual void        clear()                                                                                          = 0;

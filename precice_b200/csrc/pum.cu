@@ -52,7 +52,24 @@ public:
 
   std::string name() const override { return "partition-of-unity RBF (cuda-executor)"; }
 
-  void computeMapping(const double *dInputXyz, int64_t nInput, const double *dOutputXyz, int64_t nOutput) override;
+  void computeMapping(const double *dInputXyz, int64_t nInput, const double *dOutputXyz, int64_t nOutput) override
+  {
+    computeImpl(dInputXyz, nInput, dOutputXyz, nOutput, cudaMemcpyDeviceToDevice);
+  }
+  bool computeMappingHost(const double *hInputXyz, int64_t nInput, const double *hOutputXyz, int64_t nOutput) override
+  {
+    computeImpl(hInputXyz, nInput, hOutputXyz, nOutput, cudaMemcpyHostToDevice);
+    return true;
+  }
+  ~PumMapping() override
+  {
+    if (_outReady)
+      cudaEventDestroy(_outReady);
+    if (_allocReady)
+      cudaEventDestroy(_allocReady);
+    if (_copyStream)
+      cudaStreamDestroy(_copyStream);
+  }
   void mapConsistent(const double *dIn, int dims, double *dOut) override { map(false, dIn, dims, dOut); }
   void mapConservative(const double *dIn, int dims, double *dOut) override { map(true, dIn, dims, dOut); }
   void clear() override
@@ -79,6 +96,7 @@ public:
   const PumMembership  &membership() const { return _mem; }
 
 private:
+  void   computeImpl(const double *srcInputXyz, int64_t nInput, const double *srcOutputXyz, int64_t nOutput, cudaMemcpyKind kind);
   void   map(bool conservative, const double *dIn, int dims, double *dOut);
   double estimateClusterRadius(const double bbMin[3], const double bbMax[3]);
   PumSolveArgs solveArgs() const;
@@ -95,6 +113,9 @@ private:
   DevBuf<double>  _wsum;
   DevBuf<int>     _wcount;
   PumBuckets      _buckets;
+  // upload of the solver-side outMesh beside the work on the inMesh (computeMappingHost)
+  cudaStream_t _copyStream = nullptr;
+  cudaEvent_t  _allocReady = nullptr, _outReady = nullptr;
 };
 
 PumSolveArgs PumMapping::solveArgs() const
@@ -156,7 +177,7 @@ double PumMapping::estimateClusterRadius(const double bbMin[3], const double bbM
   return radii[middle];
 }
 
-void PumMapping::computeMapping(const double *dInputXyz, int64_t nInput, const double *dOutputXyz, int64_t nOutput)
+void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const double *dOutputXyz, int64_t nOutput, cudaMemcpyKind kind)
 {
   if (_computed)
     throw MapError(RBFMAP_ERR_STATE, "Please clear the mapping before recomputing."); // PartitionOfUnityMapping.hpp:188
@@ -178,9 +199,41 @@ void PumMapping::computeMapping(const double *dInputXyz, int64_t nInput, const d
   _inXyz.alloc(3 * std::max<int64_t>(_nIn, 1));
   _outXyz.alloc(3 * std::max<int64_t>(_nOut, 1));
   if (_nIn > 0)
-    RBF_CUDA(cudaMemcpyAsync(_inXyz.p, srcIn, 3 * _nIn * sizeof(double), cudaMemcpyDeviceToDevice, _stream));
-  if (_nOut > 0)
-    RBF_CUDA(cudaMemcpyAsync(_outXyz.p, srcOut, 3 * _nOut * sizeof(double), cudaMemcpyDeviceToDevice, _stream));
+    RBF_CUDA(cudaMemcpyAsync(_inXyz.p, srcIn, 3 * _nIn * sizeof(double), kind, _stream));
+  // From host memory the outMesh travels on a second stream: bounds, cluster-radius estimate and binning of the inMesh
+  // run while it is still in flight; the main stream waits for it (waitForOutMesh) right before its first use.
+  struct PendingCopy { // the host buffer must not be in use any more when this call returns, however it returns
+    cudaStream_t s       = nullptr;
+    bool         pending = false;
+    ~PendingCopy()
+    {
+      if (pending)
+        cudaStreamSynchronize(s);
+    }
+  } outCopy;
+  if (_nOut > 0) {
+    if (kind == cudaMemcpyHostToDevice) {
+      if (!_copyStream) {
+        RBF_CUDA(cudaStreamCreateWithFlags(&_copyStream, cudaStreamNonBlocking));
+        RBF_CUDA(cudaEventCreateWithFlags(&_allocReady, cudaEventDisableTiming));
+        RBF_CUDA(cudaEventCreateWithFlags(&_outReady, cudaEventDisableTiming));
+      }
+      RBF_CUDA(cudaEventRecord(_allocReady, _stream)); // the buffer comes from the stream-ordered pool of _stream
+      RBF_CUDA(cudaStreamWaitEvent(_copyStream, _allocReady, 0));
+      RBF_CUDA(cudaMemcpyAsync(_outXyz.p, srcOut, 3 * _nOut * sizeof(double), kind, _copyStream));
+      RBF_CUDA(cudaEventRecord(_outReady, _copyStream));
+      outCopy.s       = _copyStream;
+      outCopy.pending = true;
+    } else {
+      RBF_CUDA(cudaMemcpyAsync(_outXyz.p, srcOut, 3 * _nOut * sizeof(double), kind, _stream));
+    }
+  }
+  auto waitForOutMesh = [&] {
+    if (outCopy.pending) {
+      RBF_CUDA(cudaStreamWaitEvent(_stream, _outReady, 0));
+      outCopy.pending = false; // ordered behind _stream from here on; every exit path below synchronises _stream
+    }
+  };
 
   stats       = rbfmap_stats{};
   stats.n_in  = _nIn;
@@ -196,7 +249,6 @@ void PumMapping::computeMapping(const double *dInputXyz, int64_t nInput, const d
   const int dim = _cfg.dimensions;
   double    bbMin[3], bbMax[3], obMin[3], obMax[3];
   computeBounds(_inXyz.p, _nIn, bbMin, bbMax, _stream); // :334 (bounds of the inMesh)
-  computeBounds(_outXyz.p, _nOut, obMin, obMax, _stream);
   trace.phase("copy + bounds");
   auto edge = [&](int d) { return std::abs(bbMax[d] - bbMin[d]); };
 
@@ -217,6 +269,8 @@ void PumMapping::computeMapping(const double *dInputXyz, int64_t nInput, const d
     RBF_CUDA(cudaStreamSynchronize(_stream));
     _nClusters = 1;
     inGrid.build(_inXyz.p, _nIn, bbMin, bbMax, _radius, _stream);
+    waitForOutMesh();
+    computeBounds(_outXyz.p, _nOut, obMin, obMax, _stream);
     outGrid.build(_outXyz.p, _nOut, obMin, obMax, _radius, _stream);
   } else {
     _radius = estimateClusterRadius(bbMin, bbMax);
@@ -276,6 +330,8 @@ void PumMapping::computeMapping(const double *dInputXyz, int64_t nInput, const d
 
     trace.phase("lattice");
     inGrid.build(_inXyz.p, _nIn, bbMin, bbMax, _radius, _stream);
+    waitForOutMesh();
+    computeBounds(_outXyz.p, _nOut, obMin, obMax, _stream);
     outGrid.build(_outXyz.p, _nOut, obMin, obMax, _radius, _stream);
     trace.phase("bin meshes");
 
