@@ -208,6 +208,11 @@ def main():
         raise SystemExit("bench.py: no CUDA device (precice_b200 has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # NCCL announces its version on stdout when the first communicator is created; stdout carries exactly one JSON line,
+    # so file descriptor 1 points to stderr until that line is printed
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -317,13 +322,13 @@ def main():
         r_map = fp64_roofline("pumMapConsistentKernel (gather + polynomial + solve + on-the-fly evaluation + blend, all buckets)",
                               2.0 * stats["sum_n2"] + (F_PHI + 2.0) * stats["sum_mn"], map_ms)
         # DRAM traffic: `ncu --set full` capture of the same kernels on the 1M-vertex workload (profiles/r1c_*_summary.txt,
-        # dram__bytes_read.sum + dram__bytes_write.sum of the n = 49..56 bucket: 11.6 KB resp. 19.6 KB per cluster), scaled by
+        # dram__bytes_read.sum + dram__bytes_write.sum of the n = 49..56 bucket: 11.5 KB resp. 19.8 KB per cluster), scaled by
         # the number of clusters of this run. Algorithmic bytes per cluster: packed factor 8 n(n+1)/2 B (written once by the
         # factor kernel, read once per map) + 24 B per gathered vertex + 8 B per value.
-        r_factor["traffic"] = 11.6e3 * stats["n_clusters"]
-        r_map["traffic"] = 19.6e3 * stats["n_clusters"]
+        r_factor["traffic"] = 11.5e3 * stats["n_clusters"]
+        r_map["traffic"] = 19.8e3 * stats["n_clusters"]
         for r_ in (r_factor, r_map):
-            r_["traffic_source"] = "ncu capture at 1M vertices (profiles/r1c_*), bytes per cluster x clusters"
+            r_["traffic_source"] = "ncu capture at 1M vertices (profiles/r1d_*_kernel_summary.txt), bytes per cluster x clusters"
         r_factor["algorithmic_bytes"] = 8.0 * (stats["sum_n2"] + stats["sum_n"]) / 2.0 + 24.0 * stats["sum_n"]
         r_map["algorithmic_bytes"] = 8.0 * (stats["sum_n2"] + stats["sum_n"]) / 2.0 + 32.0 * stats["sum_n"] + 32.0 * stats["sum_m"]
         roofline, roofline_other = (r_factor, r_map) if asm_ms >= map_ms else (r_map, r_factor)
@@ -355,6 +360,8 @@ def main():
             for k in ("t_compute_s", "t_map_s", "total_vertices"):
                 cb.pop(k)
             line["cpu_baseline"] = cb
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
