@@ -91,6 +91,35 @@ struct DevBuf {
   size_t bytes() const { return n * sizeof(T); }
 };
 
+// Grow-only scratch outside the stream-ordered pool (plain cudaMalloc): for buffers that a mapping object keeps across
+// clear(). Kept in the pool they sit between the blocks that every step releases and re-allocates (the 9 GB factor
+// buffer, the bins), and the pool then re-creates those blocks each step (measured: +4 ... +120 ms per step).
+template <typename T>
+struct ScratchBuf {
+  T     *p = nullptr;
+  size_t n = 0;
+  ScratchBuf() = default;
+  ScratchBuf(const ScratchBuf &)            = delete;
+  ScratchBuf &operator=(const ScratchBuf &) = delete;
+  ~ScratchBuf()
+  {
+    if (p)
+      cudaFree(p);
+  }
+  void reserve(size_t count) // contents are not preserved
+  {
+    if (count <= n)
+      return;
+    if (p)
+      RBF_CUDA(cudaFree(p));
+    p = nullptr;
+    n = 0;
+    RBF_CUDA(cudaMalloc(reinterpret_cast<void **>(&p), count * sizeof(T)));
+    n = count;
+  }
+  size_t bytes() const { return n * sizeof(T); }
+};
+
 inline int divUp(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / b); }
 
 // number of SMs of the current device (cached)

@@ -2,6 +2,8 @@
 // kernels (pum_cluster.cu), the per-cluster algebra kernels (pum_solve.cu) and the host driver (pum.cu).
 #pragma once
 
+#include <vector>
+
 #include "basis.cuh"
 #include "common.cuh"
 #include "spatial.cuh"
@@ -44,7 +46,7 @@ struct PumMembership {
 // mapping object and survives clear(): re-allocating ~1 GB between the release and the re-allocation of the 9 GB factor
 // buffer makes the stream-ordered pool split and re-create its large blocks every step (measured: +30 ms at 10M).
 struct PumScratch {
-  DevBuf<int> slotIn, slotOut;
+  ScratchBuf<int> slotIn, slotOut;
   size_t      bytes() const { return slotIn.bytes() + slotOut.bytes(); }
 };
 

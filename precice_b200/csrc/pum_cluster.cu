@@ -478,11 +478,12 @@ void pumBuildMembership(const double *dCenters, int64_t nClusters, const BinGrid
   m.matOff.alloc(nClusters + 1);
   m.nIn.alloc(nClusters);
   m.nOut.alloc(nClusters);
-  DevBuf<int> &slotIn = scratch.slotIn, &slotOut = scratch.slotOut;
-  const size_t slots  = static_cast<size_t>(std::max<int64_t>(nClusters, 1)) * kSlotCap;
+  ScratchBuf<int> &slotIn = scratch.slotIn, &slotOut = scratch.slotOut;
+  const size_t     slots  = static_cast<size_t>(std::max<int64_t>(nClusters, 1)) * kSlotCap;
   if (slotIn.n < slots) { // grow only
-    slotIn.alloc(slots + slots / 8);
-    slotOut.alloc(slots + slots / 8);
+    RBF_CUDA(cudaStreamSynchronize(s));
+    slotIn.reserve(slots + slots / 8);
+    slotOut.reserve(slots + slots / 8);
   }
   DevBuf<int> overflow;
   overflow.alloc(1);
