@@ -268,10 +268,10 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
     RBF_CUDA(cudaMemcpyAsync(_centers.p, c, sizeof(c), cudaMemcpyHostToDevice, _stream));
     RBF_CUDA(cudaStreamSynchronize(_stream));
     _nClusters = 1;
-    inGrid.build(_inXyz.p, _nIn, bbMin, bbMax, _radius, _stream);
+    inGrid.build(_inXyz.p, _nIn, bbMin, bbMax, 0.5 * _radius, _stream); // half-radius cells, 5x5x5 neighbourhoods (forCandidatesWarp<2>)
     waitForOutMesh();
     computeBounds(_outXyz.p, _nOut, obMin, obMax, _stream);
-    outGrid.build(_outXyz.p, _nOut, obMin, obMax, _radius, _stream);
+    outGrid.build(_outXyz.p, _nOut, obMin, obMax, 0.5 * _radius, _stream);
   } else {
     _radius = estimateClusterRadius(bbMin, bbMax);
     trace.phase("estimateClusterRadius");
@@ -329,10 +329,10 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
     RBF_LAUNCHED();
 
     trace.phase("lattice");
-    inGrid.build(_inXyz.p, _nIn, bbMin, bbMax, _radius, _stream);
+    inGrid.build(_inXyz.p, _nIn, bbMin, bbMax, 0.5 * _radius, _stream); // half-radius cells, 5x5x5 neighbourhoods (forCandidatesWarp<2>)
     waitForOutMesh();
     computeBounds(_outXyz.p, _nOut, obMin, obMax, _stream);
-    outGrid.build(_outXyz.p, _nOut, obMin, obMax, _radius, _stream);
+    outGrid.build(_outXyz.p, _nOut, obMin, obMax, 0.5 * _radius, _stream);
     trace.phase("bin meshes");
 
     // :468-471

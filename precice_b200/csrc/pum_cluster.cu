@@ -28,7 +28,7 @@ __global__ void tagEmptyKernel(const double *__restrict__ centers, int *__restri
     return;
   const double cx = centers[3 * c], cy = centers[3 * c + 1], cz = centers[3 * c + 2];
   bool         found = false;
-  forCandidatesWarp(g, cx, cy, cz, lane, [&](int pos, bool valid) {
+  forCandidatesWarp<2>(g, cx, cy, cz, lane, [&](int pos, bool valid) {
     bool hit = false;
     if (valid)
       hit = __dsqrt_rn(sqDist3(cx, cy, cz, g.xyz[3 * pos], g.xyz[3 * pos + 1], g.xyz[3 * pos + 2])) < radius;
@@ -52,7 +52,7 @@ __global__ void projectKernel(double *__restrict__ centers, const int *__restric
   const double cx = centers[3 * c], cy = centers[3 * c + 1], cz = centers[3 * c + 2];
   double       best = 1.7976931348623157e308;
   int          bestId = 0x7fffffff, bestPos = -1;
-  forCandidatesWarp(g, cx, cy, cz, lane, [&](int pos, bool valid) {
+  forCandidatesWarp<2>(g, cx, cy, cz, lane, [&](int pos, bool valid) {
     if (valid) {
       const double d2 = sqDist3(cx, cy, cz, g.xyz[3 * pos], g.xyz[3 * pos + 1], g.xyz[3 * pos + 2]);
       const int    id = g.ids[pos];
@@ -212,7 +212,7 @@ constexpr int kSortCap = 1024; // ints staged per warp
 __device__ void gatherMembers(const BinGridView &g, double cx, double cy, double cz, double r, int *seg, int lane)
 {
   int base = 0;
-  forCandidatesWarp(g, cx, cy, cz, lane, [&](int pos, bool valid) {
+  forCandidatesWarp<2>(g, cx, cy, cz, lane, [&](int pos, bool valid) {
     const bool     hit = valid && __dsqrt_rn(sqDist3(cx, cy, cz, g.xyz[3 * pos], g.xyz[3 * pos + 1], g.xyz[3 * pos + 2])) < r;
     const unsigned m   = __ballot_sync(0xffffffffu, hit);
     if (hit)
@@ -237,7 +237,7 @@ __device__ __forceinline__ int gatherToShared(const BinGridView &g, double cx, d
                                               double rinv = 0.0, double *__restrict__ wsum = nullptr, int *__restrict__ wcount = nullptr)
 {
   int base = 0;
-  forCandidatesWarp(g, cx, cy, cz, lane, [&](int pos, bool valid) {
+  forCandidatesWarp<2>(g, cx, cy, cz, lane, [&](int pos, bool valid) {
     double d = 1.7976931348623157e308;
     if (valid) // computeWeight (SphericalVertexCluster.hpp:337-344): squared difference (centre, vertex)
       d = __dsqrt_rn(sqDist3(cx, cy, cz, g.xyz[3 * pos], g.xyz[3 * pos + 1], g.xyz[3 * pos + 2]));
