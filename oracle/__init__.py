@@ -58,6 +58,7 @@ def lib():
             _lib = C.CDLL(_LIB_PATH)
         _lib.orc_last_error.restype = C.c_char_p
         _lib.orc_pum_create.restype = C.c_void_p
+        _lib.orc_pum_cache_create.restype = C.c_void_p
         _lib.orc_global_create.restype = C.c_void_p
         _lib.orc_pum_radius.restype = C.c_double
         for name in ("orc_pum_compute", "orc_pum_map", "orc_pum_clear", "orc_pum_destroy", "orc_pum_radius",
@@ -150,6 +151,44 @@ class PumMapping:
         out = np.zeros(self._n_out * dims)
         _check(self._l.orc_pum_map(self._h, _dp(v), C.c_int(dims), _dp(out), C.c_int(threads)))
         return out
+
+    # ---- just-in-time mapping (PartitionOfUnityMapping.hpp:382-476) ----
+    def compute_mapping_jit(self, mesh_xyz, threads=1):
+        """The other mesh is a just-in-time mesh; mesh_xyz is the mesh that exists (input for consistent, output for conservative)."""
+        a = as_xyz(mesh_xyz)
+        self._n_in, self._n_out = (a.shape[0], 0) if self.constraint != "conservative" else (0, a.shape[0])
+        self._n_mesh = a.shape[0]
+        _check(self._l.orc_pum_compute_jit(self._h, _dp(a), C.c_int(a.shape[0]), C.c_int(threads)))
+
+    def initialize_cache(self, dims):
+        c = self._l.orc_pum_cache_create(self._h, C.c_int(dims))
+        if not c:
+            raise OracleError(self._l.orc_last_error().decode())
+        return {"h": C.c_void_p(c), "dims": dims}
+
+    def reset_cache(self, cache):
+        _check(self._l.orc_pum_cache_reset(self._h, cache["h"]))
+
+    def update_cache(self, cache, values):
+        v = np.ascontiguousarray(np.asarray(values, dtype=np.float64).reshape(-1))
+        assert v.size == self._n_mesh * cache["dims"]
+        _check(self._l.orc_pum_cache_update(self._h, cache["h"], _dp(v)))
+
+    def map_consistent_at(self, coords, cache) -> np.ndarray:
+        x = as_xyz(coords)
+        out = np.zeros(x.shape[0] * cache["dims"])
+        _check(self._l.orc_pum_map_consistent_at(self._h, cache["h"], _dp(x), C.c_int(x.shape[0]), _dp(out)))
+        return out
+
+    def map_conservative_at(self, coords, source, cache):
+        x = as_xyz(coords)
+        v = np.ascontiguousarray(np.asarray(source, dtype=np.float64).reshape(-1))
+        assert v.size == x.shape[0] * cache["dims"]
+        _check(self._l.orc_pum_map_conservative_at(self._h, cache["h"], _dp(x), C.c_int(x.shape[0]), _dp(v)))
+
+    def complete_just_in_time_mapping(self, cache, out):
+        assert out.dtype == np.float64 and out.size == self._n_mesh * cache["dims"]
+        _check(self._l.orc_pum_complete_jit(self._h, cache["h"], _dp(out)))
 
     def clear(self):
         self._l.orc_pum_clear(self._h)

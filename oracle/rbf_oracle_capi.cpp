@@ -86,6 +86,44 @@ int orc_pum_map(void *h, const double *in, int dims, double *out, int threads)
 {
   return guarded([&] { static_cast<orc::PumMapping *>(h)->map(in, dims, out, threads); });
 }
+// ---- just-in-time mapping (PartitionOfUnityMapping.hpp:382-476) ----
+int orc_pum_compute_jit(void *h, const double *meshXYZ, int n, int threads)
+{
+  return guarded([&] { static_cast<orc::PumMapping *>(h)->computeMappingJustInTime(meshXYZ, n, threads); });
+}
+void *orc_pum_cache_create(void *h, int dims)
+{
+  orc::PumMapping::Cache *c = nullptr;
+  guarded([&] {
+    c = new orc::PumMapping::Cache();
+    static_cast<orc::PumMapping *>(h)->initializeCache(*c, dims);
+  });
+  return c;
+}
+void orc_pum_cache_destroy(void *c) { delete static_cast<orc::PumMapping::Cache *>(c); }
+int  orc_pum_cache_reset(void *h, void *c)
+{
+  return guarded([&] {
+    auto *cache = static_cast<orc::PumMapping::Cache *>(c);
+    static_cast<orc::PumMapping *>(h)->initializeCache(*cache, cache->dims);
+  });
+}
+int orc_pum_cache_update(void *h, void *c, const double *in)
+{
+  return guarded([&] { static_cast<orc::PumMapping *>(h)->updateCache(*static_cast<orc::PumMapping::Cache *>(c), in); });
+}
+int orc_pum_map_consistent_at(void *h, void *c, const double *coords, int nPts, double *out)
+{
+  return guarded([&] { static_cast<orc::PumMapping *>(h)->mapConsistentAt(coords, nPts, *static_cast<orc::PumMapping::Cache *>(c), out); });
+}
+int orc_pum_map_conservative_at(void *h, void *c, const double *coords, int nPts, const double *source)
+{
+  return guarded([&] { static_cast<orc::PumMapping *>(h)->mapConservativeAt(coords, nPts, source, *static_cast<orc::PumMapping::Cache *>(c)); });
+}
+int orc_pum_complete_jit(void *h, void *c, double *out)
+{
+  return guarded([&] { static_cast<orc::PumMapping *>(h)->completeJustInTimeMapping(*static_cast<orc::PumMapping::Cache *>(c), out); });
+}
 void   orc_pum_clear(void *h) { static_cast<orc::PumMapping *>(h)->clear(); }
 void   orc_pum_destroy(void *h) { delete static_cast<orc::PumMapping *>(h); }
 double orc_pum_radius(void *h) { return static_cast<orc::PumMapping *>(h)->clusterRadius(); }

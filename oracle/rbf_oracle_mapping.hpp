@@ -3,6 +3,7 @@
 // See rbf_oracle.hpp for the scope statement. All file:line citations are relative to
 // /root/reference/src/.
 #pragma once
+#include <memory>
 
 #include "rbf_oracle.hpp"
 
@@ -394,6 +395,83 @@ public:
     return out;
   }
 
+  // ---- just-in-time mapping (RadialBasisFctSolver.hpp:470-573) ----
+  // computeCacheData :470-482
+  void computeCacheData(Mat &in, Polynomial polynomial, Mat &polyOut, Mat &coeffsOut) const
+  {
+    if (polynomial == Polynomial::SEPARATE) {
+      polyOut     = _qrQ.solve(in);
+      const Mat P = matmul(_Q, polyOut);
+      for (size_t i = 0; i < in.a.size(); ++i)
+        in.a[i] -= P.a[i];
+    }
+    coeffsOut = solveC(in);
+  }
+
+  // interpolateAt :484-520 (all three axes in the distance, "we ignore the dead axis here")
+  void interpolateAt(const double *v, const Mat &poly, const Mat &coeffs, const Rbf &f, const double *inXYZ, const std::vector<int> &inIDs, double *result) const
+  {
+    const int dims = coeffs.c;
+    for (int d = 0; d < dims; ++d)
+      result[d] = 0.0;
+    for (size_t j = 0; j < inIDs.size(); ++j) {
+      const double eval = f(std::sqrt(squaredDifference(v, inXYZ + 3 * static_cast<size_t>(inIDs[j]))));
+      for (int d = 0; d < dims; ++d)
+        result[d] += eval * coeffs(static_cast<int>(j), d);
+    }
+    if (!poly.a.empty()) {
+      for (int d = 0; d < dims; ++d)
+        result[d] += 1 * poly(0, d);
+      int k = 1;
+      for (int ax = 0; ax < 3; ++ax)
+        if (_localActive[ax]) {
+          for (int d = 0; d < dims; ++d)
+            result[d] += v[ax] * poly(k, d);
+          ++k;
+        }
+    }
+  }
+
+  // addWriteDataToCache :522-560
+  void addWriteDataToCache(const double *v, const double *load, Mat &epsilon, Mat &Au, const Rbf &f, const double *inXYZ, const std::vector<int> &inIDs) const
+  {
+    const int dims = Au.c;
+    for (size_t j = 0; j < inIDs.size(); ++j) {
+      const double eval = f(std::sqrt(squaredDifference(v, inXYZ + 3 * static_cast<size_t>(inIDs[j]))));
+      for (int d = 0; d < dims; ++d)
+        Au(static_cast<int>(j), d) += eval * load[d];
+    }
+    if (!epsilon.a.empty()) {
+      for (int d = 0; d < dims; ++d)
+        epsilon(0, d) += 1 * load[d];
+      int k = 1;
+      for (int ax = 0; ax < 3; ++ax)
+        if (_localActive[ax]) {
+          for (int d = 0; d < dims; ++d)
+            epsilon(k, d) += v[ax] * load[d];
+          ++k;
+        }
+    }
+  }
+
+  // evaluateConservativeCache :562-573
+  Mat evaluateConservativeCache(Mat &epsilon, const Mat &Au) const
+  {
+    Mat out = solveC(Au);
+    if (!epsilon.a.empty()) {
+      const Mat Qm = matmulT(_Q, out);
+      for (size_t i = 0; i < epsilon.a.size(); ++i)
+        epsilon.a[i] -= Qm.a[i];
+      Mat neg = epsilon;
+      for (auto &e : neg.a)
+        e = -e;
+      const Mat sigma = _qrQ.solveTransposed(neg);
+      for (size_t i = 0; i < out.a.size(); ++i)
+        out.a[i] -= sigma.a[i];
+    }
+    return out;
+  }
+
   const Mat &matrixA() const { return _A; }
   const Mat &choleskyL() const { return _llt.L; }
 
@@ -653,6 +731,130 @@ public:
 
   // computeMapping :181-223 + _computeCPU :225-288. `input`/`output` are the meshes in the
   // Mapping::input()/output() sense; the swap for conservative constraints happens here (:190-198).
+  // The other mesh is a just-in-time mesh (mesh::MeshConfiguration::getJustInTimeMappingMesh): consistent -> the data
+  // is read at arbitrary points later (mapConsistentAt), conservative -> loads are written at arbitrary points
+  // (mapConservativeAt + completeJustInTimeMapping). `meshXYZ` is the real mesh (= solver-side inMesh in both cases).
+  void computeMappingJustInTime(const double *meshXYZ, int n, int threads = 1)
+  {
+    _jit = true;
+    if (_constraint == Constraint::CONSERVATIVE)
+      computeMapping(nullptr, 0, meshXYZ, n, threads);
+    else
+      computeMapping(meshXYZ, n, nullptr, 0, threads);
+  }
+
+  struct Cache { // impl/MappingDataCache.hpp:23-71
+    int              dims = 0;
+    std::vector<Mat> poly, p;
+  };
+
+  // initializeMappingDataCache :424-434 (+ MappingDataCache::resetData)
+  void initializeCache(Cache &cache, int dims) const
+  {
+    cache.dims = dims;
+    cache.poly.assign(_clusters.size(), Mat());
+    cache.p.assign(_clusters.size(), Mat());
+    for (size_t c = 0; c < _clusters.size(); ++c) {
+      if (_poly == Polynomial::SEPARATE)
+        cache.poly[c] = Mat(_clusters[c].solver.numberOfPolynomials(), dims);
+      cache.p[c] = Mat(static_cast<int>(_clusters[c].inIDs.size()), dims);
+    }
+  }
+
+  // updateMappingDataCache :436-448 -> SphericalVertexCluster::computeCacheData :255-270
+  void updateCache(Cache &cache, const double *in) const
+  {
+    const int dims = cache.dims;
+    for (size_t c = 0; c < _clusters.size(); ++c) {
+      const Cluster &k = _clusters[c];
+      Mat            f(k.solver.inputSize(), dims);
+      for (size_t i = 0; i < k.inIDs.size(); ++i)
+        for (int d = 0; d < dims; ++d)
+          f(static_cast<int>(i), d) = in[static_cast<size_t>(k.inIDs[i]) * dims + d];
+      k.solver.computeCacheData(f, _poly, cache.poly[c], cache.p[c]);
+    }
+  }
+
+  // computeNormalizedWeight :290-341 for an arbitrary point
+  void normalizedWeights(const double *x, std::vector<int> &ids, std::vector<double> &w) const
+  {
+    ids = _centerGrid->verticesInsideSphere(x, _radius);
+    if (ids.empty())
+      throw Error("Output vertex could not be assigned to any cluster in the rbf-pum mapping. This probably means that the meshes do not match well geometry-wise: Visualize the exported preCICE meshes to confirm. "
+                  "If the meshes are fine geometry-wise, you can try to increase the number of \"vertices-per-cluster\" (default is 50), the \"relative-overlap\" (default is 0.15), or disable the option \"project-to-input\". "
+                  "These options are only valid for the <mapping:rbf-pum-direct/> tag.");
+    const Rbf weighting = Rbf::make(BasisFunction::WendlandC2, _radius);
+    w.assign(ids.size(), 0.0);
+    double sum = 0.0;
+    for (size_t i = 0; i < ids.size(); ++i) {
+      w[i] = weighting(std::sqrt(squaredDifference(_clusters[ids[i]].center.data(), x)));
+      sum += w[i];
+    }
+    if (sum <= 0) {
+      for (auto &e : w)
+        e = 1. / w.size();
+      sum = 1;
+    }
+    for (auto &e : w)
+      e /= sum;
+  }
+
+  // mapConsistentAt :450-476; coords: nPts x 3, out: nPts x dims (vertex-major)
+  void mapConsistentAt(const double *coords, int nPts, const Cache &cache, double *out) const
+  {
+    const int           dims = cache.dims;
+    std::vector<double> res(dims);
+    std::vector<int>    ids;
+    std::vector<double> w;
+    for (int v = 0; v < nPts; ++v) {
+      for (int d = 0; d < dims; ++d)
+        out[static_cast<size_t>(v) * dims + d] = 0.0;
+      normalizedWeights(coords + 3 * v, ids, w);
+      for (size_t i = 0; i < ids.size(); ++i) {
+        const Cluster &k = _clusters[ids[i]];
+        k.solver.interpolateAt(coords + 3 * v, cache.poly[ids[i]], cache.p[ids[i]], _f, _inXYZ.data(), k.inIDs, res.data());
+        for (int d = 0; d < dims; ++d)
+          out[static_cast<size_t>(v) * dims + d] += w[i] * res[d];
+      }
+    }
+  }
+
+  // mapConservativeAt :382-409; source: nPts x dims
+  void mapConservativeAt(const double *coords, int nPts, const double *source, Cache &cache) const
+  {
+    const int           dims = cache.dims;
+    std::vector<double> load(dims);
+    std::vector<int>    ids;
+    std::vector<double> w;
+    for (int v = 0; v < nPts; ++v) {
+      normalizedWeights(coords + 3 * v, ids, w);
+      for (size_t i = 0; i < ids.size(); ++i) {
+        const Cluster &k = _clusters[ids[i]];
+        for (int d = 0; d < dims; ++d)
+          load[d] = w[i] * source[static_cast<size_t>(v) * dims + d];
+        k.solver.addWriteDataToCache(coords + 3 * v, load.data(), cache.poly[ids[i]], cache.p[ids[i]], _f, _inXYZ.data(), k.inIDs);
+      }
+    }
+  }
+
+  // completeJustInTimeMapping :411-422 -> SphericalVertexCluster::evaluateConservativeCache :242-253; out accumulates
+  void completeJustInTimeMapping(Cache &cache, double *out) const
+  {
+    const int dims = cache.dims;
+    for (size_t c = 0; c < _clusters.size(); ++c) {
+      double sq = 0.0;
+      for (double e : cache.p[c].a)
+        sq += e * e;
+      if (!(sq > 0))
+        continue;
+      const Cluster &k = _clusters[c];
+      const Mat      r = k.solver.evaluateConservativeCache(cache.poly[c], cache.p[c]);
+      for (size_t i = 0; i < k.inIDs.size(); ++i)
+        for (int d = 0; d < dims; ++d)
+          out[static_cast<size_t>(k.inIDs[i]) * dims + d] += r(static_cast<int>(i), d);
+    }
+  }
+
   void computeMapping(const double *inputXYZ, int nInput, const double *outputXYZ, int nOutput, int threads = 1)
   {
     if (_computed)
@@ -664,7 +866,7 @@ public:
     _nOut = cons ? nInput : nOutput;
     PointGrid inGrid(_inXYZ.data(), _nIn), outGrid(_outXYZ.data(), _nOut);
 
-    const Clustering cl = createClustering(inGrid, outGrid, _dim, _overlap, _vpc, _project);
+    const Clustering cl = createClustering(inGrid, outGrid, _dim, _overlap, _vpc, _project, _jit);
     _radius             = cl.radius;
     const int nc        = cl.count();
 
@@ -694,7 +896,9 @@ public:
     for (size_t c = 0; c < _clusters.size(); ++c)
       for (int d = 0; d < 3; ++d)
         centerXYZ[3 * c + d] = _clusters[c].center[d];
-    PointGrid centerGrid(centerXYZ.data(), static_cast<int>(_clusters.size()));
+    _centerXYZ = centerXYZ;
+    _centerGrid.reset(new PointGrid(_centerXYZ.data(), static_cast<int>(_clusters.size()))); // kept for just-in-time queries (:285-287)
+    PointGrid &centerGrid = *_centerGrid;
     const Rbf weighting = Rbf::make(BasisFunction::WendlandC2, _radius); // SphericalVertexCluster.hpp:146
     parallelFor(_nOut, threads, [&](size_t v, int) {
       const double    *x   = &_outXYZ[3 * v];
@@ -782,8 +986,10 @@ public:
   void clear() // :593-600
   {
     _clusters.clear();
+    _centerGrid.reset();
     _radius   = 0;
     _computed = false;
+    _jit      = false;
   }
 
   bool                        hasComputedMapping() const { return _computed; }
@@ -805,6 +1011,9 @@ private:
   int                  _nIn = 0, _nOut = 0;
   std::vector<double>  _inXYZ, _outXYZ;
   std::vector<Cluster> _clusters;
+  bool                 _jit = false;
+  std::vector<double>  _centerXYZ;
+  std::unique_ptr<PointGrid> _centerGrid;
 };
 
 // ---------------------------------------------------------------------------------------------

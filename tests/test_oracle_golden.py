@@ -53,3 +53,87 @@ DEAD = refcases.dead_axis_cases()
 @pytest.mark.parametrize("case", DEAD, ids=[c["name"] for c in DEAD])
 def test_global_dead_axis_goldens(case):
     refcases.run_global_case(case, lambda **kw: oracle.GlobalMapping(**kw))
+
+
+# ---------------------------------------------------------------------------------------------- just-in-time mapping
+def _jit_boxes():
+    def box(x0):
+        return [(x0, 0, 0), (x0 + 1, 0, 0), (x0 + 1, 1, 0), (x0, 1, 0), (x0, 0, 1), (x0 + 1, 0, 1), (x0 + 1, 1, 1), (x0, 1, 1)]
+    return np.array(box(0) + box(2) + box(4), float)
+
+
+JIT_VALUES_24 = np.array([1, 2, 2, 1, 3, 6, 6, 3, 3, 4, 4, 3, 9, 12, 12, 9, 5, 6, 6, 5, 15, 18, 18, 15], float)
+
+
+def test_jit_consistent_3d_with_polynomial():
+    """PartitionOfUnityMappingTest.cpp:772-937 (perform3DTestJustInTimeMappingWithPolynomial, instantiated :1908-1909)."""
+    m = oracle.PumMapping("consistent", 3, "compact-polynomial-c0", 3.0, "separate", 5, 0.265, False)
+    m.compute_mapping_jit(_jit_boxes())
+    c = m.initialize_cache(1)
+    m.update_cache(c, JIT_VALUES_24)
+    at = lambda pts: m.map_consistent_at(np.array(pts, float), c)
+    assert at([(0, 0, 0)])[0] == pytest.approx(1.0, rel=1e-12)
+    assert at([(3.5, 0.5, 0.5)])[0] == pytest.approx(9.0, rel=1e-12)
+    assert at([(2.5, 0.5, 1.0)])[0] == pytest.approx(10.5, rel=1e-12)
+    assert at([(0, 0.5, 0.5), (0, 1, 1), (1, 0, 0)]) == pytest.approx([2.0, 3.0, 2.0], rel=1e-12)
+    m.update_cache(c, 2 * JIT_VALUES_24)
+    assert at([(0, 0.5, 0.5), (0, 1, 1), (1, 0, 0)]) == pytest.approx([4.0, 6.0, 4.0], rel=1e-12)
+    assert at([(0.5, 0, 0.5), (0.5, 0.5, 1.0), (0.5, 1.0, 0.0)]) == pytest.approx([6.0, 9.0, 3.0], rel=1e-12)
+    # :904-936 the mesh is extended by one more face, the mapping recomputed
+    m.clear()
+    mesh = np.vstack([_jit_boxes(), [(6, 0, 0), (7, 0, 0), (7, 1, 0), (6, 1, 0)]])
+    m.compute_mapping_jit(mesh)
+    c = m.initialize_cache(1)
+    m.update_cache(c, np.concatenate([JIT_VALUES_24, [7.0, 8.0, 8.0, 7.0]]))
+    assert at([(6.5, 1.0, 0.0), (0.5, 0.5, 1.0), (0.5, 1.0, 0.0)]) == pytest.approx([7.5, 4.5, 1.5], rel=1e-12)
+
+
+def test_jit_consistent_2d_no_polynomial():
+    """PartitionOfUnityMappingTest.cpp:939-1098 (perform2DTestJustInTimeMappingNoPolynomial, :1911-1913): goldens at 1e-7."""
+    mesh = np.array([(0, 0), (1, 0), (1, 1), (0, 1), (2, 0), (3, 0), (3, 1), (2, 1), (4, 0), (5, 0), (5, 1), (4, 1)], float)
+    m = oracle.PumMapping("consistent", 2, "compact-polynomial-c4", 3.0, "off", 5, 0.265, False)
+    m.compute_mapping_jit(mesh)
+    c = m.initialize_cache(2)
+    m.update_cache(c, JIT_VALUES_24)
+    at = lambda pts: m.map_consistent_at(np.array(pts, float), c)
+    assert at([(0, 0)]) == pytest.approx([1.0, 2.0], rel=1e-12)
+    assert at([(5, 1)]) == pytest.approx([15.0, 18.0], rel=1e-12)
+    assert at([(0.5, 0.0)]) == pytest.approx([1.71978075, 1.71978075], rel=1e-7)
+    assert at([(3.5, 0.5)]) == pytest.approx([10.39684625, 10.48101386], rel=1e-7)
+    assert at([(4, 0), (5, 0)]) == pytest.approx([5.0, 6.0, 6.0, 5.0], rel=1e-12)
+    m.update_cache(c, 0.5 * JIT_VALUES_24)
+    assert at([(4, 0), (5, 0)]) == pytest.approx([2.5, 3.0, 3.0, 2.5], rel=1e-12)
+
+
+def test_jit_conservative_3d():
+    """PartitionOfUnityMappingTest.cpp:1311-1495 (perform3DTestJustInTimeMappingConservative, :1915-1918)."""
+    m = oracle.PumMapping("conservative", 3, "compact-polynomial-c2", 3.0, "separate", 5, 0.265, False)
+    m.compute_mapping_jit(_jit_boxes())
+    c = m.initialize_cache(1)
+    out = np.zeros(24)
+    m.map_conservative_at([(5.0, 0.0, 1.0)], [4.3], c)
+    m.complete_just_in_time_mapping(c, out)
+    expected = np.zeros(24)
+    expected[21] = 4.3
+    assert out.sum() == pytest.approx(4.3, rel=1e-12)
+    assert out == pytest.approx(expected, abs=1e-12)
+    m.reset_cache(c)
+    out[:] = 0
+    m.map_conservative_at([(5.0, 0.0, 1.0)], [4.3], c)
+    m.map_conservative_at([(3.5, 0.5, 0.5), (4.5, 1.0, 1.0), (0.1, 0.0, 1.0)], [4.3, 17.3, 5.8], c)
+    m.complete_just_in_time_mapping(c, out)
+    assert out.sum() == pytest.approx(4.3 + 4.3 + 17.3 + 5.8, rel=1e-12)
+    assert out[6] == pytest.approx(0.063700286667, rel=1e-7)
+    assert out[23] == pytest.approx(9.2744883594, rel=1e-7)
+    # :1461-1494 one more vertex, mapping recomputed
+    m.clear()
+    mesh = np.vstack([_jit_boxes(), [(6, 0, 0)]])
+    m.compute_mapping_jit(mesh)
+    c = m.initialize_cache(1)
+    out = np.zeros(25)
+    m.map_conservative_at([(0.5, 0.5, 0.5)], [4.3], c)
+    m.map_conservative_at([(6.0, 0.0, 0.0)], [42.0], c)
+    m.complete_just_in_time_mapping(c, out)
+    assert out.sum() == pytest.approx(46.3, rel=1e-12)
+    assert out[24] == pytest.approx(42.0, rel=1e-12)
+    assert out[0] == pytest.approx(0.505106848, rel=1e-7)
