@@ -103,6 +103,42 @@ int rbfmap_create(const rbfmap_config *cfg, rbfmap_handle **out);
  * (what Mapping::setMeshes + mesh.vertex(i).rawCoords() provide). Host pointers. */
 int rbfmap_compute_mapping(rbfmap_handle *h, const double *input_xyz, int64_t n_input, const double *output_xyz, int64_t n_output);
 
+/* ---- just-in-time mapping (rbf-pum-direct only, other variants return
+ * RBFMAP_ERR_UNSUPPORTED). The reference forbids it on its own GPU path (PartitionOfUnityMapping.hpp:211). ----
+ *
+ * Mapping::computeMapping() when the other mesh is a just-in-time mesh
+ * (mesh::MeshConfiguration::getJustInTimeMappingMesh; CreateClustering.hpp:313, 469, 492): `mesh_xyz` is the mesh that
+ * exists - Mapping::input() for a consistent (read) mapping, Mapping::output() for a conservative (write) mapping.
+ * Host pointer. */
+int rbfmap_compute_mapping_just_in_time(rbfmap_handle *h, const double *mesh_xyz, int64_t n);
+
+/* impl::MappingDataCache (mapping/impl/MappingDataCache.hpp:23-71) on the device, one per data. */
+typedef struct rbfmap_cache rbfmap_cache;
+
+/* Mapping::initializeMappingDataCache (Mapping.hpp, PartitionOfUnityMapping.hpp:424-434): sized for the current
+ * mapping and zeroed; create it after rbfmap_compute_mapping_just_in_time and again after every re-computation. */
+int rbfmap_cache_create(rbfmap_handle *h, int dims, rbfmap_cache **out);
+/* MappingDataCache::resetData (:60-70). */
+int  rbfmap_cache_reset(rbfmap_handle *h, rbfmap_cache *cache);
+void rbfmap_cache_destroy(rbfmap_cache *cache);
+
+/* Mapping::updateMappingDataCache (PartitionOfUnityMapping.hpp:436-448): `values` = n*dims doubles on the mesh,
+ * vertex-major. Consistent mappings only. */
+int rbfmap_cache_update(rbfmap_handle *h, rbfmap_cache *cache, const double *values);
+
+/* Mapping::mapConsistentAt (PartitionOfUnityMapping.hpp:450-476): evaluates the cached interpolant at `n_points`
+ * arbitrary points (n_points x 3, z = 0 in 2-D); `out` = n_points*dims doubles, overwritten. A point outside every
+ * cluster raises RBFMAP_ERR_UNASSIGNED with the reference's message (:314-318). */
+int rbfmap_map_consistent_at(rbfmap_handle *h, rbfmap_cache *cache, const double *coords, int64_t n_points, double *out);
+
+/* Mapping::mapConservativeAt (PartitionOfUnityMapping.hpp:382-409): adds the loads `values` (n_points*dims) given at
+ * arbitrary points to the cache. Conservative mappings only. */
+int rbfmap_map_conservative_at(rbfmap_handle *h, rbfmap_cache *cache, const double *coords, int64_t n_points, const double *values);
+
+/* Mapping::completeJustInTimeMapping (PartitionOfUnityMapping.hpp:411-422): solves the cached systems and ADDS the
+ * result to `out` (n*dims doubles on the mesh), like the reference accumulates into its buffer. */
+int rbfmap_complete_just_in_time_mapping(rbfmap_handle *h, rbfmap_cache *cache, double *out);
+
 /* Mapping::map(Sample, VectorXd&) dispatch (mapping/Mapping.cpp:158-173): conservative ->
  * mapConservative, otherwise mapConsistent. `in` has n_input*dims, `out` n_output*dims doubles.
  * `out` is overwritten with the mapped values (the reference accumulates into a pre-zeroed vector,

@@ -32,7 +32,8 @@ EXPORTS = [
     "rbfmap_has_computed_mapping", "rbfmap_destroy", "rbfmap_get_name", "rbfmap_last_error", "rbfmap_get_stats",
     "rbfmap_pum_get_clusters", "rbfmap_pum_get_cluster_ids", "rbfmap_eval_basis", "rbfmap_device_count",
     "rbfmap_device_info", "rbfmap_measure_fp64_peak", "rbfmap_debug_dist_sqrt", "rbfmap_nccl_unique_id", "rbfmap_distributed_init",
-    "rbfmap_partition_rows",
+    "rbfmap_partition_rows", "rbfmap_compute_mapping_just_in_time", "rbfmap_cache_create", "rbfmap_cache_reset", "rbfmap_cache_destroy",
+    "rbfmap_cache_update", "rbfmap_map_consistent_at", "rbfmap_map_conservative_at", "rbfmap_complete_just_in_time_mapping",
 ]
 
 
@@ -103,5 +104,14 @@ def lib():
         L.rbfmap_nccl_unique_id.argtypes = [C.c_char_p]
         L.rbfmap_distributed_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int]
         L.rbfmap_partition_rows.argtypes = [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.rbfmap_compute_mapping_just_in_time.argtypes = [vp, vp, C.c_int64]
+        L.rbfmap_cache_create.argtypes = [vp, C.c_int, C.POINTER(vp)]
+        L.rbfmap_cache_reset.argtypes = [vp, vp]
+        L.rbfmap_cache_destroy.argtypes = [vp]
+        L.rbfmap_cache_destroy.restype = None
+        L.rbfmap_cache_update.argtypes = [vp, vp, vp]
+        L.rbfmap_map_consistent_at.argtypes = [vp, vp, vp, C.c_int64, vp]
+        L.rbfmap_map_conservative_at.argtypes = [vp, vp, vp, C.c_int64, vp]
+        L.rbfmap_complete_just_in_time_mapping.argtypes = [vp, vp, vp]
         _lib = L
     return _lib

@@ -262,6 +262,65 @@ int rbfmap_compute_mapping(rbfmap_handle *h, const double *input_xyz, int64_t n_
   });
 }
 
+struct rbfmap_cache {
+  std::unique_ptr<DeviceMapping::JitCache> impl;
+};
+
+extern "C" {
+int rbfmap_compute_mapping_just_in_time(rbfmap_handle *h, const double *mesh_xyz, int64_t n)
+{
+  if (!h)
+    return RBFMAP_ERR_INVALID;
+  return guarded(h, [&] {
+    if (n < 0 || (n > 0 && !mesh_xyz))
+      throw MapError(RBFMAP_ERR_INVALID, "invalid mesh");
+    h->impl->jitComputeMapping(mesh_xyz, n);
+  });
+}
+int rbfmap_cache_create(rbfmap_handle *h, int dims, rbfmap_cache **out)
+{
+  if (!h || !out)
+    return RBFMAP_ERR_INVALID;
+  *out = nullptr;
+  return guarded(h, [&] {
+    auto c  = std::make_unique<rbfmap_cache>();
+    c->impl = h->impl->jitCreateCache(dims);
+    *out    = c.release();
+  });
+}
+int rbfmap_cache_reset(rbfmap_handle *h, rbfmap_cache *cache)
+{
+  if (!h || !cache)
+    return RBFMAP_ERR_INVALID;
+  return guarded(h, [&] { h->impl->jitResetCache(*cache->impl); });
+}
+void rbfmap_cache_destroy(rbfmap_cache *cache) { delete cache; }
+int  rbfmap_cache_update(rbfmap_handle *h, rbfmap_cache *cache, const double *values)
+{
+  if (!h || !cache)
+    return RBFMAP_ERR_INVALID;
+  return guarded(h, [&] { h->impl->jitUpdateCache(*cache->impl, values); });
+}
+int rbfmap_map_consistent_at(rbfmap_handle *h, rbfmap_cache *cache, const double *coords, int64_t n_points, double *out)
+{
+  if (!h || !cache)
+    return RBFMAP_ERR_INVALID;
+  return guarded(h, [&] { h->impl->jitMapConsistentAt(*cache->impl, coords, n_points, out); });
+}
+int rbfmap_map_conservative_at(rbfmap_handle *h, rbfmap_cache *cache, const double *coords, int64_t n_points, const double *values)
+{
+  if (!h || !cache)
+    return RBFMAP_ERR_INVALID;
+  return guarded(h, [&] { h->impl->jitMapConservativeAt(*cache->impl, coords, n_points, values); });
+}
+int rbfmap_complete_just_in_time_mapping(rbfmap_handle *h, rbfmap_cache *cache, double *out)
+{
+  if (!h || !cache)
+    return RBFMAP_ERR_INVALID;
+  return guarded(h, [&] { h->impl->jitComplete(*cache->impl, out); });
+}
+} // extern "C"
+
 static void mapDeviceImpl(rbfmap_handle *h, int mode /*0 dispatch, 1 consistent, 2 conservative*/, const double *d_in, int dims, double *d_out)
 {
   DeviceMapping *m    = h->impl.get();

@@ -22,6 +22,20 @@ public:
   // caller then stages both meshes on the device and calls computeMapping). rbf-pum-direct overrides it to overlap the
   // upload of the second mesh with the work that only needs the first one.
   virtual bool computeMappingHost(const double * /*hInputXyz*/, int64_t /*nInput*/, const double * /*hOutputXyz*/, int64_t /*nOutput*/) { return false; }
+  // ---- just-in-time mapping (Mapping.hpp: initializeMappingDataCache / updateMappingDataCache / mapConsistentAt /
+  // mapConservativeAt / completeJustInTimeMapping); host pointers; only rbf-pum-direct implements it ----
+  struct JitCache { // impl/MappingDataCache.hpp:23-71 on the device
+    int                dims = 0;
+    ScratchBuf<double> coef, poly;
+  };
+  [[noreturn]] static void noJit() { throw MapError(RBFMAP_ERR_UNSUPPORTED, "just-in-time mapping is implemented for rbf-pum-direct only"); }
+  virtual void                      jitComputeMapping(const double * /*hMeshXyz*/, int64_t /*n*/) { noJit(); }
+  virtual std::unique_ptr<JitCache> jitCreateCache(int /*dims*/) { noJit(); }
+  virtual void                      jitResetCache(JitCache &) { noJit(); }
+  virtual void                      jitUpdateCache(JitCache &, const double * /*hValues*/) { noJit(); }
+  virtual void jitMapConsistentAt(JitCache &, const double * /*hCoords*/, int64_t /*nPts*/, double * /*hOut*/) { noJit(); }
+  virtual void jitMapConservativeAt(JitCache &, const double * /*hCoords*/, int64_t /*nPts*/, const double * /*hSource*/) { noJit(); }
+  virtual void jitComplete(JitCache &, double * /*hOut, accumulated*/) { noJit(); }
   virtual void        mapConsistent(const double *dIn, int dims, double *dOut)                                         = 0;
   virtual void        mapConservative(const double *dIn, int dims, double *dOut)                                       = 0;
   virtual void        clear()                                                                                          = 0;

@@ -61,6 +61,45 @@ public:
     computeImpl(hInputXyz, nInput, hOutputXyz, nOutput, cudaMemcpyHostToDevice);
     return true;
   }
+  // ---- just-in-time mapping ----
+  void jitComputeMapping(const double *hMeshXyz, int64_t n) override
+  {
+    _jit = true;
+    try {
+      if (isConservative())
+        computeImpl(nullptr, 0, hMeshXyz, n, cudaMemcpyHostToDevice);
+      else
+        computeImpl(hMeshXyz, n, nullptr, 0, cudaMemcpyHostToDevice);
+    } catch (...) {
+      _jit = false;
+      throw;
+    }
+  }
+  std::unique_ptr<JitCache> jitCreateCache(int dims) override
+  {
+    requireJit();
+    if (dims < 1)
+      throw MapError(RBFMAP_ERR_INVALID, "data dimension has to be positive");
+    auto c  = std::make_unique<JitCache>();
+    c->dims = dims;
+    c->coef.reserve(static_cast<size_t>(std::max<int64_t>(_mem.sumIn, 1)) * dims);
+    c->poly.reserve(static_cast<size_t>(std::max<int64_t>(_nClusters, 1)) * 4 * dims);
+    jitResetCache(*c);
+    return c;
+  }
+  void jitResetCache(JitCache &c) override
+  {
+    requireJit();
+    checkCache(c);
+    RBF_CUDA(cudaMemsetAsync(c.coef.p, 0, c.coef.bytes(), _stream));
+    RBF_CUDA(cudaMemsetAsync(c.poly.p, 0, c.poly.bytes(), _stream));
+    RBF_CUDA(cudaStreamSynchronize(_stream));
+  }
+  void jitUpdateCache(JitCache &c, const double *hValues) override;
+  void jitMapConsistentAt(JitCache &c, const double *hCoords, int64_t nPts, double *hOut) override;
+  void jitMapConservativeAt(JitCache &c, const double *hCoords, int64_t nPts, const double *hSource) override;
+  void jitComplete(JitCache &c, double *hOut) override;
+
   ~PumMapping() override
   {
     if (_outReady)
@@ -84,7 +123,9 @@ public:
     _wsum.release();
     _wcount.release();
     _buckets.order.release();
-    _nClusters = 0;
+    _centerGrid = BinGrid();
+    _jit        = false;
+    _nClusters  = 0;
     _radius    = 0.0;
     _computed  = false;
     stats      = rbfmap_stats{};
@@ -96,6 +137,17 @@ public:
   const PumMembership  &membership() const { return _mem; }
 
 private:
+  void requireJit() const
+  {
+    if (!_computed || !_jit)
+      throw MapError(RBFMAP_ERR_STATE, "The mapping has not been computed as a just-in-time mapping; call computeMappingJustInTime() first.");
+  }
+  void checkCache(const JitCache &c) const
+  {
+    if (c.coef.n < static_cast<size_t>(std::max<int64_t>(_mem.sumIn, 1)) * c.dims || c.poly.n < static_cast<size_t>(std::max<int64_t>(_nClusters, 1)) * 4 * c.dims)
+      throw MapError(RBFMAP_ERR_STATE, "The data cache does not belong to the current mapping; create it after computeMappingJustInTime().");
+  }
+  void throwUnassigned(const double *dCoords, int64_t bad, bool cons) const;
   void   computeImpl(const double *srcInputXyz, int64_t nInput, const double *srcOutputXyz, int64_t nOutput, cudaMemcpyKind kind);
   void   map(bool conservative, const double *dIn, int dims, double *dOut);
   double estimateClusterRadius(const double bbMin[3], const double bbMax[3]);
@@ -113,6 +165,8 @@ private:
   DevBuf<double>  _wsum;
   DevBuf<int>     _wcount;
   PumBuckets      _buckets;
+  bool            _jit = false; // the other mesh is a just-in-time mesh
+  BinGrid         _centerGrid;  // cluster centres, kept for just-in-time queries (PartitionOfUnityMapping.hpp:285-287)
   // upload of the solver-side outMesh beside the work on the inMesh (computeMappingHost)
   cudaStream_t _copyStream = nullptr;
   cudaEvent_t  _allocReady = nullptr, _outReady = nullptr;
@@ -242,7 +296,8 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
   _radius     = 0.0;
 
   // impl/CreateClustering.hpp:314-316: nothing to do for empty meshes
-  if (_nIn == 0 || _nOut == 0) {
+  const bool jit = _jit; // CreateClustering.hpp:313: a just-in-time outMesh is empty by construction
+  if (_nIn == 0 || (_nOut == 0 && !jit)) {
     _computed = true;
     return;
   }
@@ -270,7 +325,11 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
     _nClusters = 1;
     inGrid.build(_inXyz.p, _nIn, bbMin, bbMax, 0.5 * _radius, _stream); // half-radius cells, 5x5x5 neighbourhoods (forCandidatesWarp<2>)
     waitForOutMesh();
-    computeBounds(_outXyz.p, _nOut, obMin, obMax, _stream);
+    if (_nOut > 0)
+      computeBounds(_outXyz.p, _nOut, obMin, obMax, _stream);
+    else
+      for (int d = 0; d < 3; ++d)
+        obMin[d] = bbMin[d], obMax[d] = bbMax[d];
     outGrid.build(_outXyz.p, _nOut, obMin, obMax, 0.5 * _radius, _stream);
   } else {
     _radius = estimateClusterRadius(bbMin, bbMax);
@@ -331,13 +390,18 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
     trace.phase("lattice");
     inGrid.build(_inXyz.p, _nIn, bbMin, bbMax, 0.5 * _radius, _stream); // half-radius cells, 5x5x5 neighbourhoods (forCandidatesWarp<2>)
     waitForOutMesh();
-    computeBounds(_outXyz.p, _nOut, obMin, obMax, _stream);
+    if (_nOut > 0)
+      computeBounds(_outXyz.p, _nOut, obMin, obMax, _stream);
+    else
+      for (int d = 0; d < 3; ++d)
+        obMin[d] = bbMin[d], obMax[d] = bbMax[d];
     outGrid.build(_outXyz.p, _nOut, obMin, obMax, 0.5 * _radius, _stream);
     trace.phase("bin meshes");
 
     // :468-471
     cl.tagEmpty(inGrid, _stream);
-    cl.tagEmpty(outGrid, _stream);
+    if (!jit) // CreateClustering.hpp:469
+      cl.tagEmpty(outGrid, _stream);
     trace.phase("tagEmpty x2");
     if (_cfg.project_to_input) { // :475-496
       cl.project(inGrid, _stream);
@@ -354,7 +418,8 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
           }
       cl.tagDuplicates(offs, threshold, _stream);
       trace.phase("tagDuplicates");
-      cl.tagEmpty(outGrid, _stream);
+      if (!jit) // CreateClustering.hpp:492
+        cl.tagEmpty(outGrid, _stream);
       trace.phase("tagEmpty");
     }
     _nClusters = cl.compact(_centers, _stream);
@@ -369,8 +434,15 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
   // per-cluster vertex sets (SphericalVertexCluster.hpp:153-162)
   _wsum.alloc(_nOut);
   _wcount.alloc(_nOut);
-  RBF_CUDA(cudaMemsetAsync(_wsum.p, 0, _nOut * sizeof(double), _stream));
-  RBF_CUDA(cudaMemsetAsync(_wcount.p, 0, _nOut * sizeof(int), _stream));
+  if (_nOut > 0) {
+    RBF_CUDA(cudaMemsetAsync(_wsum.p, 0, _nOut * sizeof(double), _stream));
+    RBF_CUDA(cudaMemsetAsync(_wcount.p, 0, _nOut * sizeof(int), _stream));
+  }
+  if (jit) { // the centre index is kept for the point queries of mapConsistentAt / mapConservativeAt (:285-287)
+    double cMin[3], cMax[3];
+    computeBounds(_centers.p, _nClusters, cMin, cMax, _stream);
+    _centerGrid.build(_centers.p, _nClusters, cMin, cMax, 0.5 * _radius, _stream);
+  }
   pumBuildMembership(_centers.p, _nClusters, inGrid, outGrid, _radius, _mem, _scratch, _wsum.p, _wcount.p, _stream);
   trace.phase("membership");
 
@@ -455,6 +527,112 @@ void PumMapping::map(bool conservative, const double *dIn, int dims, double *dOu
   }
   stats.ms_map_kernels = t.stop();
   stats.kernel_launches += g_launches - launchesBefore;
+}
+
+// ---- just-in-time mapping (host pointers) ----
+void PumMapping::throwUnassigned(const double *dCoords, int64_t bad, bool cons) const
+{
+  double v[3];
+  RBF_CUDA(cudaMemcpy(v, dCoords + 3 * bad, sizeof(v), cudaMemcpyDeviceToHost));
+  std::ostringstream os;
+  os.precision(17);
+  os << "Output vertex " << v[0] << " " << v[1];
+  if (_cfg.dimensions == 3)
+    os << " " << v[2];
+  os << " of mesh \"" << (cons ? "input" : "output")
+     << "\" could not be assigned to any cluster in the rbf-pum mapping. This probably means that the meshes do not match well geometry-wise: "
+        "Visualize the exported preCICE meshes to confirm. If the meshes are fine geometry-wise, you can try to increase the number of "
+        "\"vertices-per-cluster\" (default is 50), the \"relative-overlap\" (default is 0.15), or disable the option \"project-to-input\". "
+        "These options are only valid for the <mapping:rbf-pum-direct/> tag.";
+  throw MapError(RBFMAP_ERR_UNASSIGNED, os.str());
+}
+
+void PumMapping::jitUpdateCache(JitCache &c, const double *hValues)
+{
+  requireJit();
+  checkCache(c);
+  if (isConservative())
+    throw MapError(RBFMAP_ERR_STATE, "updateMappingDataCache belongs to consistent (read) just-in-time mappings.");
+  AllocStreamScope allocScope(_stream);
+  DevBuf<double>   dIn;
+  dIn.alloc(static_cast<size_t>(std::max<int64_t>(_nIn, 1)) * c.dims);
+  if (_nIn > 0)
+    RBF_CUDA(cudaMemcpyAsync(dIn.p, hValues, static_cast<size_t>(_nIn) * c.dims * sizeof(double), cudaMemcpyHostToDevice, _stream));
+  if (_nClusters > 0)
+    pumJitUpdateCache(solveArgs(), _buckets, dIn.p, c.dims, c.coef.p, c.poly.p, _stream);
+  RBF_CUDA(cudaStreamSynchronize(_stream));
+}
+
+void PumMapping::jitMapConsistentAt(JitCache &c, const double *hCoords, int64_t nPts, double *hOut)
+{
+  requireJit();
+  checkCache(c);
+  if (nPts <= 0)
+    return;
+  AllocStreamScope allocScope(_stream);
+  DevBuf<double>   dX, dOut;
+  DevBuf<int>      first;
+  dX.alloc(3 * nPts);
+  dOut.alloc(static_cast<size_t>(nPts) * c.dims);
+  first.alloc(1);
+  RBF_CUDA(cudaMemcpyAsync(dX.p, hCoords, 3 * nPts * sizeof(double), cudaMemcpyHostToDevice, _stream));
+  RBF_CUDA(cudaMemsetAsync(first.p, 0x7f, sizeof(int), _stream));
+  RBF_CUDA(cudaMemsetAsync(dOut.p, 0, static_cast<size_t>(nPts) * c.dims * sizeof(double), _stream)); // values.setZero() :458
+  pumJitInterpolateAt(solveArgs(), _centerGrid.view(), dX.p, nPts, c.dims, c.coef.p, c.poly.p, dOut.p, first.p, _stream);
+  int f = 0;
+  RBF_CUDA(cudaMemcpyAsync(&f, first.p, sizeof(int), cudaMemcpyDeviceToHost, _stream));
+  RBF_CUDA(cudaMemcpyAsync(hOut, dOut.p, static_cast<size_t>(nPts) * c.dims * sizeof(double), cudaMemcpyDeviceToHost, _stream));
+  RBF_CUDA(cudaStreamSynchronize(_stream));
+  if (f != 0x7f7f7f7f)
+    throwUnassigned(dX.p, f, false);
+}
+
+void PumMapping::jitMapConservativeAt(JitCache &c, const double *hCoords, int64_t nPts, const double *hSource)
+{
+  requireJit();
+  checkCache(c);
+  if (!isConservative())
+    throw MapError(RBFMAP_ERR_STATE, "mapConservativeAt belongs to conservative (write) just-in-time mappings.");
+  if (nPts <= 0)
+    return;
+  AllocStreamScope allocScope(_stream);
+  DevBuf<double>   dX, dU;
+  DevBuf<int>      first;
+  dX.alloc(3 * nPts);
+  dU.alloc(static_cast<size_t>(nPts) * c.dims);
+  first.alloc(1);
+  RBF_CUDA(cudaMemcpyAsync(dX.p, hCoords, 3 * nPts * sizeof(double), cudaMemcpyHostToDevice, _stream));
+  RBF_CUDA(cudaMemcpyAsync(dU.p, hSource, static_cast<size_t>(nPts) * c.dims * sizeof(double), cudaMemcpyHostToDevice, _stream));
+  RBF_CUDA(cudaMemsetAsync(first.p, 0x7f, sizeof(int), _stream));
+  pumJitAccumulateAt(solveArgs(), _centerGrid.view(), dX.p, nPts, c.dims, dU.p, c.coef.p, c.poly.p, first.p, _stream);
+  int f = 0;
+  RBF_CUDA(cudaMemcpyAsync(&f, first.p, sizeof(int), cudaMemcpyDeviceToHost, _stream));
+  RBF_CUDA(cudaStreamSynchronize(_stream));
+  if (f != 0x7f7f7f7f)
+    throwUnassigned(dX.p, f, true);
+}
+
+void PumMapping::jitComplete(JitCache &c, double *hOut)
+{
+  requireJit();
+  checkCache(c);
+  if (!isConservative())
+    throw MapError(RBFMAP_ERR_STATE, "completeJustInTimeMapping belongs to conservative (write) just-in-time mappings.");
+  if (_nIn == 0)
+    return;
+  AllocStreamScope allocScope(_stream);
+  DevBuf<double>   dOut;
+  const size_t     bytes = static_cast<size_t>(_nIn) * c.dims * sizeof(double);
+  dOut.alloc(static_cast<size_t>(_nIn) * c.dims);
+  RBF_CUDA(cudaMemcpyAsync(dOut.p, hOut, bytes, cudaMemcpyHostToDevice, _stream)); // the result is accumulated (:248-252)
+  if (_nClusters > 0) {
+    PumSolveArgs args = solveArgs();
+    args.cacheAu      = c.coef.p;
+    args.cachePoly    = c.poly.p;
+    pumMapConservative(args, _buckets, nullptr, c.dims, dOut.p, _stream);
+  }
+  RBF_CUDA(cudaMemcpyAsync(hOut, dOut.p, bytes, cudaMemcpyDeviceToHost, _stream));
+  RBF_CUDA(cudaStreamSynchronize(_stream));
 }
 
 } // namespace

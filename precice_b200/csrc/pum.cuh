@@ -78,6 +78,9 @@ struct PumSolveArgs {
   PolyRec         *poly;
   const double    *wsum;
   const int       *wcount;
+  // just-in-time write mapping (completeJustInTimeMapping): accumulated A^T (w u) and V^T (w u) of a cache, laid out
+  // [(inOff[c] + i) * dims + d] and [(4 c + k) * dims + d]; null for the ordinary conservative map
+  const double *cacheAu = nullptr, *cachePoly = nullptr;
 };
 
 // Clusters are bucketed by size; every bucket is served by its own kernel instantiation:
@@ -109,5 +112,11 @@ void pumFactor(const PumSolveArgs &a, const PumBuckets &b, int *fail, cudaStream
 void pumFactorWarp(const PumSolveArgs &a, int bucket, const int *list, int64_t count, int *fail, cudaStream_t s);
 void pumMapConsistent(const PumSolveArgs &a, const PumBuckets &b, const double *in, int dims, double *out, cudaStream_t s);
 void pumMapConservative(const PumSolveArgs &a, const PumBuckets &b, const double *in, int dims, double *out, cudaStream_t s);
+// just-in-time mapping (pum_jit.cu)
+void pumJitUpdateCache(const PumSolveArgs &a, const PumBuckets &bk, const double *in, int dims, double *coef, double *poly, cudaStream_t s);
+void pumJitInterpolateAt(const PumSolveArgs &a, const BinGridView &centers, const double *coords, int64_t nPts, int dims, const double *coef, const double *poly,
+                         double *out, int *firstUnassigned, cudaStream_t s);
+void pumJitAccumulateAt(const PumSolveArgs &a, const BinGridView &centers, const double *coords, int64_t nPts, int dims, const double *source, double *coef,
+                        double *poly, int *firstUnassigned, cudaStream_t s);
 
 } // namespace rbfmap

@@ -22,9 +22,13 @@ __global__ void __launch_bounds__(NT) pumMapConservativeKernel(PumSolveArgs args
   const int n   = args.nIn[c];
   const int m   = args.nOut[c];
   const int tid = threadIdx.x;
-  if (m == 0)
+  // completeJustInTimeMapping (PartitionOfUnityMapping.hpp:411-422): Au and epsilon come from the cache
+  // (SphericalVertexCluster::evaluateConservativeCache :242-253, RadialBasisFctSolver::evaluateConservativeCache :562-573)
+  const bool fromCache = args.cacheAu != nullptr;
+  if (m == 0 && !fromCache)
     return;
-  const int      *ids  = args.inIds + args.inOff[c];
+  const long long inOffC = args.inOff[c];
+  const int      *ids  = args.inIds + inOffC;
   const int      *oids = args.outIds + args.outOff[c];
   const double   *mg   = args.mat + args.matOff[c];
   const RbfParams rbf  = args.rbf;
@@ -52,7 +56,7 @@ __global__ void __launch_bounds__(NT) pumMapConservativeKernel(PumSolveArgs args
     vt[i * LDV + 2] = p[2];
 #pragma unroll
     for (int cc = 0; cc < NC; ++cc)
-      vt[i * LDV + 3 + cc] = 0.0;
+      vt[i * LDV + 3 + cc] = fromCache ? args.cacheAu[(inOffC + i) * dims + c0 + cc] : 0.0;
   }
   const int polyMode = args.poly[c].mode, polyMask = args.poly[c].mask, polyRefine = args.poly[c].pad;
 
@@ -60,9 +64,10 @@ __global__ void __launch_bounds__(NT) pumMapConservativeKernel(PumSolveArgs args
   double eps[4 * NC];
 #pragma unroll
   for (int e = 0; e < 4 * NC; ++e)
-    eps[e] = 0.0;
+    eps[e] = fromCache ? args.cachePoly[(static_cast<long long>(c) * 4 + e / NC) * dims + c0 + e % NC] : 0.0;
   const int rowsPerThread = (n + NT - 1) / NT; // 1 for the register-tiled buckets
-  for (int o0 = 0; o0 < m; o0 += NT) {
+  const int mLoop         = fromCache ? 0 : m;
+  for (int o0 = 0; o0 < mLoop; o0 += NT) {
     __syncthreads();
     const int o = o0 + tid;
     if (o < m) {
@@ -118,7 +123,7 @@ __global__ void __launch_bounds__(NT) pumMapConservativeKernel(PumSolveArgs args
       }
     }
   }
-  if (polyMode != 0)
+  if (polyMode != 0 && !fromCache)
     blockReduceSum<4 * NC>(eps, red, NT);
   __syncthreads();
 

@@ -117,6 +117,41 @@ class _Mapping:
     def mapConservative(self, values, dims=1, out=None):
         return self._map(self._L.rbfmap_map_conservative, values, dims, out)
 
+    # ---- just-in-time mapping (Mapping.hpp: initializeMappingDataCache, updateMappingDataCache, mapConsistentAt,
+    # mapConservativeAt, completeJustInTimeMapping); rbf-pum-direct only ----
+    def computeMappingJustInTime(self, mesh_xyz):
+        """computeMapping() when the other mesh is a just-in-time mesh: mesh_xyz = input() (consistent) / output() (conservative)."""
+        a = as_xyz(mesh_xyz)
+        self._n_mesh = a.shape[0]
+        self._n_input, self._n_output = (a.shape[0], 0) if self._cfg.constraint != 1 else (0, a.shape[0])
+        self._check(self._L.rbfmap_compute_mapping_just_in_time(self._h, a.ctypes.data, a.shape[0]))
+
+    def initializeMappingDataCache(self, dims):
+        c = C.c_void_p()
+        self._check(self._L.rbfmap_cache_create(self._h, dims, C.byref(c)))
+        return MappingDataCache(self, c, dims)
+
+    def updateMappingDataCache(self, cache, values):
+        v = np.ascontiguousarray(np.asarray(values, dtype=np.float64).reshape(-1))
+        assert v.size == self._n_mesh * cache.dims, (v.size, self._n_mesh, cache.dims)
+        self._check(self._L.rbfmap_cache_update(self._h, cache._c, v.ctypes.data))
+
+    def mapConsistentAt(self, coords, cache) -> np.ndarray:
+        x = as_xyz(coords)
+        out = np.zeros(x.shape[0] * cache.dims)
+        self._check(self._L.rbfmap_map_consistent_at(self._h, cache._c, x.ctypes.data, x.shape[0], out.ctypes.data))
+        return out
+
+    def mapConservativeAt(self, coords, source, cache):
+        x = as_xyz(coords)
+        v = np.ascontiguousarray(np.asarray(source, dtype=np.float64).reshape(-1))
+        assert v.size == x.shape[0] * cache.dims
+        self._check(self._L.rbfmap_map_conservative_at(self._h, cache._c, x.ctypes.data, x.shape[0], v.ctypes.data))
+
+    def completeJustInTimeMapping(self, cache, out):
+        assert isinstance(out, np.ndarray) and out.dtype == np.float64 and out.flags.c_contiguous and out.size == self._n_mesh * cache.dims
+        self._check(self._L.rbfmap_complete_just_in_time_mapping(self._h, cache._c, out.ctypes.data))
+
     def clear(self):
         self._check(self._L.rbfmap_clear(self._h))
 
@@ -139,6 +174,22 @@ class _Mapping:
 
     # snake-case aliases used by the shared test tables
     compute_mapping = computeMapping
+
+
+class MappingDataCache:
+    """impl::MappingDataCache (mapping/impl/MappingDataCache.hpp:23-71): device-resident per-cluster coefficients of one data."""
+
+    def __init__(self, mapping, handle, dims):
+        self._m, self._c, self.dims = mapping, handle, dims
+
+    def resetData(self):
+        self._m._check(self._m._L.rbfmap_cache_reset(self._m._h, self._c))
+
+    def __del__(self):
+        try:
+            self._m._L.rbfmap_cache_destroy(self._c)
+        except Exception:
+            pass
 
 
 def _config(variant, constraint, dim, basis, param, polynomial, dead_axis=(False, False, False), vpc=50, overlap=0.15,

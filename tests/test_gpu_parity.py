@@ -521,3 +521,144 @@ def test_global_iterative_sharded_two_gpus(pb):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "rel.L2 sharded vs single" in out.stdout
+
+
+# ---------------------------------------------------------------------------------------------- just-in-time mapping
+def _jit_boxes():
+    def box(x0):
+        return [(x0, 0, 0), (x0 + 1, 0, 0), (x0 + 1, 1, 0), (x0, 1, 0), (x0, 0, 1), (x0 + 1, 0, 1), (x0 + 1, 1, 1), (x0, 1, 1)]
+    return np.array(box(0) + box(2) + box(4), float)
+
+
+JIT_VALUES_24 = np.array([1, 2, 2, 1, 3, 6, 6, 3, 3, 4, 4, 3, 9, 12, 12, 9, 5, 6, 6, 5, 15, 18, 18, 15], float)
+
+
+@pytest.mark.gpu
+def test_jit_consistent_3d_with_polynomial_goldens(pb):
+    """PartitionOfUnityMappingTest.cpp:772-937 through the C ABI."""
+    m = pb.PartitionOfUnityMapping("consistent", 3, "compact-polynomial-c0", 3.0, "separate", 5, 0.265, False)
+    m.computeMappingJustInTime(_jit_boxes())
+    assert m.hasComputedMapping()
+    c = m.initializeMappingDataCache(1)
+    m.updateMappingDataCache(c, JIT_VALUES_24)
+    at = lambda pts: m.mapConsistentAt(np.array(pts, float), c)
+    assert at([(0, 0, 0)])[0] == pytest.approx(1.0, rel=1e-12)
+    assert at([(3.5, 0.5, 0.5)])[0] == pytest.approx(9.0, rel=1e-12)
+    assert at([(2.5, 0.5, 1.0)])[0] == pytest.approx(10.5, rel=1e-12)
+    assert at([(0, 0.5, 0.5), (0, 1, 1), (1, 0, 0)]) == pytest.approx([2.0, 3.0, 2.0], rel=1e-12)
+    m.updateMappingDataCache(c, 2 * JIT_VALUES_24)
+    assert at([(0, 0.5, 0.5), (0, 1, 1), (1, 0, 0)]) == pytest.approx([4.0, 6.0, 4.0], rel=1e-12)
+    assert at([(0.5, 0, 0.5), (0.5, 0.5, 1.0), (0.5, 1.0, 0.0)]) == pytest.approx([6.0, 9.0, 3.0], rel=1e-12)
+    m.clear()
+    assert not m.hasComputedMapping()
+    mesh = np.vstack([_jit_boxes(), [(6, 0, 0), (7, 0, 0), (7, 1, 0), (6, 1, 0)]])
+    m.computeMappingJustInTime(mesh)
+    c = m.initializeMappingDataCache(1)
+    m.updateMappingDataCache(c, np.concatenate([JIT_VALUES_24, [7.0, 8.0, 8.0, 7.0]]))
+    assert at([(6.5, 1.0, 0.0), (0.5, 0.5, 1.0), (0.5, 1.0, 0.0)]) == pytest.approx([7.5, 4.5, 1.5], rel=1e-12)
+
+
+@pytest.mark.gpu
+def test_jit_consistent_2d_no_polynomial_goldens(pb):
+    """PartitionOfUnityMappingTest.cpp:939-1098 through the C ABI (goldens at 1e-7)."""
+    mesh = np.array([(0, 0), (1, 0), (1, 1), (0, 1), (2, 0), (3, 0), (3, 1), (2, 1), (4, 0), (5, 0), (5, 1), (4, 1)], float)
+    m = pb.PartitionOfUnityMapping("consistent", 2, "compact-polynomial-c4", 3.0, "off", 5, 0.265, False)
+    m.computeMappingJustInTime(mesh)
+    c = m.initializeMappingDataCache(2)
+    m.updateMappingDataCache(c, JIT_VALUES_24)
+    at = lambda pts: m.mapConsistentAt(np.array(pts, float), c)
+    assert at([(0, 0)]) == pytest.approx([1.0, 2.0], rel=1e-12)
+    assert at([(5, 1)]) == pytest.approx([15.0, 18.0], rel=1e-12)
+    assert at([(0.5, 0.0)]) == pytest.approx([1.71978075, 1.71978075], rel=1e-7)
+    assert at([(3.5, 0.5)]) == pytest.approx([10.39684625, 10.48101386], rel=1e-7)
+    assert at([(4, 0), (5, 0)]) == pytest.approx([5.0, 6.0, 6.0, 5.0], rel=1e-12)
+    m.updateMappingDataCache(c, 0.5 * JIT_VALUES_24)
+    assert at([(4, 0), (5, 0)]) == pytest.approx([2.5, 3.0, 3.0, 2.5], rel=1e-12)
+
+
+@pytest.mark.gpu
+def test_jit_conservative_3d_goldens(pb):
+    """PartitionOfUnityMappingTest.cpp:1311-1495 through the C ABI."""
+    m = pb.PartitionOfUnityMapping("conservative", 3, "compact-polynomial-c2", 3.0, "separate", 5, 0.265, False)
+    m.computeMappingJustInTime(_jit_boxes())
+    c = m.initializeMappingDataCache(1)
+    out = np.zeros(24)
+    m.mapConservativeAt([(5.0, 0.0, 1.0)], [4.3], c)
+    m.completeJustInTimeMapping(c, out)
+    expected = np.zeros(24)
+    expected[21] = 4.3
+    assert out.sum() == pytest.approx(4.3, rel=1e-12)
+    assert out == pytest.approx(expected, abs=1e-12)
+    c.resetData()
+    out[:] = 0
+    m.mapConservativeAt([(5.0, 0.0, 1.0)], [4.3], c)
+    m.mapConservativeAt([(3.5, 0.5, 0.5), (4.5, 1.0, 1.0), (0.1, 0.0, 1.0)], [4.3, 17.3, 5.8], c)
+    m.completeJustInTimeMapping(c, out)
+    assert out.sum() == pytest.approx(4.3 + 4.3 + 17.3 + 5.8, rel=1e-12)
+    assert out[6] == pytest.approx(0.063700286667, rel=1e-7)
+    assert out[23] == pytest.approx(9.2744883594, rel=1e-7)
+    m.clear()
+    mesh = np.vstack([_jit_boxes(), [(6, 0, 0)]])
+    m.computeMappingJustInTime(mesh)
+    c = m.initializeMappingDataCache(1)
+    out = np.zeros(25)
+    m.mapConservativeAt([(0.5, 0.5, 0.5)], [4.3], c)
+    m.mapConservativeAt([(6.0, 0.0, 0.0)], [42.0], c)
+    m.completeJustInTimeMapping(c, out)
+    assert out.sum() == pytest.approx(46.3, rel=1e-12)
+    assert out[24] == pytest.approx(42.0, rel=1e-12)
+    assert out[0] == pytest.approx(0.505106848, rel=1e-7)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dim,ncomp,polynomial", [(3, 1, "separate"), (3, 3, "off"), (2, 2, "separate")])
+def test_jit_vs_oracle_halton(pb, orc, dim, ncomp, polynomial):
+    """Read and write just-in-time mapping on Halton meshes: device vs oracle, 1e-10 relative L2."""
+    n, npts = 3000, 1000
+    mesh = refcases.halton(n, (2, 3, 5)[:dim])
+    pts = 0.05 + 0.9 * refcases.halton(npts, (7, 11, 13)[:dim])
+    probe = orc.PumMapping("consistent", dim, "compact-polynomial-c6", 1.0, polynomial, 50, 0.15, True)
+    probe.compute_mapping_jit(mesh)
+    support = 2.0 * probe.cluster_radius  # SURVEY 8d: support = 2 x cluster radius
+    vals = np.stack([refcases.field(mesh) * (k + 1) + k for k in range(ncomp)], axis=1).reshape(-1)
+    g = pb.PartitionOfUnityMapping("consistent", dim, "compact-polynomial-c6", support, polynomial, 50, 0.15, True)
+    o = orc.PumMapping("consistent", dim, "compact-polynomial-c6", support, polynomial, 50, 0.15, True)
+    g.computeMappingJustInTime(mesh)
+    o.compute_mapping_jit(mesh)
+    cg, co = g.initializeMappingDataCache(ncomp), o.initialize_cache(ncomp)
+    g.updateMappingDataCache(cg, vals)
+    o.update_cache(co, vals)
+    rg, ro = g.mapConsistentAt(pts, cg), o.map_consistent_at(pts, co)
+    assert refcases.rel_l2(rg, ro) <= 1e-10, refcases.rel_l2(rg, ro)
+    # write direction
+    g2 = pb.PartitionOfUnityMapping("conservative", dim, "compact-polynomial-c6", support, polynomial, 50, 0.15, True)
+    o2 = orc.PumMapping("conservative", dim, "compact-polynomial-c6", support, polynomial, 50, 0.15, True)
+    g2.computeMappingJustInTime(mesh)
+    o2.compute_mapping_jit(mesh)
+    cg, co = g2.initializeMappingDataCache(ncomp), o2.initialize_cache(ncomp)
+    loads = np.stack([refcases.field(pts) * (k + 1) + 0.5 for k in range(ncomp)], axis=1).reshape(-1)
+    g2.mapConservativeAt(pts, loads, cg)
+    o2.map_conservative_at(pts, loads, co)
+    og, oo = np.zeros(n * ncomp), np.zeros(n * ncomp)
+    g2.completeJustInTimeMapping(cg, og)
+    o2.complete_just_in_time_mapping(co, oo)
+    assert refcases.rel_l2(og, oo) <= 1e-8, refcases.rel_l2(og, oo)
+    if polynomial == "separate":  # sums are conserved
+        assert og.reshape(-1, ncomp).sum(axis=0) == pytest.approx(loads.reshape(-1, ncomp).sum(axis=0), rel=1e-10)
+
+
+@pytest.mark.gpu
+def test_jit_errors(pb):
+    m = pb.PartitionOfUnityMapping("consistent", 3, "compact-polynomial-c6", 0.5, "separate", 50, 0.15, True)
+    with pytest.raises(pb.MappingError):
+        m.initializeMappingDataCache(1)  # not computed
+    mesh = refcases.halton(2000, (2, 3, 5))
+    m.computeMappingJustInTime(mesh)
+    c = m.initializeMappingDataCache(1)
+    m.updateMappingDataCache(c, refcases.field(mesh))
+    with pytest.raises(pb.MappingError) as e:
+        m.mapConsistentAt(np.array([[5.0, 5.0, 5.0]]), c)
+    assert "could not be assigned to any cluster" in str(e.value)
+    g = pb.RadialBasisFctMapping("consistent", 3, "compact-polynomial-c2", 0.5)
+    with pytest.raises(pb.MappingError):
+        g.computeMappingJustInTime(mesh)
