@@ -662,3 +662,27 @@ def test_jit_errors(pb):
     g = pb.RadialBasisFctMapping("consistent", 3, "compact-polynomial-c2", 0.5)
     with pytest.raises(pb.MappingError):
         g.computeMappingJustInTime(mesh)
+
+
+# ---------------------------------------------------------------------------------------------- committed fixtures (tests/golden)
+@pytest.mark.gpu
+@pytest.mark.parametrize("idx", range(4))
+def test_against_committed_fixtures(pb, idx):
+    """CUDA path vs tests/golden/pum_halton.npz (oracle outputs, generated by tests/golden/make_golden.py): 1e-10 relative L2
+    (1e-9 in the conservative direction), cluster count and radius exact."""
+    import importlib.util, os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "make_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    data = np.load(os.path.join(here, "pum_halton.npz"))
+    name, constraint, dim, basis, polynomial, n_in, n_out, dims = mod.CASES[idx]
+    inp, out, vals = mod.inputs(dim, n_in, n_out, dims, constraint)
+    m = pb.PartitionOfUnityMapping(constraint, dim, basis, float(data[name + "/support"]), polynomial, 50, 0.15, True)
+    m.compute_mapping(inp, out)
+    st = m.stats()
+    assert st["n_clusters"] == int(data[name + "/clusters"])
+    assert st["cluster_radius"] == float(data[name + "/radius"])
+    res = m.map(vals, dims)
+    tol = 1e-10 if constraint == "consistent" else 1e-9
+    assert refcases.rel_l2(res, data[name + "/result"]) <= tol, refcases.rel_l2(res, data[name + "/result"])

@@ -137,3 +137,24 @@ def test_jit_conservative_3d():
     assert out.sum() == pytest.approx(46.3, rel=1e-12)
     assert out[24] == pytest.approx(42.0, rel=1e-12)
     assert out[0] == pytest.approx(0.505106848, rel=1e-7)
+
+
+# ---------------------------------------------------------------------------------------------- committed fixtures (tests/golden)
+def _golden():
+    import importlib.util, os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "make_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod, np.load(os.path.join(here, "pum_halton.npz"))
+
+
+@pytest.mark.parametrize("idx", range(4))
+def test_oracle_reproduces_committed_fixtures(idx):
+    """tests/golden/pum_halton.npz was written by tests/golden/make_golden.py from this oracle; it must stay reproducible."""
+    mod, data = _golden()
+    case = mod.CASES[idx]
+    support, res, nc, radius = mod.run_case(case)
+    assert support == pytest.approx(float(data[case[0] + "/support"]), rel=1e-14)
+    assert nc == int(data[case[0] + "/clusters"])
+    assert refcases.rel_l2(res, data[case[0] + "/result"]) <= 1e-12
