@@ -7,7 +7,21 @@
 // (Kokkos prior art: do_batched_solve, device/KokkosPUMKernels_Impl.hpp:491-814.)
 #include "pum_map.cuh"
 
+#include <cstdio>
+
 namespace rbfmap {
+#ifdef RBF_PHASE_TIMING
+__device__ unsigned long long g_mapPhase[8]; // cycles: 0 start->gathered, 1 poly, 2 solve, 3 eval, 4 clusters
+#define RBF_STAMP(k)                                                                   \
+  do {                                                                                 \
+    const long long now_ = clock64();                                                  \
+    if (threadIdx.x == 0)                                                              \
+      atomicAdd(&g_mapPhase[k], static_cast<unsigned long long>(now_ - stamp_));       \
+    stamp_ = now_;                                                                     \
+  } while (0)
+#else
+#define RBF_STAMP(k)
+#endif
 namespace {
 
 template <int KIND, int NC, int NT, bool STAGE_M, bool DIM3>
@@ -18,6 +32,9 @@ __global__ void __launch_bounds__(NT) pumMapConsistentKernel(PumSolveArgs args, 
   extern __shared__ __align__(16) double dyn[];
   __shared__ __align__(8) unsigned long long mbar;
 
+#ifdef RBF_PHASE_TIMING
+  long long stamp_ = clock64();
+#endif
   const int       c    = list[blockIdx.x];
   const int       n    = args.nIn[c];
   const int       m    = args.nOut[c];
@@ -59,6 +76,7 @@ __global__ void __launch_bounds__(NT) pumMapConsistentKernel(PumSolveArgs args, 
   }
   __syncthreads();
 
+  RBF_STAMP(0);
   // ---- separated polynomial: beta = lstsq(Q, f); f <- f - Q beta (RadialBasisFctSolver.hpp:446-449) ----
   const int polyMode = args.poly[c].mode, polyMask = args.poly[c].mask, polyRefine = args.poly[c].pad;
   double    beta[4][NC];
@@ -130,6 +148,7 @@ __global__ void __launch_bounds__(NT) pumMapConsistentKernel(PumSolveArgs args, 
     __syncthreads();
   }
 
+  RBF_STAMP(1);
   // ---- lambda = C^-1 f ----
   if (STAGE_M) {
     if (tid < 32) { // one warp solves; the others wait at the barrier
@@ -141,6 +160,7 @@ __global__ void __launch_bounds__(NT) pumMapConsistentKernel(PumSolveArgs args, 
     blockedSolve<NC, LDV, long long>(mg, n, vt + 3, tid, NT);
   }
 
+  RBF_STAMP(2);
   // ---- out = A lambda + V beta, weighted accumulation (SphericalVertexCluster.hpp:322-334) ----
   // One out-vertex per lane and pass. When the last pass has 16 or fewer vertices left, 2 / 4 / 8 lanes share a vertex
   // (each takes every 2nd / 4th / 8th in-vertex, partial sums are combined with shuffles) so that no lane idles.
@@ -220,6 +240,11 @@ __global__ void __launch_bounds__(NT) pumMapConsistentKernel(PumSolveArgs args, 
         atomicAdd(&out[gid * dims + c0 + cc], acc[cc] * w);
     }
   }
+  RBF_STAMP(3);
+#ifdef RBF_PHASE_TIMING
+  if (threadIdx.x == 0)
+    atomicAdd(&g_mapPhase[4], 1ull);
+#endif
 }
 
 template <int KIND, int NC, int NT, bool STAGE_M>
@@ -275,8 +300,20 @@ void dispatchConsistent(const PumSolveArgs &a, const PumBuckets &bk, const doubl
 
 void pumMapConsistent(const PumSolveArgs &a, const PumBuckets &bk, const double *in, int dims, double *out, cudaStream_t s)
 {
+#ifdef RBF_PHASE_TIMING
+  unsigned long long zero[8] = {0};
+  RBF_CUDA(cudaMemcpyToSymbolAsync(g_mapPhase, zero, sizeof(zero), 0, cudaMemcpyHostToDevice, s));
+#endif
   RBF_DISPATCH_HOT_BASIS(a.rbf.kind, dispatchConsistent<KIND>(a, bk, in, dims, out, s));
   RBF_CUDA(cudaGetLastError());
+#ifdef RBF_PHASE_TIMING
+  unsigned long long h[8];
+  RBF_CUDA(cudaMemcpyFromSymbolAsync(h, g_mapPhase, sizeof(h), 0, cudaMemcpyDeviceToHost, s));
+  RBF_CUDA(cudaStreamSynchronize(s));
+  if (h[4])
+    fprintf(stderr, "[map phases] cycles per cluster: gather %.0f poly %.0f solve %.0f eval %.0f (clusters %llu)\n", double(h[0]) / h[4], double(h[1]) / h[4],
+            double(h[2]) / h[4], double(h[3]) / h[4], h[4]);
+#endif
 }
 
 } // namespace rbfmap
