@@ -123,6 +123,7 @@ public:
     _wsum.release();
     _wcount.release();
     _buckets.order.release();
+    _buckets.entries.release();
     _centerGrid = BinGrid();
     _jit        = false;
     _nClusters  = 0;

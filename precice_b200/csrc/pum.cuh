@@ -97,8 +97,16 @@ __host__ __device__ inline int pumBucketOf(int n)
     return 8 + (n + 15) / 16 - 5;
   return 12;
 }
+// What a per-cluster kernel needs to start, in one 48-byte record per bucket slot: without it a CTA walks
+// list -> sizes / offsets -> vertex IDs -> coordinates, four dependent DRAM accesses of ~1.5 us each under load.
+struct __align__(16) PumEntry {
+  int       c, n, m, pad;
+  long long inOff, outOff, matOff, pad2;
+};
+
 struct PumBuckets {
-  DevBuf<int> order;                  // cluster indices sorted by bucket
+  DevBuf<int>      order;             // cluster indices sorted by bucket
+  DevBuf<PumEntry> entries;           // the same order, with sizes and offsets
   int64_t     start[kNumBuckets + 1]; // offsets into `order`
   int         maxN[kNumBuckets];      // largest cluster of each bucket
 };
@@ -109,7 +117,7 @@ void pumClassify(const PumMembership &m, int64_t nClusters, PumBuckets &b, rbfma
 void pumPolySetup(const PumSolveArgs &a, int64_t nClusters, int polynomial, cudaStream_t s);
 // fail = device int (lowest failing cluster index or INT_MAX)
 void pumFactor(const PumSolveArgs &a, const PumBuckets &b, int *fail, cudaStream_t s);
-void pumFactorWarp(const PumSolveArgs &a, int bucket, const int *list, int64_t count, int *fail, cudaStream_t s);
+void pumFactorWarp(const PumSolveArgs &a, int bucket, const PumEntry *list, int64_t count, int *fail, cudaStream_t s);
 void pumMapConsistent(const PumSolveArgs &a, const PumBuckets &b, const double *in, int dims, double *out, cudaStream_t s);
 void pumMapConservative(const PumSolveArgs &a, const PumBuckets &b, const double *in, int dims, double *out, cudaStream_t s);
 // just-in-time mapping (pum_jit.cu)

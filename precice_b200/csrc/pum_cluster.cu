@@ -389,7 +389,9 @@ __global__ void classifyKernel(const int *__restrict__ nIn, const int *__restric
   }
 }
 
-__global__ void bucketScatterKernel(const int *__restrict__ nIn, int64_t nClusters, const long long *__restrict__ start, int *__restrict__ cursor, int *__restrict__ order)
+__global__ void bucketScatterKernel(const int *__restrict__ nIn, const int *__restrict__ nOut, const long long *__restrict__ inOff,
+                                    const long long *__restrict__ outOff, const long long *__restrict__ matOff, int64_t nClusters,
+                                    const long long *__restrict__ start, int *__restrict__ cursor, int *__restrict__ order, PumEntry *__restrict__ entries)
 {
   const int64_t c    = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   const int     lane = threadIdx.x & 31;
@@ -401,7 +403,9 @@ __global__ void bucketScatterKernel(const int *__restrict__ nIn, int64_t nCluste
     if (lane == leader)
       base = atomicAdd(&cursor[b], __popc(peers));
     base = __shfl_sync(peers, base, leader);
-    order[start[b] + base + __popc(peers & ((1u << lane) - 1u))] = static_cast<int>(c);
+    const long long at = start[b] + base + __popc(peers & ((1u << lane) - 1u));
+    order[at]          = static_cast<int>(c);
+    entries[at]        = PumEntry{static_cast<int>(c), nIn[c], nOut[c], 0, inOff[c], outOff[c], matOff[c], 0};
   }
 }
 
@@ -566,7 +570,10 @@ void pumClassify(const PumMembership &m, int64_t nClusters, PumBuckets &b, rbfma
   stats.max_n  = static_cast<int64_t>(h[18]);
   RBF_CUDA(cudaMemcpyAsync(dStart.p, start, sizeof(start), cudaMemcpyHostToDevice, s));
   b.order.alloc(std::max<int64_t>(nClusters, 1));
-  bucketScatterKernel<<<divUp(nClusters, 256), 256, 0, s>>>(m.nIn.p, nClusters, dStart.p, cursor.p, b.order.p);
+  b.entries.alloc(std::max<int64_t>(nClusters, 1));
+  bucketScatterKernel<<<divUp(nClusters, 256), 256, 0, s>>>(m.nIn.p, m.nOut.p, reinterpret_cast<const long long *>(m.inOff.p),
+                                                           reinterpret_cast<const long long *>(m.outOff.p), reinterpret_cast<const long long *>(m.matOff.p),
+                                                           nClusters, dStart.p, cursor.p, b.order.p, b.entries.p);
   RBF_LAUNCHED();
   RBF_CUDA(cudaGetLastError());
   RBF_CUDA(cudaStreamSynchronize(s)); // `start` (host stack) and the temporaries must outlive the copies

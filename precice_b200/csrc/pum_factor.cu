@@ -302,7 +302,7 @@ void pumFactor(const PumSolveArgs &a, const PumBuckets &bk, int *fail, cudaStrea
       continue;
     const int *list = bk.order.p + bk.start[b];
     if (b < 8 && !g_pumForceTiledFactor) { // clusters of up to 64 vertices: one warp per cluster on DMMA (pum_factor_warp.cu)
-      pumFactorWarp(a, b, list, count, fail, s);
+      pumFactorWarp(a, b, bk.entries.p + bk.start[b], count, fail, s);
       continue;
     }
     RBF_DISPATCH_HOT_BASIS(a.rbf.kind, factorBucket<KIND>(a, b, list, count, bk.maxN[b], fail, s));

@@ -48,17 +48,18 @@ __device__ __forceinline__ double pivotReciprocal3(double d)
 }
 
 template <int KIND, int NB, bool DIM3>
-__global__ void __launch_bounds__(32, NB <= 4 ? 20 : NB == 5 ? 16 : NB == 6 ? 14 : NB == 7 ? kW7 : 10) pumFactorWarpKernel(PumSolveArgs args, const int *__restrict__ list, int *__restrict__ fail)
+__global__ void __launch_bounds__(32, NB <= 4 ? 20 : NB == 5 ? 16 : NB == 6 ? 14 : NB == 7 ? kW7 : 10) pumFactorWarpKernel(PumSolveArgs args, const PumEntry *__restrict__ list, int *__restrict__ fail)
 {
   constexpr int NMAX = NB * 8;
   __shared__ __align__(16) double sx[NMAX], sy[NMAX], sz[NMAX];
   __shared__ __align__(16) double slot[NB][8 * kSlotLd];
 
-  const int       c    = list[blockIdx.x];
-  const int       n    = args.nIn[c];
+  const PumEntry  en   = list[blockIdx.x];
+  const int       c    = en.c;
+  const int       n    = en.n;
   const int       lane = threadIdx.x;
   const int       g = lane >> 2, q = lane & 3;
-  const int      *ids   = args.inIds + args.inOff[c];
+  const int      *ids   = args.inIds + en.inOff;
   const RbfParams rbf   = args.rbf;
   const double    invR2 = rbf.p1 * rbf.p1;
 
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(32, NB <= 4 ? 20 : NB == 5 ? 16 : NB == 6 ? 14
   }
 
   // ---- packed store ----
-  double *mp = args.mat + args.matOff[c];
+  double *mp = args.mat + en.matOff;
 #pragma unroll
   for (int b = 0; b < NB; ++b) {
     const int j0 = 8 * b + 2 * q;
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(32, NB <= 4 ? 20 : NB == 5 ? 16 : NB == 6 ? 14
 }
 
 template <int KIND, int NB>
-void launchWarp(const PumSolveArgs &a, const int *list, int64_t count, int *fail, cudaStream_t s)
+void launchWarp(const PumSolveArgs &a, const PumEntry *list, int64_t count, int *fail, cudaStream_t s)
 {
   if (a.dim == 3)
     pumFactorWarpKernel<KIND, NB, true><<<static_cast<unsigned>(count), 32, 0, s>>>(a, list, fail);
@@ -223,7 +224,7 @@ void launchWarp(const PumSolveArgs &a, const int *list, int64_t count, int *fail
 }
 
 template <int KIND>
-void warpBucket(const PumSolveArgs &a, int bucket, const int *list, int64_t count, int *fail, cudaStream_t s)
+void warpBucket(const PumSolveArgs &a, int bucket, const PumEntry *list, int64_t count, int *fail, cudaStream_t s)
 {
   switch (bucket) {
   case 0: launchWarp<KIND, 1>(a, list, count, fail, s); break;
@@ -241,7 +242,7 @@ void warpBucket(const PumSolveArgs &a, int bucket, const int *list, int64_t coun
 } // namespace
 
 // buckets 0..7 (clusters of up to 8 (bucket + 1) <= 64 vertices)
-void pumFactorWarp(const PumSolveArgs &a, int bucket, const int *list, int64_t count, int *fail, cudaStream_t s)
+void pumFactorWarp(const PumSolveArgs &a, int bucket, const PumEntry *list, int64_t count, int *fail, cudaStream_t s)
 {
   RBF_DISPATCH_HOT_BASIS(a.rbf.kind, warpBucket<KIND>(a, bucket, list, count, fail, s));
 }

@@ -25,7 +25,7 @@ __device__ unsigned long long g_mapPhase[8]; // cycles: 0 start->gathered, 1 pol
 namespace {
 
 template <int KIND, int NC, int NT, bool STAGE_M, bool DIM3>
-__global__ void __launch_bounds__(NT) pumMapConsistentKernel(PumSolveArgs args, const int *__restrict__ list, const double *__restrict__ in, int dims, int c0,
+__global__ void __launch_bounds__(NT) pumMapConsistentKernel(PumSolveArgs args, const PumEntry *__restrict__ list, const double *__restrict__ in, int dims, int c0,
                                                              double *__restrict__ out)
 {
   constexpr int LDV = TileLd<NC>::value;
@@ -35,15 +35,16 @@ __global__ void __launch_bounds__(NT) pumMapConsistentKernel(PumSolveArgs args, 
 #ifdef RBF_PHASE_TIMING
   long long stamp_ = clock64();
 #endif
-  const int       c    = list[blockIdx.x];
-  const int       n    = args.nIn[c];
-  const int       m    = args.nOut[c];
+  const PumEntry  en   = list[blockIdx.x];
+  const int       c    = en.c;
+  const int       n    = en.n;
+  const int       m    = en.m;
   const int       tid  = threadIdx.x;
   if (m == 0)
     return; // nothing to evaluate (uniform per CTA)
-  const int      *ids  = args.inIds + args.inOff[c];
-  const int      *oids = args.outIds + args.outOff[c];
-  const double   *mg   = args.mat + args.matOff[c];
+  const int      *ids  = args.inIds + en.inOff;
+  const int      *oids = args.outIds + en.outOff;
+  const double   *mg   = args.mat + en.matOff;
   const RbfParams rbf  = args.rbf;
   const double    cx = args.centers[3 * c], cy = args.centers[3 * c + 1], cz = args.centers[3 * c + 2];
   const double    rinv = 1.0 / args.radius;
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__(NT) pumMapConsistentKernel(PumSolveArgs args, 
 }
 
 template <int KIND, int NC, int NT, bool STAGE_M>
-void launchConsistent(const PumSolveArgs &a, const int *list, int64_t count, int maxN, const double *in, int dims, int c0, double *out, cudaStream_t s)
+void launchConsistent(const PumSolveArgs &a, const PumEntry *list, int64_t count, int maxN, const double *in, int dims, int c0, double *out, cudaStream_t s)
 {
   const size_t tri = STAGE_M ? static_cast<size_t>(paddedTri(maxN)) : 0;
   const size_t sm  = (tri + static_cast<size_t>(TileLd<NC>::value) * maxN + 16 * (NT / 32)) * sizeof(double);
@@ -265,7 +266,7 @@ void launchConsistent(const PumSolveArgs &a, const int *list, int64_t count, int
 }
 
 template <int KIND, int NC>
-void bucketConsistent(const PumSolveArgs &a, int bucket, const int *list, int64_t count, int maxN, const double *in, int dims, int c0, double *out, cudaStream_t s)
+void bucketConsistent(const PumSolveArgs &a, int bucket, const PumEntry *list, int64_t count, int maxN, const double *in, int dims, int c0, double *out, cudaStream_t s)
 {
   if (bucket < 8)
     launchConsistent<KIND, NC, 32, true>(a, list, count, maxN, in, dims, c0, out, s);
@@ -282,7 +283,7 @@ void dispatchConsistent(const PumSolveArgs &a, const PumBuckets &bk, const doubl
     const int64_t count = bk.start[b + 1] - bk.start[b];
     if (count <= 0)
       continue;
-    const int *list = bk.order.p + bk.start[b];
+    const PumEntry *list = bk.entries.p + bk.start[b];
     for (int c0 = 0; c0 < dims;) { // components are processed in groups of up to 3 per launch
       const int nc = std::min(3, dims - c0);
       if (nc == 1)
