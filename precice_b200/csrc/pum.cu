@@ -579,7 +579,32 @@ void PumMapping::jitMapConsistentAt(JitCache &c, const double *hCoords, int64_t 
   RBF_CUDA(cudaMemcpyAsync(dX.p, hCoords, 3 * nPts * sizeof(double), cudaMemcpyHostToDevice, _stream));
   RBF_CUDA(cudaMemsetAsync(first.p, 0x7f, sizeof(int), _stream));
   RBF_CUDA(cudaMemsetAsync(dOut.p, 0, static_cast<size_t>(nPts) * c.dims * sizeof(double), _stream)); // values.setZero() :458
-  pumJitInterpolateAt(solveArgs(), _centerGrid.view(), dX.p, nPts, c.dims, c.coef.p, c.poly.p, dOut.p, first.p, _stream);
+  bool clustered = false;
+  if (nPts >= 4096 && stats.max_n <= 128) {
+    // large point sets: bin the points, list them per cluster and evaluate cluster by cluster like the ordinary map
+    double pMin[3], pMax[3];
+    computeBounds(dX.p, nPts, pMin, pMax, _stream);
+    BinGrid ptGrid;
+    ptGrid.build(dX.p, nPts, pMin, pMax, 0.5 * _radius, _stream);
+    DevBuf<double>  wsum;
+    DevBuf<int>     wcount, nP, ptIds;
+    DevBuf<int64_t> ptOff;
+    wsum.alloc(nPts);
+    wcount.alloc(nPts);
+    RBF_CUDA(cudaMemsetAsync(wsum.p, 0, nPts * sizeof(double), _stream));
+    RBF_CUDA(cudaMemsetAsync(wcount.p, 0, nPts * sizeof(int), _stream));
+    clustered = pumBuildPointMembership(_centers.p, _nClusters, ptGrid, _radius, _scratch, nP, ptOff, ptIds, wsum.p, wcount.p, _stream);
+    if (clustered) {
+      const int64_t bad = pumFirstUnassigned(wcount.p, nPts, _stream);
+      if (bad >= 0)
+        throwUnassigned(dX.p, bad, false);
+      pumJitEvaluateClustered(solveArgs(), _nClusters, static_cast<int>(stats.max_n), dX.p, nP.p, reinterpret_cast<const long long *>(ptOff.p), ptIds.p, wsum.p,
+                              wcount.p, c.dims, c.coef.p, c.poly.p, dOut.p, _stream);
+      RBF_CUDA(cudaStreamSynchronize(_stream)); // the temporaries of this scope are in use until here
+    }
+  }
+  if (!clustered)
+    pumJitInterpolateAt(solveArgs(), _centerGrid.view(), dX.p, nPts, c.dims, c.coef.p, c.poly.p, dOut.p, first.p, _stream);
   int f = 0;
   RBF_CUDA(cudaMemcpyAsync(&f, first.p, sizeof(int), cudaMemcpyDeviceToHost, _stream));
   RBF_CUDA(cudaMemcpyAsync(hOut, dOut.p, static_cast<size_t>(nPts) * c.dims * sizeof(double), cudaMemcpyDeviceToHost, _stream));

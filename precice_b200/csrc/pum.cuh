@@ -52,6 +52,8 @@ struct PumScratch {
 
 void    pumBuildMembership(const double *dCenters, int64_t nClusters, const BinGrid &inMesh, const BinGrid &outMesh, double radius, PumMembership &m,
                            PumScratch &scratch, double *wsum, int *wcount, cudaStream_t s);
+bool    pumBuildPointMembership(const double *dCenters, int64_t nClusters, const BinGrid &points, double radius, PumScratch &scratch, DevBuf<int> &nPts,
+                                DevBuf<int64_t> &off, DevBuf<int> &ids, double *wsum, int *wcount, cudaStream_t s);
 int64_t pumFirstUnassigned(const int *wcount, int64_t nOut, cudaStream_t s); // -1: every out-vertex lies in a cluster
 
 // Per-cluster separated-polynomial record (RadialBasisFctSolver.hpp:377-410 condensed).
@@ -124,6 +126,9 @@ void pumMapConservative(const PumSolveArgs &a, const PumBuckets &b, const double
 void pumJitUpdateCache(const PumSolveArgs &a, const PumBuckets &bk, const double *in, int dims, double *coef, double *poly, cudaStream_t s);
 void pumJitInterpolateAt(const PumSolveArgs &a, const BinGridView &centers, const double *coords, int64_t nPts, int dims, const double *coef, const double *poly,
                          double *out, int *firstUnassigned, cudaStream_t s);
+// cluster-centric evaluation for large point sets: per-cluster point lists (pumBuildPointMembership) + the map kernel's evaluation
+void pumJitEvaluateClustered(const PumSolveArgs &a, int64_t nClusters, int maxN, const double *coords, const int *nPts, const long long *ptOff, const int *ptIds,
+                             const double *wsum, const int *wcount, int dims, const double *coef, const double *poly, double *out, cudaStream_t s);
 void pumJitAccumulateAt(const PumSolveArgs &a, const BinGridView &centers, const double *coords, int64_t nPts, int dims, const double *source, double *coef,
                         double *poly, int *firstUnassigned, cudaStream_t s);
 

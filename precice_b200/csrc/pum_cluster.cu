@@ -521,6 +521,73 @@ void pumBuildMembership(const double *dCenters, int64_t nClusters, const BinGrid
   RBF_CUDA(cudaGetLastError());
 }
 
+// ---- membership of arbitrary points (just-in-time read mapping): the points within the cluster radius of every centre,
+// sorted ascending per cluster, plus their partition-of-unity weight sums; PartitionOfUnityMapping.hpp:290-341 seen
+// from the cluster side. Returns false if a cluster holds more than kSlotCap points (the caller falls back). ----
+__global__ void memberGatherPointsKernel(const double *__restrict__ centers, int64_t nClusters, BinGridView gpts, double radius, int *__restrict__ nPts,
+                                         int *__restrict__ slot, int *__restrict__ overflow, double *__restrict__ wsum, int *__restrict__ wcount)
+{
+  __shared__ __align__(16) int stage[kWarpsPerBlock][kSlotCap];
+  const int64_t c    = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int     lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (c >= nClusters)
+    return;
+  const double cx = centers[3 * c], cy = centers[3 * c + 1], cz = centers[3 * c + 2];
+  const int    co = gatherToShared<true>(gpts, cx, cy, cz, radius, stage[w], lane, radius, 1.0 / radius, wsum, wcount);
+  if (co <= kSlotCap)
+    rankSortToGlobal(stage[w], co, slot + c * kSlotCap, lane);
+  if (lane == 0) {
+    nPts[c] = co;
+    if (co > kSlotCap)
+      atomicOr(overflow, 1);
+  }
+}
+
+__global__ void memberPackPointsKernel(int64_t nClusters, const int *__restrict__ nPts, const long long *__restrict__ off, const int *__restrict__ slot,
+                                       int *__restrict__ ids)
+{
+  const int64_t c    = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int     lane = threadIdx.x & 31;
+  if (c >= nClusters)
+    return;
+  const int  n = nPts[c];
+  int       *d = ids + off[c];
+  const int *q = slot + c * kSlotCap;
+  for (int i = lane; i < n; i += 32)
+    d[i] = q[i];
+}
+
+bool pumBuildPointMembership(const double *dCenters, int64_t nClusters, const BinGrid &points, double radius, PumScratch &scratch, DevBuf<int> &nPts,
+                             DevBuf<int64_t> &off, DevBuf<int> &ids, double *wsum, int *wcount, cudaStream_t s)
+{
+  nPts.alloc(nClusters);
+  off.alloc(nClusters + 1);
+  const size_t slots = static_cast<size_t>(std::max<int64_t>(nClusters, 1)) * kSlotCap;
+  if (scratch.slotOut.n < slots) {
+    RBF_CUDA(cudaStreamSynchronize(s));
+    scratch.slotOut.reserve(slots + slots / 8);
+  }
+  DevBuf<int> overflow;
+  overflow.alloc(1);
+  RBF_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), s));
+  memberGatherPointsKernel<<<warpGrid(nClusters), kBlockThreads, 0, s>>>(dCenters, nClusters, points.view(), radius, nPts.p, scratch.slotOut.p, overflow.p, wsum,
+                                                                        wcount);
+  RBF_LAUNCHED();
+  exclusiveScan(nPts.p, off.p, nClusters, s);
+  int64_t total = 0;
+  int     over  = 0;
+  RBF_CUDA(cudaMemcpyAsync(&total, off.p + nClusters, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  RBF_CUDA(cudaMemcpyAsync(&over, overflow.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  RBF_CUDA(cudaStreamSynchronize(s));
+  if (over)
+    return false;
+  ids.alloc(std::max<int64_t>(total, 1));
+  memberPackPointsKernel<<<warpGrid(nClusters), kBlockThreads, 0, s>>>(nClusters, nPts.p, reinterpret_cast<const long long *>(off.p), scratch.slotOut.p, ids.p);
+  RBF_LAUNCHED();
+  RBF_CUDA(cudaGetLastError());
+  return true;
+}
+
 int64_t pumFirstUnassigned(const int *wcount, int64_t nOut, cudaStream_t s)
 {
   DevBuf<int> first;

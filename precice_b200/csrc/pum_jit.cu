@@ -307,6 +307,146 @@ __global__ void __launch_bounds__(32 * kJitWarps) pumAccumulateAtKernel(PumSolve
   }
 }
 
+// ---- cluster-centric mapConsistentAt for large point sets: one warp per cluster evaluates all query points that lie in
+// it (the evaluation loop of pumMapConsistentKernel with the cached coefficients instead of a solve) ----
+template <int KIND, int NC>
+__global__ void __launch_bounds__(32) pumEvaluateClusteredKernel(PumSolveArgs args, const double *__restrict__ coords, const int *__restrict__ nPts,
+                                                                 const long long *__restrict__ ptOff, const int *__restrict__ ptIds,
+                                                                 const double *__restrict__ wsum, const int *__restrict__ wcount, int dims, int c0,
+                                                                 const double *__restrict__ coef, const double *__restrict__ poly, double *__restrict__ out)
+{
+  constexpr int LDV = TileLd<NC>::value;
+  extern __shared__ __align__(16) double vt[];
+  const int c = blockIdx.x;
+  const int m = nPts[c];
+  if (m == 0)
+    return;
+  const int       n    = args.nIn[c];
+  const int       tid  = threadIdx.x;
+  const long long off  = args.inOff[c];
+  const int      *ids  = args.inIds + off;
+  const int      *oids = ptIds + ptOff[c];
+  const RbfParams rbf  = args.rbf;
+  const double    cx = args.centers[3 * c], cy = args.centers[3 * c + 1], cz = args.centers[3 * c + 2];
+  const double    rinv  = 1.0 / args.radius;
+  const double    invR2 = rbf.p1 * rbf.p1;
+  const int       polyMode = args.poly[c].mode, polyMask = args.poly[c].mask;
+  for (int i = tid; i < n; i += 32) {
+    const double *p = args.inXyz + 3 * static_cast<long long>(ids[i]);
+    vt[i * LDV]     = p[0];
+    vt[i * LDV + 1] = p[1];
+    vt[i * LDV + 2] = p[2];
+#pragma unroll
+    for (int cc = 0; cc < NC; ++cc)
+      vt[i * LDV + 3 + cc] = coef[(off + i) * dims + c0 + cc];
+  }
+  double beta[4][NC];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int cc = 0; cc < NC; ++cc)
+      beta[k][cc] = polyMode != 0 ? poly[(static_cast<long long>(c) * 4 + k) * dims + c0 + cc] : 0.0;
+  __syncwarp();
+  for (int o0 = 0; o0 < m; o0 += 32) {
+    const int rem   = m - o0;
+    const int split = rem <= 16 ? (rem <= 4 ? 8 : rem <= 8 ? 4 : 2) : 1;
+    const int per   = 32 / split;
+    const int ol = tid % per, sub = tid / per;
+    const bool have = ol < rem;
+    long long  gid = 0;
+    double     x = 0.0, y = 0.0, z = 0.0;
+    if (have) {
+      gid             = oids[o0 + ol];
+      const double *p = coords + 3 * gid;
+      x = p[0], y = p[1], z = p[2];
+    }
+    double acc[NC];
+#pragma unroll
+    for (int cc = 0; cc < NC; ++cc)
+      acc[cc] = 0.0;
+    if (have) {
+      const double *vp = vt + sub * LDV;
+      const int     stride = split * LDV;
+      int j = sub;
+      for (; j + 3 * split < n; j += 4 * split, vp += 4 * stride) {
+        double bx[4], by[4], bz[4], cf[4][NC], phi[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const double2 xy = *reinterpret_cast<const double2 *>(vp + u * stride);
+          const double2 zb = *reinterpret_cast<const double2 *>(vp + u * stride + 2);
+          bx[u] = xy.x, by[u] = xy.y, bz[u] = zb.x, cf[u][0] = zb.y;
+          if (NC > 1) {
+            const double2 b12 = *reinterpret_cast<const double2 *>(vp + u * stride + 4);
+            cf[u][1]          = b12.x;
+            if (NC > 2)
+              cf[u][2] = b12.y;
+          }
+        }
+        pairBasisBatch<KIND, true, 4>(x, y, z, bx, by, bz, rbf, invR2, phi);
+#pragma unroll
+        for (int cc = 0; cc < NC; ++cc)
+          acc[cc] += fma(phi[0], cf[0][cc], phi[1] * cf[1][cc]) + fma(phi[2], cf[2][cc], phi[3] * cf[3][cc]);
+      }
+      for (; j < n; j += split, vp += stride) {
+        const double2 xy  = *reinterpret_cast<const double2 *>(vp);
+        const double2 zb  = *reinterpret_cast<const double2 *>(vp + 2);
+        const double  phi = pairBasis<KIND, true>(x, y, z, xy.x, xy.y, zb.x, rbf, invR2);
+        acc[0]            = fma(phi, zb.y, acc[0]);
+        if (NC > 1) {
+          const double2 b12 = *reinterpret_cast<const double2 *>(vp + 4);
+          acc[1]            = fma(phi, b12.x, acc[1]);
+          if (NC > 2)
+            acc[2] = fma(phi, b12.y, acc[2]);
+        }
+      }
+    }
+    if (split > 1) {
+      for (int o = per; o < 32; o <<= 1) {
+#pragma unroll
+        for (int cc = 0; cc < NC; ++cc)
+          acc[cc] += __shfl_xor_sync(0xffffffffu, acc[cc], o);
+      }
+    }
+    if (have && sub == 0) {
+      if (polyMode != 0) {
+        double q[4];
+        polyRow(polyMode, polyMask, x, y, z, cx, cy, cz, rinv, q);
+#pragma unroll
+        for (int cc = 0; cc < NC; ++cc)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            acc[cc] += q[k] * beta[k][cc];
+      }
+      const double w = normalizedWeight(x, y, z, cx, cy, cz, rinv, wsum[gid], wcount[gid]);
+#pragma unroll
+      for (int cc = 0; cc < NC; ++cc)
+        atomicAdd(&out[gid * dims + c0 + cc], acc[cc] * w);
+    }
+  }
+}
+
+template <int KIND>
+void evaluateClustered(const PumSolveArgs &a, int64_t nClusters, int maxN, const double *coords, const int *nPts, const long long *ptOff, const int *ptIds,
+                       const double *wsum, const int *wcount, int dims, const double *coef, const double *poly, double *out, cudaStream_t s)
+{
+  for (int c0 = 0; c0 < dims;) {
+    const int nc = std::min(3, dims - c0);
+    const unsigned grid = static_cast<unsigned>(nClusters);
+    if (nc == 1) {
+      const size_t sm = static_cast<size_t>(TileLd<1>::value) * maxN * sizeof(double);
+      pumEvaluateClusteredKernel<KIND, 1><<<grid, 32, sm, s>>>(a, coords, nPts, ptOff, ptIds, wsum, wcount, dims, c0, coef, poly, out);
+    } else if (nc == 2) {
+      const size_t sm = static_cast<size_t>(TileLd<2>::value) * maxN * sizeof(double);
+      pumEvaluateClusteredKernel<KIND, 2><<<grid, 32, sm, s>>>(a, coords, nPts, ptOff, ptIds, wsum, wcount, dims, c0, coef, poly, out);
+    } else {
+      const size_t sm = static_cast<size_t>(TileLd<3>::value) * maxN * sizeof(double);
+      pumEvaluateClusteredKernel<KIND, 3><<<grid, 32, sm, s>>>(a, coords, nPts, ptOff, ptIds, wsum, wcount, dims, c0, coef, poly, out);
+    }
+    RBF_LAUNCHED();
+    c0 += nc;
+  }
+}
+
 template <int NC>
 void launchCoefficient(const PumSolveArgs &a, int bucket, const int *list, int64_t count, int maxN, const double *in, int dims, int c0, double *coef, double *poly,
                        cudaStream_t s)
@@ -355,6 +495,15 @@ void pumJitInterpolateAt(const PumSolveArgs &a, const BinGridView &centers, cons
   const unsigned grid = static_cast<unsigned>((nPts + kJitWarps - 1) / kJitWarps);
   RBF_DISPATCH_BASIS(a.rbf.kind, (pumInterpolateAtKernel<KIND><<<grid, 32 * kJitWarps, 0, s>>>(a, centers, coords, nPts, dims, coef, poly, out, firstUnassigned)));
   RBF_LAUNCHED();
+  RBF_CUDA(cudaGetLastError());
+}
+
+void pumJitEvaluateClustered(const PumSolveArgs &a, int64_t nClusters, int maxN, const double *coords, const int *nPts, const long long *ptOff, const int *ptIds,
+                             const double *wsum, const int *wcount, int dims, const double *coef, const double *poly, double *out, cudaStream_t s)
+{
+  if (nClusters <= 0)
+    return;
+  RBF_DISPATCH_HOT_BASIS(a.rbf.kind, evaluateClustered<KIND>(a, nClusters, maxN, coords, nPts, ptOff, ptIds, wsum, wcount, dims, coef, poly, out, s));
   RBF_CUDA(cudaGetLastError());
 }
 

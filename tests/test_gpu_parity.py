@@ -611,10 +611,11 @@ def test_jit_conservative_3d_goldens(pb):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("npts", [1000, 6000])  # 6000: the cluster-centric evaluation for large point sets
 @pytest.mark.parametrize("dim,ncomp,polynomial", [(3, 1, "separate"), (3, 3, "off"), (2, 2, "separate")])
-def test_jit_vs_oracle_halton(pb, orc, dim, ncomp, polynomial):
+def test_jit_vs_oracle_halton(pb, orc, dim, ncomp, polynomial, npts):
     """Read and write just-in-time mapping on Halton meshes: device vs oracle, 1e-10 relative L2."""
-    n, npts = 3000, 1000
+    n = 3000
     mesh = refcases.halton(n, (2, 3, 5)[:dim])
     pts = 0.05 + 0.9 * refcases.halton(npts, (7, 11, 13)[:dim])
     probe = orc.PumMapping("consistent", dim, "compact-polynomial-c6", 1.0, polynomial, 50, 0.15, True)
