@@ -188,7 +188,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--vertices", dest="n", type=int, default=10_000_000, help="vertices per mesh per GPU (BASELINE.json configs[3]: 10M)")
-    ap.add_argument("--ref-sample", type=int, default=1_000_000, help="vertices of the bounded CPU sample")
+    ap.add_argument("--ref-sample", type=int, default=8_000_000, help="vertices of the bounded CPU sample (about 10 s of CPU work on 16 threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
