@@ -126,25 +126,25 @@ __device__ __forceinline__ double pairBasis(double ax, double ay, double az, dou
 // ~16-20 cycles for its operand, so a single evaluation (a chain of ~20 dependent operations) uses a twentieth of the
 // pipe; ptxas does not interleave unrolled iterations by itself, but it keeps this order. All N pairs share the point a.
 template <int KIND, bool DIM3, int N>
-__device__ __forceinline__ void pairBasisBatch(double ax, double ay, double az, const double (&bx)[N], const double (&by)[N], const double (&bz)[N],
-                                               const RbfParams &f, double invR2, double (&out)[N])
+__device__ __forceinline__ void pairBasisBatch(const double (&ax)[N], const double (&ay)[N], const double (&az)[N], const double (&bx)[N],
+                                               const double (&by)[N], const double (&bz)[N], const RbfParams &f, double invR2, double (&out)[N])
 {
   if (FastBasis<KIND>::value) {
     double x[N], y[N], s[N], e[N], p[N], q[N], q2[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      const double dx = ax - bx[i];
+      const double dx = ax[i] - bx[i];
       x[i]            = dx * dx;
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      const double dy = ay - by[i];
+      const double dy = ay[i] - by[i];
       x[i]            = fma(dy, dy, x[i]);
     }
     if (DIM3) {
 #pragma unroll
       for (int i = 0; i < N; ++i) {
-        const double dz = az - bz[i];
+        const double dz = az[i] - bz[i];
         x[i]            = fma(dz, dz, x[i]);
       }
     }
@@ -218,8 +218,20 @@ __device__ __forceinline__ void pairBasisBatch(double ax, double ay, double az, 
   } else {
 #pragma unroll
     for (int i = 0; i < N; ++i)
-      out[i] = evalBasisK<KIND>(distSqrt(sqDistD<DIM3>(ax, ay, az, bx[i], by[i], bz[i])), f);
+      out[i] = evalBasisK<KIND>(distSqrt(sqDistD<DIM3>(ax[i], ay[i], az[i], bx[i], by[i], bz[i])), f);
   }
+}
+
+// all N pairs share the point a
+template <int KIND, bool DIM3, int N>
+__device__ __forceinline__ void pairBasisBatch(double ax, double ay, double az, const double (&bx)[N], const double (&by)[N], const double (&bz)[N],
+                                               const RbfParams &f, double invR2, double (&out)[N])
+{
+  double axs[N], ays[N], azs[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    axs[i] = ax, ays[i] = ay, azs[i] = az;
+  pairBasisBatch<KIND, DIM3, N>(axs, ays, azs, bx, by, bz, f, invR2, out);
 }
 
 // reciprocal of a positive pivot: MUFU.RCP64H seed + two Newton steps, no slow path (~1 ulp)

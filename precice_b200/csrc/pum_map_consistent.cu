@@ -25,7 +25,7 @@ __device__ unsigned long long g_mapPhase[8]; // cycles: 0 start->gathered, 1 pol
 namespace {
 
 template <int KIND, int NC, int NT, bool STAGE_M, bool DIM3>
-__global__ void __launch_bounds__(NT) pumMapConsistentKernel(PumSolveArgs args, const PumEntry *__restrict__ list, const double *__restrict__ in, int dims, int c0,
+__global__ void __launch_bounds__(NT, NT == 32 ? 14 : 1) pumMapConsistentKernel(PumSolveArgs args, const PumEntry *__restrict__ list, const double *__restrict__ in, int dims, int c0,
                                                              double *__restrict__ out)
 {
   constexpr int LDV = TileLd<NC>::value;
@@ -186,10 +186,11 @@ __global__ void __launch_bounds__(NT) pumMapConsistentKernel(PumSolveArgs args, 
       const double *vp = vt + sub * LDV;
       const int     stride = split * LDV;
       int j = sub;
-      for (; j + 3 * split < n; j += 4 * split, vp += 4 * stride) { // four in-vertices side by side (see pairBasisBatch)
-        double bx[4], by[4], bz[4], cf[4][NC], phi[4];
+      constexpr int kBatch = 4; // in-vertices evaluated side by side (see pairBasisBatch)
+      for (; j + (kBatch - 1) * split < n; j += kBatch * split, vp += kBatch * stride) {
+        double bx[kBatch], by[kBatch], bz[kBatch], cf[kBatch][NC], phi[kBatch];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < kBatch; ++u) {
           const double2 xy = *reinterpret_cast<const double2 *>(vp + u * stride);
           const double2 zb = *reinterpret_cast<const double2 *>(vp + u * stride + 2);
           bx[u] = xy.x, by[u] = xy.y, bz[u] = zb.x, cf[u][0] = zb.y;
@@ -200,10 +201,18 @@ __global__ void __launch_bounds__(NT) pumMapConsistentKernel(PumSolveArgs args, 
               cf[u][2] = b12.y;
           }
         }
-        pairBasisBatch<KIND, DIM3, 4>(x, y, z, bx, by, bz, rbf, invR2, phi);
+        pairBasisBatch<KIND, DIM3, kBatch>(x, y, z, bx, by, bz, rbf, invR2, phi);
 #pragma unroll
-        for (int cc = 0; cc < NC; ++cc)
-          acc[cc] += fma(phi[0], cf[0][cc], phi[1] * cf[1][cc]) + fma(phi[2], cf[2][cc], phi[3] * cf[3][cc]);
+        for (int cc = 0; cc < NC; ++cc) {
+          double part[kBatch / 2];
+#pragma unroll
+          for (int u = 0; u < kBatch / 2; ++u)
+            part[u] = fma(phi[2 * u], cf[2 * u][cc], phi[2 * u + 1] * cf[2 * u + 1][cc]);
+#pragma unroll
+          for (int u = 1; u < kBatch / 2; ++u)
+            part[0] += part[u];
+          acc[cc] += part[0];
+        }
       }
       for (; j < n; j += split, vp += stride) {
         const double2 xy  = *reinterpret_cast<const double2 *>(vp);
