@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(32 * kJitWarps) pumAccumulateAtKernel(PumSolve
 // ---- cluster-centric mapConsistentAt for large point sets: one warp per cluster evaluates all query points that lie in
 // it (the evaluation loop of pumMapConsistentKernel with the cached coefficients instead of a solve) ----
 template <int KIND, int NC>
-__global__ void __launch_bounds__(32) pumEvaluateClusteredKernel(PumSolveArgs args, const double *__restrict__ coords, const int *__restrict__ nPts,
+__global__ void __launch_bounds__(32, 16) pumEvaluateClusteredKernel(PumSolveArgs args, const double *__restrict__ coords, const int *__restrict__ nPts,
                                                                  const long long *__restrict__ ptOff, const int *__restrict__ ptIds,
                                                                  const double *__restrict__ wsum, const int *__restrict__ wcount, int dims, int c0,
                                                                  const double *__restrict__ coef, const double *__restrict__ poly, double *__restrict__ out)
