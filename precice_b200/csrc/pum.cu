@@ -121,6 +121,7 @@ public:
     _mat.release();
     _poly.release();
     _wsum.release();
+    _outRec.release();
     _wcount.release();
     _buckets.order.release();
     _buckets.entries.release();
@@ -164,6 +165,7 @@ private:
   DevBuf<double>  _mat;
   DevBuf<PolyRec> _poly;
   DevBuf<double>  _wsum;
+  DevBuf<double4> _outRec;
   DevBuf<int>     _wcount;
   PumBuckets      _buckets;
   bool            _jit = false; // the other mesh is a just-in-time mesh
@@ -193,6 +195,7 @@ PumSolveArgs PumMapping::solveArgs() const
   a.poly    = _poly.p;
   a.wsum    = _wsum.p;
   a.wcount  = _wcount.p;
+  a.outRec  = _outRec.p;
   return a;
 }
 
@@ -467,6 +470,10 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
     }
   }
 
+  if (_mem.sumOut > 0) { // cluster-ordered out-vertex records for the map kernels
+    _outRec.alloc(_mem.sumOut);
+    pumBuildOutRecords(solveArgs(), _nClusters, _outRec.p, _stream);
+  }
   trace.phase("weights");
   // size buckets + statistics (device pass over the per-cluster counts)
   pumClassify(_mem, _nClusters, _buckets, stats, _stream);
@@ -499,7 +506,7 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
                                             "Please check if your coupling meshes are correct (e.g. no vertices are duplicated) or reconfigure "
                                             "your basis-function (e.g. reduce the support-radius).");
   }
-  stats.device_bytes       = static_cast<int64_t>(_inXyz.bytes() + _outXyz.bytes() + _centers.bytes() + _mem.bytes() + _mat.bytes() + _poly.bytes() + _wsum.bytes() + _wcount.bytes());
+  stats.device_bytes       = static_cast<int64_t>(_inXyz.bytes() + _outXyz.bytes() + _centers.bytes() + _mem.bytes() + _mat.bytes() + _poly.bytes() + _wsum.bytes() + _wcount.bytes() + _outRec.bytes());
   stats.ms_compute_kernels = whole.stop();
   stats.kernel_launches    = g_launches;
   _computed                = true;

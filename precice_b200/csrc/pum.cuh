@@ -83,6 +83,9 @@ struct PumSolveArgs {
   // just-in-time write mapping (completeJustInTimeMapping): accumulated A^T (w u) and V^T (w u) of a cache, laid out
   // [(inOff[c] + i) * dims + d] and [(4 c + k) * dims + d]; null for the ordinary conservative map
   const double *cacheAu = nullptr, *cachePoly = nullptr;
+  // cluster-ordered out-vertex records (x, y, z, normalised partition-of-unity weight) at [outOff[c] + o]: one coalesced
+  // 32-byte load per out-vertex in the map kernels instead of ID -> coordinates -> weight sum -> weight evaluation
+  const double4 *outRec = nullptr;
 };
 
 // Clusters are bucketed by size; every bucket is served by its own kernel instantiation:
@@ -117,6 +120,7 @@ struct PumBuckets {
 void pumClassify(const PumMembership &m, int64_t nClusters, PumBuckets &b, rbfmap_stats &stats, cudaStream_t s);
 
 void pumPolySetup(const PumSolveArgs &a, int64_t nClusters, int polynomial, cudaStream_t s);
+void pumBuildOutRecords(const PumSolveArgs &a, int64_t nClusters, double4 *rec, cudaStream_t s);
 // fail = device int (lowest failing cluster index or INT_MAX)
 void pumFactor(const PumSolveArgs &a, const PumBuckets &b, int *fail, cudaStream_t s);
 void pumFactorWarp(const PumSolveArgs &a, int bucket, const PumEntry *list, int64_t count, int *fail, cudaStream_t s);

@@ -7,7 +7,7 @@
 //   impl/CreateClustering.hpp:205-208  removeTaggedVertices
 //   impl/SphericalVertexCluster.hpp:153-162  per-cluster sphere queries + sorted ID sets
 //   PartitionOfUnityMapping.hpp:290-341  computeNormalizedWeight (the per-vertex weight sums, accumulated from the cluster side)
-#include "pum.cuh"
+#include "pum_device.cuh"
 
 #include <algorithm>
 
@@ -586,6 +586,34 @@ bool pumBuildPointMembership(const double *dCenters, int64_t nClusters, const Bi
   RBF_LAUNCHED();
   RBF_CUDA(cudaGetLastError());
   return true;
+}
+
+// ---- cluster-ordered out-vertex records: coordinates + normalised weight (PartitionOfUnityMapping.hpp:321-336), static per mapping ----
+__global__ void outRecordKernel(PumSolveArgs a, int64_t nClusters, double4 *__restrict__ rec)
+{
+  const int64_t c    = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int     lane = threadIdx.x & 31;
+  if (c >= nClusters)
+    return;
+  const int       m   = a.nOut[c];
+  const long long off = a.outOff[c];
+  const double    cx = a.centers[3 * c], cy = a.centers[3 * c + 1], cz = a.centers[3 * c + 2];
+  const double    rinv = 1.0 / a.radius;
+  for (int o = lane; o < m; o += 32) {
+    const long long gid = a.outIds[off + o];
+    const double   *p   = a.outXyz + 3 * gid;
+    const double    x = p[0], y = p[1], z = p[2];
+    rec[off + o]        = make_double4(x, y, z, normalizedWeight(x, y, z, cx, cy, cz, rinv, a.wsum[gid], a.wcount[gid]));
+  }
+}
+
+void pumBuildOutRecords(const PumSolveArgs &a, int64_t nClusters, double4 *rec, cudaStream_t s)
+{
+  if (nClusters <= 0)
+    return;
+  outRecordKernel<<<warpGrid(nClusters), kBlockThreads, 0, s>>>(a, nClusters, rec);
+  RBF_LAUNCHED();
+  RBF_CUDA(cudaGetLastError());
 }
 
 int64_t pumFirstUnassigned(const int *wcount, int64_t nOut, cudaStream_t s)

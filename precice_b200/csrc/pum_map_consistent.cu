@@ -172,11 +172,11 @@ __global__ void __launch_bounds__(NT, NT == 32 ? 14 : 1) pumMapConsistentKernel(
     const int ol = tid % per, sub = tid / per;
     const bool have = ol < rem;
     long long  gid = 0;
-    double     x = 0.0, y = 0.0, z = 0.0;
+    double     x = 0.0, y = 0.0, z = 0.0, wNorm = 0.0;
     if (have) {
-      gid             = oids[o0 + ol];
-      const double *p = args.outXyz + 3 * gid;
-      x = p[0], y = p[1], z = p[2];
+      const double4 r = args.outRec[en.outOff + o0 + ol]; // x, y, z, normalised weight: one coalesced load
+      x = r.x, y = r.y, z = r.z, wNorm = r.w;
+      gid = oids[o0 + ol];
     }
     double acc[NC];
 #pragma unroll
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(NT, NT == 32 ? 14 : 1) pumMapConsistentKernel(
           for (int k = 0; k < 4; ++k)
             acc[cc] += q[k] * beta[k][cc];
       }
-      const double w = normalizedWeight(x, y, z, cx, cy, cz, rinv, args.wsum[gid], args.wcount[gid]);
+      const double w = wNorm;
 #pragma unroll
       for (int cc = 0; cc < NC; ++cc)
         atomicAdd(&out[gid * dims + c0 + cc], acc[cc] * w);
