@@ -122,6 +122,7 @@ public:
     _poly.release();
     _wsum.release();
     _outRec.release();
+    _inRec.release();
     _wcount.release();
     _buckets.order.release();
     _buckets.entries.release();
@@ -166,6 +167,7 @@ private:
   DevBuf<PolyRec> _poly;
   DevBuf<double>  _wsum;
   DevBuf<double4> _outRec;
+  DevBuf<double>  _inRec;
   DevBuf<int>     _wcount;
   PumBuckets      _buckets;
   bool            _jit = false; // the other mesh is a just-in-time mesh
@@ -196,6 +198,7 @@ PumSolveArgs PumMapping::solveArgs() const
   a.wsum    = _wsum.p;
   a.wcount  = _wcount.p;
   a.outRec  = _outRec.p;
+  a.inRec   = _inRec.p;
   return a;
 }
 
@@ -447,7 +450,7 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
     computeBounds(_centers.p, _nClusters, cMin, cMax, _stream);
     _centerGrid.build(_centers.p, _nClusters, cMin, cMax, 0.5 * _radius, _stream);
   }
-  pumBuildMembership(_centers.p, _nClusters, inGrid, outGrid, _radius, _mem, _scratch, _wsum.p, _wcount.p, _stream);
+  pumBuildMembership(_centers.p, _nClusters, inGrid, outGrid, _radius, _mem, _scratch, _wsum.p, _wcount.p, _inXyz.p, _outXyz.p, _inRec, _outRec, _stream);
   trace.phase("membership");
 
   // partition-of-unity weight sums (PartitionOfUnityMapping.hpp:263-276, 290-341)
@@ -470,10 +473,6 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
     }
   }
 
-  if (_mem.sumOut > 0) { // cluster-ordered out-vertex records for the map kernels
-    _outRec.alloc(_mem.sumOut);
-    pumBuildOutRecords(solveArgs(), _nClusters, _outRec.p, _stream);
-  }
   trace.phase("weights");
   // size buckets + statistics (device pass over the per-cluster counts)
   pumClassify(_mem, _nClusters, _buckets, stats, _stream);
@@ -506,7 +505,7 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
                                             "Please check if your coupling meshes are correct (e.g. no vertices are duplicated) or reconfigure "
                                             "your basis-function (e.g. reduce the support-radius).");
   }
-  stats.device_bytes       = static_cast<int64_t>(_inXyz.bytes() + _outXyz.bytes() + _centers.bytes() + _mem.bytes() + _mat.bytes() + _poly.bytes() + _wsum.bytes() + _wcount.bytes() + _outRec.bytes());
+  stats.device_bytes       = static_cast<int64_t>(_inXyz.bytes() + _outXyz.bytes() + _centers.bytes() + _mem.bytes() + _mat.bytes() + _poly.bytes() + _wsum.bytes() + _wcount.bytes() + _outRec.bytes() + _inRec.bytes());
   stats.ms_compute_kernels = whole.stop();
   stats.kernel_launches    = g_launches;
   _computed                = true;

@@ -51,7 +51,8 @@ struct PumScratch {
 };
 
 void    pumBuildMembership(const double *dCenters, int64_t nClusters, const BinGrid &inMesh, const BinGrid &outMesh, double radius, PumMembership &m,
-                           PumScratch &scratch, double *wsum, int *wcount, cudaStream_t s);
+                           PumScratch &scratch, double *wsum, int *wcount, const double *inXyz, const double *outXyz, DevBuf<double> &inRec,
+                           DevBuf<double4> &outRec, cudaStream_t s);
 bool    pumBuildPointMembership(const double *dCenters, int64_t nClusters, const BinGrid &points, double radius, PumScratch &scratch, DevBuf<int> &nPts,
                                 DevBuf<int64_t> &off, DevBuf<int> &ids, double *wsum, int *wcount, cudaStream_t s);
 int64_t pumFirstUnassigned(const int *wcount, int64_t nOut, cudaStream_t s); // -1: every out-vertex lies in a cluster
@@ -86,6 +87,9 @@ struct PumSolveArgs {
   // cluster-ordered out-vertex records (x, y, z, normalised partition-of-unity weight) at [outOff[c] + o]: one coalesced
   // 32-byte load per out-vertex in the map kernels instead of ID -> coordinates -> weight sum -> weight evaluation
   const double4 *outRec = nullptr;
+  // cluster-ordered in-vertex coordinates at [(inOff[c] + i) * 3 + d] (factorisation and polynomial set-up read them
+  // contiguously instead of ID -> coordinates)
+  const double *inRec = nullptr;
 };
 
 // Clusters are bucketed by size; every bucket is served by its own kernel instantiation:
@@ -121,6 +125,7 @@ void pumClassify(const PumMembership &m, int64_t nClusters, PumBuckets &b, rbfma
 
 void pumPolySetup(const PumSolveArgs &a, int64_t nClusters, int polynomial, cudaStream_t s);
 void pumBuildOutRecords(const PumSolveArgs &a, int64_t nClusters, double4 *rec, cudaStream_t s);
+void pumBuildInRecords(const PumSolveArgs &a, int64_t sumIn, double *rec, cudaStream_t s);
 // fail = device int (lowest failing cluster index or INT_MAX)
 void pumFactor(const PumSolveArgs &a, const PumBuckets &b, int *fail, cudaStream_t s);
 void pumFactorWarp(const PumSolveArgs &a, int bucket, const PumEntry *list, int64_t count, int *fail, cudaStream_t s);

@@ -233,7 +233,7 @@ constexpr int kSlotCap = 128;
 // PartitionOfUnityMapping.hpp:306-333 seen from the cluster side: w_c = C2(|x - c| / r) is added to the weight sum of
 // the vertex and its cluster count is incremented (the reference loops over the clusters of a vertex instead).
 template <bool WEIGHTS>
-__device__ __forceinline__ int gatherToShared(const BinGridView &g, double cx, double cy, double cz, double r, int *stage, int lane, double rW = 0.0,
+__device__ __forceinline__ int gatherToShared(const BinGridView &g, double cx, double cy, double cz, double r, int *stage, int *stagePos, int lane, double rW = 0.0,
                                               double rinv = 0.0, double *__restrict__ wsum = nullptr, int *__restrict__ wcount = nullptr)
 {
   int base = 0;
@@ -247,8 +247,10 @@ __device__ __forceinline__ int gatherToShared(const BinGridView &g, double cx, d
     int            id  = 0;
     if (hit || (WEIGHTS && d < rW))
       id = g.ids[pos];
-    if (hit && at < kSlotCap)
-      stage[at] = id;
+    if (hit && at < kSlotCap) {
+      stage[at]    = id;
+      stagePos[at] = pos; // position in the binned arrays: neighbouring hits share cache lines there
+    }
     if (WEIGHTS && d < rW) {
       atomicAdd(wsum + id, pumWeight(d, rinv));
       atomicAdd(wcount + id, 1);
@@ -260,8 +262,8 @@ __device__ __forceinline__ int gatherToShared(const BinGridView &g, double cx, d
   return base;
 }
 
-// ascending rank sort of the n <= kSlotCap distinct ids in stage -> dst[0..n)
-__device__ __forceinline__ void rankSortToGlobal(const int *stage, int n, int *__restrict__ dst, int lane)
+// ascending rank sort of the n <= kSlotCap distinct ids in stage; dst[rank] = payload of that id (its binned position)
+__device__ __forceinline__ void rankSortToGlobal(const int *stage, const int *payload, int n, int *__restrict__ dst, int lane)
 {
   for (int i = lane; i < n; i += 32) {
     const int v = stage[i];
@@ -273,7 +275,7 @@ __device__ __forceinline__ void rankSortToGlobal(const int *stage, int n, int *_
     }
     for (; j < n; ++j)
       rank += stage[j] < v;
-    dst[rank] = v;
+    dst[rank] = payload[i];
   }
 }
 
@@ -282,18 +284,19 @@ __global__ void memberGatherKernel(const double *__restrict__ centers, int64_t n
                                    int *__restrict__ slotOut, int *__restrict__ overflow, double *__restrict__ wsum, int *__restrict__ wcount)
 {
   __shared__ __align__(16) int stage[kWarpsPerBlock][kSlotCap];
+  __shared__ int               stagePos[kWarpsPerBlock][kSlotCap];
   const int64_t c    = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
   const int     lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   if (c >= nClusters)
     return;
   const double cx = centers[3 * c], cy = centers[3 * c + 1], cz = centers[3 * c + 2];
-  const int    ci = gatherToShared<false>(gin, cx, cy, cz, rIn, stage[w], lane);
+  const int    ci = gatherToShared<false>(gin, cx, cy, cz, rIn, stage[w], stagePos[w], lane);
   if (ci <= kSlotCap)
-    rankSortToGlobal(stage[w], ci, slotIn + c * kSlotCap, lane);
+    rankSortToGlobal(stage[w], stagePos[w], ci, slotIn + c * kSlotCap, lane);
   __syncwarp();
-  const int co = gatherToShared<true>(gout, cx, cy, cz, rOut, stage[w], lane, rIn, 1.0 / rIn, wsum, wcount);
+  const int co = gatherToShared<true>(gout, cx, cy, cz, rOut, stage[w], stagePos[w], lane, rIn, 1.0 / rIn, wsum, wcount);
   if (co <= kSlotCap)
-    rankSortToGlobal(stage[w], co, slotOut + c * kSlotCap, lane);
+    rankSortToGlobal(stage[w], stagePos[w], co, slotOut + c * kSlotCap, lane);
   if (lane == 0) {
     nIn[c]  = ci;
     nOut[c] = co;
@@ -303,9 +306,13 @@ __global__ void memberGatherKernel(const double *__restrict__ centers, int64_t n
   }
 }
 
+// Also writes the cluster-ordered records the algebra kernels read: in-vertex coordinates and, per out-vertex, coordinates
+// + normalised partition-of-unity weight (the weight sums are final once the gather kernel has finished).
 __global__ void memberPackKernel(int64_t nClusters, const int *__restrict__ nIn, const int *__restrict__ nOut, const long long *__restrict__ inOff,
                                  const long long *__restrict__ outOff, const int *__restrict__ slotIn, const int *__restrict__ slotOut,
-                                 int *__restrict__ inIds, int *__restrict__ outIds)
+                                 int *__restrict__ inIds, int *__restrict__ outIds, const double *__restrict__ centers, double radius,
+                                 BinGridView gin, BinGridView gout, const double *__restrict__ wsum,
+                                 const int *__restrict__ wcount, double *__restrict__ inRec, double4 *__restrict__ outRec)
 {
   const int64_t c    = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
   const int     lane = threadIdx.x & 31;
@@ -314,10 +321,26 @@ __global__ void memberPackKernel(int64_t nClusters, const int *__restrict__ nIn,
   const int  ni = nIn[c], no = nOut[c];
   int       *di = inIds + inOff[c], *dO = outIds + outOff[c];
   const int *si = slotIn + c * kSlotCap, *so = slotOut + c * kSlotCap;
-  for (int i = lane; i < ni; i += 32)
-    di[i] = si[i];
-  for (int i = lane; i < no; i += 32)
-    dO[i] = so[i];
+  const double cx = centers[3 * c], cy = centers[3 * c + 1], cz = centers[3 * c + 2];
+  const double rinv = 1.0 / radius;
+  double      *ri = inRec + 3 * inOff[c];
+  double4     *ro = outRec + outOff[c];
+  for (int i = lane; i < ni; i += 32) { // the slots hold positions in the binned arrays, in ascending-ID order
+    const int pos = si[i];
+    di[i]         = gin.ids[pos];
+    const double *p = gin.xyz + 3 * static_cast<long long>(pos);
+    ri[3 * i]       = p[0];
+    ri[3 * i + 1]   = p[1];
+    ri[3 * i + 2]   = p[2];
+  }
+  for (int i = lane; i < no; i += 32) {
+    const int pos = so[i];
+    const int id  = gout.ids[pos];
+    dO[i]         = id;
+    const double *p = gout.xyz + 3 * static_cast<long long>(pos);
+    const double  x = p[0], y = p[1], z = p[2];
+    ro[i]           = make_double4(x, y, z, normalizedWeight(x, y, z, cx, cy, cz, rinv, wsum[id], wcount[id]));
+  }
 }
 
 __global__ void memberFillKernel(const double *__restrict__ centers, int64_t nClusters, BinGridView gin, BinGridView gout, double rIn, double rOut,
@@ -470,7 +493,8 @@ int64_t PumClustering::compact(DevBuf<double> &out, cudaStream_t s)
 }
 
 void pumBuildMembership(const double *dCenters, int64_t nClusters, const BinGrid &inMesh, const BinGrid &outMesh, double radius, PumMembership &m,
-                        PumScratch &scratch, double *wsum, int *wcount, cudaStream_t s)
+                        PumScratch &scratch, double *wsum, int *wcount, const double *inXyz, const double *outXyz, DevBuf<double> &inRec,
+                        DevBuf<double4> &outRec, cudaStream_t s)
 {
   const double rOut = radius - kZeroDiff; // SphericalVertexCluster.hpp:155
   DevBuf<int>  nIn, nOut;
@@ -510,14 +534,27 @@ void pumBuildMembership(const double *dCenters, int64_t nClusters, const BinGrid
   m.sumTri = totals[2];
   m.inIds.alloc(std::max<int64_t>(m.sumIn, 1));
   m.outIds.alloc(std::max<int64_t>(m.sumOut, 1));
-  if (!over)
+  inRec.alloc(3 * std::max<int64_t>(m.sumIn, 1));
+  outRec.alloc(std::max<int64_t>(m.sumOut, 1));
+  if (!over) {
     memberPackKernel<<<warpGrid(nClusters), kBlockThreads, 0, s>>>(nClusters, m.nIn.p, m.nOut.p, reinterpret_cast<const long long *>(m.inOff.p),
-                                                                  reinterpret_cast<const long long *>(m.outOff.p), slotIn.p, slotOut.p, m.inIds.p, m.outIds.p);
-  else // clusters beyond the slot size: two-pass fill with the (exact) sizes counted above
+                                                                  reinterpret_cast<const long long *>(m.outOff.p), slotIn.p, slotOut.p, m.inIds.p, m.outIds.p,
+                                                                  dCenters, radius, inMesh.view(), outMesh.view(), wsum, wcount, inRec.p, outRec.p);
+    RBF_LAUNCHED();
+  } else { // clusters beyond the slot size: two-pass fill with the (exact) sizes counted above, then the records
     memberFillKernel<<<warpGrid(nClusters), kBlockThreads, 0, s>>>(dCenters, nClusters, inMesh.view(), outMesh.view(), radius, rOut,
                                                                   reinterpret_cast<const long long *>(m.inOff.p), reinterpret_cast<const long long *>(m.outOff.p),
                                                                   m.inIds.p, m.outIds.p);
-  RBF_LAUNCHED();
+    RBF_LAUNCHED();
+    PumSolveArgs a{};
+    a.radius = radius;
+    a.inXyz = inXyz, a.outXyz = outXyz, a.centers = dCenters;
+    a.nOut = m.nOut.p, a.outOff = reinterpret_cast<const long long *>(m.outOff.p);
+    a.inIds = m.inIds.p, a.outIds = m.outIds.p;
+    a.wsum = wsum, a.wcount = wcount;
+    pumBuildInRecords(a, m.sumIn, inRec.p, s);
+    pumBuildOutRecords(a, nClusters, outRec.p, s);
+  }
   RBF_CUDA(cudaGetLastError());
 }
 
@@ -533,9 +570,10 @@ __global__ void memberGatherPointsKernel(const double *__restrict__ centers, int
   if (c >= nClusters)
     return;
   const double cx = centers[3 * c], cy = centers[3 * c + 1], cz = centers[3 * c + 2];
-  const int    co = gatherToShared<true>(gpts, cx, cy, cz, radius, stage[w], lane, radius, 1.0 / radius, wsum, wcount);
+  __shared__ int stagePos[kWarpsPerBlock][kSlotCap];
+  const int      co = gatherToShared<true>(gpts, cx, cy, cz, radius, stage[w], stagePos[w], lane, radius, 1.0 / radius, wsum, wcount);
   if (co <= kSlotCap)
-    rankSortToGlobal(stage[w], co, slot + c * kSlotCap, lane);
+    rankSortToGlobal(stage[w], stage[w], co, slot + c * kSlotCap, lane); // payload = the point ID itself
   if (lane == 0) {
     nPts[c] = co;
     if (co > kSlotCap)
@@ -612,6 +650,27 @@ void pumBuildOutRecords(const PumSolveArgs &a, int64_t nClusters, double4 *rec, 
   if (nClusters <= 0)
     return;
   outRecordKernel<<<warpGrid(nClusters), kBlockThreads, 0, s>>>(a, nClusters, rec);
+  RBF_LAUNCHED();
+  RBF_CUDA(cudaGetLastError());
+}
+
+// ---- cluster-ordered in-vertex coordinates: one thread per CSR entry ----
+__global__ void inRecordKernel(const int *__restrict__ inIds, const double *__restrict__ inXyz, int64_t sumIn, double *__restrict__ rec)
+{
+  const int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (e >= sumIn)
+    return;
+  const double *p = inXyz + 3 * static_cast<long long>(inIds[e]);
+  rec[3 * e]      = p[0];
+  rec[3 * e + 1]  = p[1];
+  rec[3 * e + 2]  = p[2];
+}
+
+void pumBuildInRecords(const PumSolveArgs &a, int64_t sumIn, double *rec, cudaStream_t s)
+{
+  if (sumIn <= 0)
+    return;
+  inRecordKernel<<<divUp(sumIn, 256), 256, 0, s>>>(a.inIds, a.inXyz, sumIn, rec);
   RBF_LAUNCHED();
   RBF_CUDA(cudaGetLastError());
 }

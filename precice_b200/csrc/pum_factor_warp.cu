@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(32, NB <= 4 ? 20 : NB == 5 ? 16 : NB == 6 ? 14
   for (int i = lane; i < NMAX; i += 32) {
     double x = paddingCoordinate(i), y = 0.0, z = 0.0;
     if (i < n) {
-      const double *p = args.inXyz + 3 * static_cast<long long>(ids[i]);
+      const double *p = args.inRec + 3 * (en.inOff + i);
       x = p[0];
       y = p[1];
       z = p[2];

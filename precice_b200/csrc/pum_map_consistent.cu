@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(NT, NT == 32 ? 14 : 1) pumMapConsistentKernel(
   // ---- gather (SphericalVertexCluster.hpp:312-320) ----
   for (int i = tid; i < n; i += NT) {
     const long long id = ids[i];
-    const double   *p  = args.inXyz + 3 * id;
+    const double   *p  = args.inRec + 3 * (en.inOff + i); // cluster-ordered copy: contiguous
     vt[i * LDV]        = p[0];
     vt[i * LDV + 1]    = p[1];
     vt[i * LDV + 2]    = p[2];

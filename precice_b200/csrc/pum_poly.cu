@@ -179,7 +179,7 @@ __global__ void polySetupKernel(PumSolveArgs a, int64_t nClusters)
     for (int j = 0; j < 4; ++j)
       mc[i][j] = 0.0;
   for (int i = 0; i < n; ++i) {
-    const double *x    = a.inXyz + 3 * static_cast<long long>(ids[i]);
+    const double *x    = a.inRec + 3 * (a.inOff[c] + i);
     const double  q[4] = {1.0, x[0], x[1], x[2]};
     const double  qc[4] = {1.0, (x[0] - cx) * rinv, (x[1] - cy) * rinv, (x[2] - cz) * rinv};
 #pragma unroll
