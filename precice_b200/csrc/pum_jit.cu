@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(32, 16) pumEvaluateClusteredKernel(PumSolveArg
   const double    invR2 = rbf.p1 * rbf.p1;
   const int       polyMode = args.poly[c].mode, polyMask = args.poly[c].mask;
   for (int i = tid; i < n; i += 32) {
-    const double *p = args.inXyz + 3 * static_cast<long long>(ids[i]);
+    const double *p = args.inRec + 3 * (off + i); // cluster-ordered coordinates
     vt[i * LDV]     = p[0];
     vt[i * LDV + 1] = p[1];
     vt[i * LDV + 2] = p[2];

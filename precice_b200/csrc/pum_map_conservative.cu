@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(NT) pumMapConservativeKernel(PumSolveArgs args
       bulkLoad(ms, mg, static_cast<unsigned>(triPad) * 8u, &mbar);
   }
   for (int i = tid; i < n; i += NT) {
-    const double *p = args.inXyz + 3 * static_cast<long long>(ids[i]);
+    const double *p = args.inRec + 3 * (inOffC + i); // cluster-ordered coordinates
     vt[i * LDV]     = p[0];
     vt[i * LDV + 1] = p[1];
     vt[i * LDV + 2] = p[2];
@@ -72,13 +72,13 @@ __global__ void __launch_bounds__(NT) pumMapConservativeKernel(PumSolveArgs args
     const int o = o0 + tid;
     if (o < m) {
       const long long gid = oids[o];
-      const double   *p   = args.outXyz + 3 * gid;
-      const double    x = p[0], y = p[1], z = p[2];
+      const double4   rec = args.outRec[args.outOff[c] + o]; // x, y, z, normalised weight
+      const double    x = rec.x, y = rec.y, z = rec.z;
       ot[tid * LDV]     = x;
       ot[tid * LDV + 1] = y;
       ot[tid * LDV + 2] = z;
       // SphericalVertexCluster.hpp:219-227: in(i,c) = data * normalizedWeight
-      const double w = normalizedWeight(x, y, z, cx, cy, cz, rinv, args.wsum[gid], args.wcount[gid]);
+      const double w = rec.w;
       double       q[4];
       if (polyMode != 0)
         polyRow(polyMode, polyMask, x, y, z, cx, cy, cz, rinv, q);
