@@ -317,7 +317,7 @@ def main():
                     "frac": ach / fp64_peak if fp64_peak else None, "traffic": None, "peak_source": src,
                     "algorithmic_flops_per_launch": flops, "ms_per_launch": sec * 1e3, "share_of_step": ms_total / ev_ms}
 
-        r_factor = fp64_roofline("pumFactorKernel (per-cluster assembly of C + square-root-free Cholesky, all buckets)",
+        r_factor = fp64_roofline("pumFactorWarpKernel (per-cluster assembly of C + square-root-free Cholesky on DMMA, all buckets)",
                                  F_PHI * (stats["sum_n2"] + stats["sum_n"]) / 2.0 + stats["sum_n3"] / 3.0, asm_ms)
         r_map = fp64_roofline("pumMapConsistentKernel (gather + polynomial + solve + on-the-fly evaluation + blend, all buckets)",
                               2.0 * stats["sum_n2"] + (F_PHI + 2.0) * stats["sum_mn"], map_ms)
