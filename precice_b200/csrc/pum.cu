@@ -17,7 +17,7 @@ namespace rbfmap {
 namespace {
 
 __global__ void latticeKernel(const double *__restrict__ ax, const double *__restrict__ ay, const double *__restrict__ az, int nx, int ny, int nz,
-                              double *__restrict__ centers, int *__restrict__ tag)
+                              double *__restrict__ centers, int *__restrict__ tag, int tag0)
 {
   const long long total = static_cast<long long>(nx) * ny * nz;
   const long long id    = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -30,7 +30,7 @@ __global__ void latticeKernel(const double *__restrict__ ax, const double *__res
   centers[3 * id]     = ax[x];
   centers[3 * id + 1] = ay[y];
   centers[3 * id + 2] = az[z];
-  tag[id]             = 0;
+  tag[id]             = tag0; // one "still empty" bit per mesh that has to populate the cluster (tagEmptyLattice clears them)
 }
 
 class PumMapping final : public DeviceMapping {
@@ -391,7 +391,8 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
     }
     cl.centers.alloc(3 * cl.total);
     cl.tag.alloc(cl.total);
-    latticeKernel<<<divUp(cl.total, 256), 256, 0, _stream>>>(dAxis[0].p, dAxis[1].p, dAxis[2].p, nLocal[0], nLocal[1], nLocal[2], cl.centers.p, cl.tag.p);
+    latticeKernel<<<divUp(cl.total, 256), 256, 0, _stream>>>(dAxis[0].p, dAxis[1].p, dAxis[2].p, nLocal[0], nLocal[1], nLocal[2], cl.centers.p, cl.tag.p,
+                                                                   jit ? 1 : 3);
     RBF_LAUNCHED();
 
     trace.phase("lattice");
@@ -406,9 +407,16 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
     trace.phase("bin meshes");
 
     // :468-471
-    cl.tagEmpty(inGrid, _stream);
+    LatticeAxes axes{};
+    for (int d = 0; d < 3; ++d) {
+      axes.a[d]       = dAxis[d].p;
+      axes.n[d]       = static_cast<int>(nLocal[d]);
+      axes.start[d]   = d < dim ? start[d] : 0.0;
+      axes.invDist[d] = (d < dim && distances[d] > 0) ? 1.0 / distances[d] : 0.0;
+    }
+    cl.tagEmptyLattice(inGrid, axes, 1, _stream);
     if (!jit) // CreateClustering.hpp:469
-      cl.tagEmpty(outGrid, _stream);
+      cl.tagEmptyLattice(outGrid, axes, 2, _stream);
     trace.phase("tagEmpty x2");
     if (_cfg.project_to_input) { // :475-496
       cl.project(inGrid, _stream);

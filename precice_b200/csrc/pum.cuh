@@ -17,6 +17,13 @@ struct NeighbourOffsets {
 };
 
 // tentative centre lattice and its tags (impl/CreateClustering.hpp:411-496)
+// the tentative centre lattice (impl/CreateClustering.hpp:438-463): per-axis coordinate arrays on the device
+struct LatticeAxes {
+  const double *a[3];
+  int           n[3];
+  double        start[3], invDist[3];
+};
+
 struct PumClustering {
   int64_t        total  = 0;
   double         radius = 0.0;
@@ -24,6 +31,9 @@ struct PumClustering {
   DevBuf<int>    tag;     // 1 = tagged for removal
 
   void    tagEmpty(const BinGrid &mesh, cudaStream_t s);
+  // the same decision for centres that still sit on the lattice, taken from the vertex side: clears `bit` of tag[c] for
+  // every centre with a vertex of `mesh` inside its sphere (tag != 0 afterwards = tagged)
+  void    tagEmptyLattice(const BinGrid &mesh, const LatticeAxes &axes, int bit, cudaStream_t s);
   void    project(const BinGrid &inMesh, cudaStream_t s);
   void    tagDuplicates(const NeighbourOffsets &offs, double threshold, cudaStream_t s);
   int64_t compact(DevBuf<double> &out, cudaStream_t s); // returns the number of surviving centres

@@ -19,64 +19,138 @@ constexpr int kBlockThreads  = kWarpsPerBlock * 32;
 
 inline int warpGrid(int64_t nWarps) { return static_cast<int>(std::max<int64_t>(1, (nWarps + kWarpsPerBlock - 1) / kWarpsPerBlock)); }
 
-// ---- tagEmptyClusters: one warp per centre --------------------------------------------------
-__global__ void tagEmptyKernel(const double *__restrict__ centers, int *__restrict__ tag, int64_t total, BinGridView g, double radius)
+// Block-local compaction of the live (untagged) centres. On a surface mesh the tentative lattice is almost empty after
+// the first test (2M-vertex surface: 12.7M lattice centres, 2-3 % alive); one warp per lattice centre would spend its time
+// launching warps that read one tag and leave. Every block looks at kBlockThreads consecutive centres (one coalesced tag
+// load), packs the live ones into shared memory and its warps then walk that list: body(c, lane), all 32 lanes together.
+template <typename F>
+__device__ __forceinline__ void forLiveCentres(const int *__restrict__ tag, int64_t total, F &&body)
 {
-  const int64_t c    = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
-  const int     lane = threadIdx.x & 31;
-  if (c >= total || tag[c] != 0)
-    return;
-  const double cx = centers[3 * c], cy = centers[3 * c + 1], cz = centers[3 * c + 2];
-  bool         found = false;
-  forCandidatesWarp<2>(g, cx, cy, cz, lane, [&](int pos, bool valid) {
-    bool hit = false;
-    if (valid)
-      hit = __dsqrt_rn(sqDist3(cx, cy, cz, g.xyz[3 * pos], g.xyz[3 * pos + 1], g.xyz[3 * pos + 2])) < radius;
-    if (__any_sync(0xffffffffu, hit)) {
-      found = true;
-      return true;
-    }
-    return false;
-  });
-  if (!found && lane == 0)
-    tag[c] = 1;
+  __shared__ int live[kBlockThreads];
+  __shared__ int nLive;
+  const int64_t  base = blockIdx.x * static_cast<int64_t>(kBlockThreads);
+  const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0)
+    nLive = 0;
+  __syncthreads();
+  const int64_t  c     = base + threadIdx.x;
+  const bool     alive = c < total && tag[c] == 0;
+  const unsigned m     = __ballot_sync(0xffffffffu, alive);
+  int            slot  = 0;
+  if (lane == 0 && m != 0)
+    slot = atomicAdd(&nLive, __popc(m));
+  slot = __shfl_sync(0xffffffffu, slot, 0);
+  if (alive)
+    live[slot + __popc(m & ((1u << lane) - 1u))] = threadIdx.x;
+  __syncthreads();
+  const int n = nLive;
+  for (int i = warp; i < n; i += kWarpsPerBlock)
+    body(base + live[i], lane);
 }
 
-// ---- projectClusterCentersToinputMesh: one warp per centre ----------------------------------
-__global__ void projectKernel(double *__restrict__ centers, const int *__restrict__ tag, int64_t total, BinGridView g)
+// ---- tagEmptyClusters on arbitrary (projected) centres: one warp per live centre -------------
+__global__ void __launch_bounds__(kBlockThreads) tagEmptyKernel(const double *__restrict__ centers, int *__restrict__ tag, int64_t total, BinGridView g, double radius)
 {
-  const int64_t c    = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
-  const int     lane = threadIdx.x & 31;
-  if (c >= total || tag[c] != 0)
+  forLiveCentres(tag, total, [&](int64_t c, int lane) {
+    const double cx = centers[3 * c], cy = centers[3 * c + 1], cz = centers[3 * c + 2];
+    bool         found = false;
+    forCandidatesWarp<2>(g, cx, cy, cz, lane, [&](int pos, bool valid) {
+      bool hit = false;
+      if (valid)
+        hit = __dsqrt_rn(sqDist3(cx, cy, cz, g.xyz[3 * pos], g.xyz[3 * pos + 1], g.xyz[3 * pos + 2])) < radius;
+      if (__any_sync(0xffffffffu, hit)) {
+        found = true;
+        return true;
+      }
+      return false;
+    });
+    if (!found && lane == 0)
+      tag[c] = 1;
+  });
+}
+
+// ---- tagEmptyClusters on the regular lattice, from the vertex side ---------------------------
+// Before the projection the centres are lattice points (x_i, y_j, z_k), so "the sphere of centre c holds a vertex" is
+// decided from the vertices: every vertex clears the bit of the (2-3 per axis) lattice centres it is closer to than the
+// radius. Work is proportional to the mesh, not to the lattice. The distance test is the one of tagEmptyKernel on the
+// same operands (centre first), so the outcome is identical; the per-axis window is only a filter: |c_d - v_d| >= r
+// implies dist >= r because IEEE multiplication, addition and square root are monotone.
+__device__ __forceinline__ void latticeAxisRange(const double *__restrict__ ax, int n, double start, double invDist, double v, double radius, int &lo,
+                                                 int &hi)
+{
+  if (n == 1) {
+    lo = 0;
+    hi = 0;
+  } else {
+    const double t = (v - start) * invDist, rho = radius * invDist;
+    // the stored coordinates grow by repeated addition (a few ulp off start + i dist): one index of slack on each side
+    lo = static_cast<int>(fmin(fmax(floor(t - rho) - 1.0, 0.0), static_cast<double>(n)));
+    hi = static_cast<int>(fmin(fmax(ceil(t + rho) + 1.0, -1.0), static_cast<double>(n - 1)));
+  }
+  while (lo <= hi && !(fabs(__dsub_rn(ax[lo], v)) < radius))
+    ++lo;
+  while (hi >= lo && !(fabs(__dsub_rn(ax[hi], v)) < radius))
+    --hi;
+}
+
+__global__ void __launch_bounds__(256) markLatticeKernel(const double *__restrict__ xyz, int64_t n, LatticeAxes L, double radius, int *__restrict__ tag, int bit)
+{
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n)
     return;
-  const double cx = centers[3 * c], cy = centers[3 * c + 1], cz = centers[3 * c + 2];
-  double       best = 1.7976931348623157e308;
-  int          bestId = 0x7fffffff, bestPos = -1;
-  forCandidatesWarp<2>(g, cx, cy, cz, lane, [&](int pos, bool valid) {
-    if (valid) {
-      const double d2 = sqDist3(cx, cy, cz, g.xyz[3 * pos], g.xyz[3 * pos + 1], g.xyz[3 * pos + 2]);
-      const int    id = g.ids[pos];
-      if (d2 < best || (d2 == best && id < bestId)) {
-        best    = d2;
-        bestId  = id;
-        bestPos = pos;
+  const double vx = xyz[3 * i], vy = xyz[3 * i + 1], vz = xyz[3 * i + 2];
+  int          x0, x1, y0, y1, z0, z1;
+  latticeAxisRange(L.a[0], L.n[0], L.start[0], L.invDist[0], vx, radius, x0, x1);
+  latticeAxisRange(L.a[1], L.n[1], L.start[1], L.invDist[1], vy, radius, y0, y1);
+  latticeAxisRange(L.a[2], L.n[2], L.start[2], L.invDist[2], vz, radius, z0, z1);
+  for (int x = x0; x <= x1; ++x) {
+    const double cx = L.a[0][x];
+    for (int y = y0; y <= y1; ++y) {
+      const double cy = L.a[1][y];
+      for (int z = z0; z <= z1; ++z) {
+        if (__dsqrt_rn(sqDist3(cx, cy, L.a[2][z], vx, vy, vz)) < radius) {
+          const int64_t id = (static_cast<int64_t>(x) * L.n[1] + y) * L.n[2] + z; // impl/CreateClustering.hpp:36-45
+          if (tag[id] & bit)
+            atomicAnd(&tag[id], ~bit);
+        }
       }
     }
-    return false;
-  });
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-    const int    oi = __shfl_xor_sync(0xffffffffu, bestId, o);
-    const int    op = __shfl_xor_sync(0xffffffffu, bestPos, o);
-    if (ob < best || (ob == best && oi < bestId)) {
-      best    = ob;
-      bestId  = oi;
-      bestPos = op;
-    }
   }
-  if (lane < 3 && bestPos >= 0)
-    centers[3 * c + lane] = g.xyz[3 * bestPos + lane];
+}
+
+// ---- projectClusterCentersToinputMesh: one warp per live centre ------------------------------
+__global__ void __launch_bounds__(kBlockThreads) projectKernel(double *__restrict__ centers, const int *__restrict__ tag, int64_t total, BinGridView g)
+{
+  forLiveCentres(tag, total, [&](int64_t c, int lane) {
+    const double cx = centers[3 * c], cy = centers[3 * c + 1], cz = centers[3 * c + 2];
+    double       best = 1.7976931348623157e308;
+    int          bestId = 0x7fffffff, bestPos = -1;
+    forCandidatesWarp<2>(g, cx, cy, cz, lane, [&](int pos, bool valid) {
+      if (valid) {
+        const double d2 = sqDist3(cx, cy, cz, g.xyz[3 * pos], g.xyz[3 * pos + 1], g.xyz[3 * pos + 2]);
+        const int    id = g.ids[pos];
+        if (d2 < best || (d2 == best && id < bestId)) {
+          best    = d2;
+          bestId  = id;
+          bestPos = pos;
+        }
+      }
+      return false;
+    });
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int    oi = __shfl_xor_sync(0xffffffffu, bestId, o);
+      const int    op = __shfl_xor_sync(0xffffffffu, bestPos, o);
+      if (ob < best || (ob == best && oi < bestId)) {
+        best    = ob;
+        bestId  = oi;
+        bestPos = op;
+      }
+    }
+    if (lane < 3 && bestPos >= 0)
+      centers[3 * c + lane] = g.xyz[3 * bestPos + lane];
+  });
 }
 
 // ---- tagDuplicateCenters ---------------------------------------------------------------------
@@ -437,13 +511,21 @@ __global__ void bucketScatterKernel(const int *__restrict__ nIn, const int *__re
 // =============================================================================================
 void PumClustering::tagEmpty(const BinGrid &mesh, cudaStream_t s)
 {
-  tagEmptyKernel<<<warpGrid(total), kBlockThreads, 0, s>>>(centers.p, tag.p, total, mesh.view(), radius);
+  tagEmptyKernel<<<divUp(total, kBlockThreads), kBlockThreads, 0, s>>>(centers.p, tag.p, total, mesh.view(), radius);
+  RBF_LAUNCHED();
+}
+
+void PumClustering::tagEmptyLattice(const BinGrid &mesh, const LatticeAxes &axes, int bit, cudaStream_t s)
+{
+  if (mesh.n == 0)
+    return; // every centre keeps its bit = tagged
+  markLatticeKernel<<<divUp(mesh.n, 256), 256, 0, s>>>(mesh.xyz.p, mesh.n, axes, radius, tag.p, bit);
   RBF_LAUNCHED();
 }
 
 void PumClustering::project(const BinGrid &inMesh, cudaStream_t s)
 {
-  projectKernel<<<warpGrid(total), kBlockThreads, 0, s>>>(centers.p, tag.p, total, inMesh.view());
+  projectKernel<<<divUp(total, kBlockThreads), kBlockThreads, 0, s>>>(centers.p, tag.p, total, inMesh.view());
   RBF_LAUNCHED();
 }
 

@@ -1,0 +1,130 @@
+"""BASELINE.json configs[4]: rbf-pum-direct with remeshing — repeated computeMapping on a perturbed 3-D SURFACE mesh
+(default 2M -> 2M vertices per GPU, compact-polynomial-c6, polynomial separate, vertices-per-cluster 50).
+
+The surface is the graph z = 0.5 + A(t) sin(2 pi x) cos(2 pi y) over the unit square, sampled at Halton points
+((2,3) for the in-mesh, (7,11) for the out-mesh). Every remeshing step moves the surface (A(t) changes) and shifts the
+vertices tangentially by a fraction of the mesh width, then runs what ParticipantImpl does after a mesh change:
+Mapping::clear() + computeMapping() + map() of one scalar field (precice/impl/ParticipantImpl.cpp, reinitialisation
+path). The local clusters are thin plates: most of them go through the cond(Q) > 1e5 axis-drop rule of
+RadialBasisFctSolver.hpp:383-402 or keep an ill-conditioned but full linear polynomial.
+
+Device-resident (CUDA events of the library) and host-pointer (perf_counter around the C ABI, PCIe included) figures;
+parity of the device path against the CPU oracle on a smaller surface sample. Multi-GPU: torchrun, one surface patch
+per rank (weak scaling, no data-path collective).
+"""
+import argparse, json, math, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import torch
+import bench
+import precice_b200 as pb
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--vertices", dest="n", type=int, default=2_000_000)
+ap.add_argument("--steps", type=int, default=6)
+ap.add_argument("--warmup", type=int, default=3)
+ap.add_argument("--oracle-sample", type=int, default=20000)
+ap.add_argument("--out", default=None)
+a = ap.parse_args()
+
+rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local_rank)
+dev = torch.device("cuda", local_rank)
+if world > 1:
+    import torch.distributed as dist
+    sys.stdout.flush(); saved = os.dup(1); os.dup2(2, 1)
+    dist.init_process_group("nccl", device_id=dev)
+    os.dup2(saved, 1)
+
+
+def surface(uv, t, n):
+    """uv: (N,3) Halton points (third column unused) -> surface vertices at remeshing step t."""
+    h = 1.0 / math.sqrt(n)  # mesh width
+    x = uv[:, 0] + 0.3 * h * math.sin(0.7 * t) * torch.cos(2 * math.pi * uv[:, 1])
+    y = uv[:, 1] + 0.3 * h * math.cos(0.9 * t) * torch.sin(2 * math.pi * uv[:, 0])
+    z = 0.5 + (0.15 + 0.02 * math.sin(0.5 * t)) * torch.sin(2 * math.pi * x) * torch.cos(2 * math.pi * y)
+    return torch.stack([x, y, z], dim=1).contiguous()
+
+
+def field(xyz):
+    # not in the span of [1, x, y, z] on the surface (bench.field_torch would be: it is linear in z there)
+    return torch.sin(3 * math.pi * xyz[:, 0]) * torch.cos(2 * math.pi * xyz[:, 1]) + torch.exp(xyz[:, 2])
+
+
+def support_radius_surface(n):
+    # cluster radius of a surface of area ~1.2 with VPC vertices per disc; support = 2 x cluster radius (as in bench.py)
+    return 2.0 * math.sqrt(1.2 * bench.VPC / (math.pi * n))
+
+
+def run(n, steps, warmup, device):
+    uv_in = bench.halton_torch(n, (2, 3, 5), 1 + rank * n, device)
+    uv_out = bench.halton_torch(n, (7, 11, 13), 1 + rank * n, device)
+    m = pb.PartitionOfUnityMapping("consistent", 3, bench.BASIS, support_radius_surface(n), "separate", bench.VPC, bench.OVERLAP, True,
+                                   device_id=local_rank)
+    res = torch.empty(n, dtype=torch.float64, device=device)
+    ev, comp, mp, asm = [], [], [], []
+    for s in range(warmup + steps):
+        xin, xout = surface(uv_in, float(s), n), surface(uv_out, float(s), n)
+        vals = field(xin).contiguous()
+        torch.cuda.synchronize()
+        if m.hasComputedMapping():
+            m.clear()
+        m.computeMapping(xin, xout)
+        m.map(vals, 1, out=res)
+        st = m.stats()
+        if s >= warmup:
+            ev.append(st["ms_compute_kernels"] + st["ms_map_kernels"]); comp.append(st["ms_compute_kernels"])
+            mp.append(st["ms_map_kernels"]); asm.append(st["ms_assembly_factor"])
+    exact = field(xout)
+    err = float(torch.linalg.norm(res - exact) / torch.linalg.norm(exact))
+    # host-pointer path: pinned buffers, H2D + D2H inside the timed region
+    hin, hout, hv = xin.cpu().pin_memory(), xout.cpu().pin_memory(), vals.cpu().pin_memory()
+    hres = torch.empty(n, dtype=torch.float64).pin_memory()
+    e2e = []
+    for s in range(2 + steps):
+        t0 = time.perf_counter()
+        m.clear(); m.computeMapping(hin, hout); m.map(hv, 1, out=hres)
+        if s >= 2:
+            e2e.append((time.perf_counter() - t0) * 1e3)
+    return m, st, ev, comp, mp, asm, e2e, err
+
+
+m, st, ev, comp, mp, asm, e2e, err = run(a.n, a.steps, a.warmup, dev)
+t = torch.tensor([sum(ev) / len(ev), sum(e2e) / len(e2e), sum(comp) / len(comp), sum(mp) / len(mp), sum(asm) / len(asm)],
+                 dtype=torch.float64, device=dev)
+if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+ms_dev, ms_e2e, ms_comp, ms_map, ms_asm = (float(x) for x in t.tolist())
+if rank == 0:
+    line = {"workload": f"rbf-pum-direct compact-polynomial-c6, remeshing: perturbed 3-D surface z = f(x, y), {a.n}->{a.n} vertices per GPU, "
+                        f"clear + computeMapping + map (scalar) per step",
+            "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step_device": ms_dev, "ms_compute_mapping": ms_comp, "ms_assembly_factor": ms_asm, "ms_map": ms_map,
+            "vertices_per_s_device": world * a.n / (ms_dev * 1e-3),
+            "ms_per_step_host_pointers": ms_e2e, "vertices_per_s_e2e": world * a.n / (ms_e2e * 1e-3),
+            "interpolation_error_rel_l2": err,
+            "mapping": {k: st[k] for k in ("n_clusters", "cluster_radius", "sum_n", "sum_m", "max_n", "device_bytes")}}
+    # parity against the CPU oracle on a smaller surface
+    if a.oracle_sample > 0:
+        import oracle as orc
+        ns = a.oracle_sample
+        sin_ = surface(bench.halton_torch(ns, (2, 3, 5), 1, "cpu"), 1.0, ns).numpy()
+        sout = surface(bench.halton_torch(ns, (7, 11, 13), 1, "cpu"), 1.0, ns).numpy()
+        sv = field(torch.from_numpy(sin_)).numpy()
+        sup = support_radius_surface(ns)
+        g = pb.PartitionOfUnityMapping("consistent", 3, bench.BASIS, sup, "separate", bench.VPC, bench.OVERLAP, True, device_id=local_rank)
+        o = orc.PumMapping("consistent", 3, bench.BASIS, sup, "separate", bench.VPC, bench.OVERLAP, True)
+        g.computeMapping(sin_, sout); rg = g.map(sv, 1)
+        t0 = time.perf_counter(); o.compute_mapping(sin_, sout, threads=os.cpu_count() or 1); ro = o.map(sv, 1, threads=os.cpu_count() or 1)
+        t1 = time.perf_counter()
+        line["parity"] = {"sample_vertices": ns, "rel_l2_gpu_vs_oracle": float(np.linalg.norm(rg - ro) / np.linalg.norm(ro)),
+                          "clusters_gpu": g.stats()["n_clusters"], "clusters_oracle": o.num_clusters,
+                          "oracle_vertices_per_s": ns / (t1 - t0), "oracle_threads": os.cpu_count()}
+    s = json.dumps(line)
+    print(s, flush=True)
+    if a.out:
+        open(a.out, "w").write(s + "\n")
+if world > 1:
+    dist.destroy_process_group()
