@@ -93,7 +93,7 @@ __device__ __forceinline__ void latticeAxisRange(const double *__restrict__ ax, 
     --hi;
 }
 
-__global__ void __launch_bounds__(256) markLatticeKernel(const double *__restrict__ xyz, int64_t n, LatticeAxes L, double radius, int *__restrict__ tag, int bit)
+__global__ void __launch_bounds__(256) markLatticeKernel(const double *__restrict__ xyz, int64_t n, LatticeAxes L, double radius, int *tag, int bit)
 {
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i >= n)
@@ -108,11 +108,10 @@ __global__ void __launch_bounds__(256) markLatticeKernel(const double *__restric
     for (int y = y0; y <= y1; ++y) {
       const double cy = L.a[1][y];
       for (int z = z0; z <= z1; ++z) {
-        if (__dsqrt_rn(sqDist3(cx, cy, L.a[2][z], vx, vy, vz)) < radius) {
-          const int64_t id = (static_cast<int64_t>(x) * L.n[1] + y) * L.n[2] + z; // impl/CreateClustering.hpp:36-45
-          if (tag[id] & bit)
-            atomicAnd(&tag[id], ~bit);
-        }
+        const int64_t id = (static_cast<int64_t>(x) * L.n[1] + y) * L.n[2] + z; // impl/CreateClustering.hpp:36-45
+        // most centres have long been cleared by another vertex (a stale read only costs a redundant test)
+        if ((tag[id] & bit) && __dsqrt_rn(sqDist3(cx, cy, L.a[2][z], vx, vy, vz)) < radius)
+          atomicAnd(&tag[id], ~bit);
       }
     }
   }
