@@ -16,23 +16,6 @@
 namespace rbfmap {
 namespace {
 
-__global__ void latticeKernel(const double *__restrict__ ax, const double *__restrict__ ay, const double *__restrict__ az, int nx, int ny, int nz,
-                              double *__restrict__ centers, int *__restrict__ tag, int tag0)
-{
-  const long long total = static_cast<long long>(nx) * ny * nz;
-  const long long id    = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (id >= total)
-    return;
-  // linear index (x * ny + y) * nz + z  (impl/CreateClustering.hpp:36-45)
-  const int z = static_cast<int>(id % nz);
-  const int y = static_cast<int>((id / nz) % ny);
-  const int x = static_cast<int>(id / (static_cast<long long>(nz) * ny));
-  centers[3 * id]     = ax[x];
-  centers[3 * id + 1] = ay[y];
-  centers[3 * id + 2] = az[z];
-  tag[id]             = tag0; // one "still empty" bit per mesh that has to populate the cluster (tagEmptyLattice clears them)
-}
-
 class PumMapping final : public DeviceMapping {
 public:
   explicit PumMapping(const rbfmap_config &cfg)
@@ -372,7 +355,6 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
     if (totalD > 1.0e9)
       throw MapError(RBFMAP_ERR_UNSUPPORTED, "rbf-pum-direct: the tentative cluster lattice is too large.");
     PumClustering cl;
-    cl.total  = static_cast<int64_t>(totalD);
     cl.radius = _radius;
     // :438-463 — coordinates grow by repeated addition, exactly like the reference loops
     std::vector<double> axis[3];
@@ -385,16 +367,18 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
       }
     }
     DevBuf<double> dAxis[3];
+    LatticeAxes    axes{};
     for (int d = 0; d < 3; ++d) {
       dAxis[d].alloc(axis[d].size());
       RBF_CUDA(cudaMemcpyAsync(dAxis[d].p, axis[d].data(), axis[d].size() * sizeof(double), cudaMemcpyHostToDevice, _stream));
+      axes.a[d]       = dAxis[d].p;
+      axes.n[d]       = static_cast<int>(nLocal[d]);
+      axes.start[d]   = d < dim ? start[d] : 0.0;
+      axes.invDist[d] = (d < dim && distances[d] > 0) ? 1.0 / distances[d] : 0.0;
     }
-    cl.centers.alloc(3 * cl.total);
-    cl.tag.alloc(cl.total);
-    latticeKernel<<<divUp(cl.total, 256), 256, 0, _stream>>>(dAxis[0].p, dAxis[1].p, dAxis[2].p, nLocal[0], nLocal[1], nLocal[2], cl.centers.p, cl.tag.p,
-                                                                   jit ? 1 : 3);
-    RBF_LAUNCHED();
-
+    // the lattice itself is never materialised: one tag per centre, one "still empty" bit per mesh that has to
+    // populate the cluster (tagEmptyLattice clears them); coordinates only for the centres that survive
+    cl.initLattice(axes, jit ? 1 : 3, _stream);
     trace.phase("lattice");
     inGrid.build(_inXyz.p, _nIn, bbMin, bbMax, 0.5 * _radius, _stream); // half-radius cells, 5x5x5 neighbourhoods (forCandidatesWarp<2>)
     waitForOutMesh();
@@ -407,17 +391,11 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
     trace.phase("bin meshes");
 
     // :468-471
-    LatticeAxes axes{};
-    for (int d = 0; d < 3; ++d) {
-      axes.a[d]       = dAxis[d].p;
-      axes.n[d]       = static_cast<int>(nLocal[d]);
-      axes.start[d]   = d < dim ? start[d] : 0.0;
-      axes.invDist[d] = (d < dim && distances[d] > 0) ? 1.0 / distances[d] : 0.0;
-    }
-    cl.tagEmptyLattice(inGrid, axes, 1, _stream);
+    cl.tagEmptyLattice(inGrid, 1, _stream);
     if (!jit) // CreateClustering.hpp:469
-      cl.tagEmptyLattice(outGrid, axes, 2, _stream);
-    trace.phase("tagEmpty x2");
+      cl.tagEmptyLattice(outGrid, 2, _stream);
+    cl.gatherLive(_stream);
+    trace.phase("tagEmpty x2 + live list");
     if (_cfg.project_to_input) { // :475-496
       cl.project(inGrid, _stream);
       trace.phase("project");

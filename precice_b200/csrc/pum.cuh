@@ -25,15 +25,23 @@ struct LatticeAxes {
 };
 
 struct PumClustering {
-  int64_t        total  = 0;
+  int64_t        total  = 0; // lattice size
   double         radius = 0.0;
-  DevBuf<double> centers; // total x 3
-  DevBuf<int>    tag;     // 1 = tagged for removal
+  LatticeAxes    axes{};
+  DevBuf<int>    tag; // per lattice centre: != 0 = empty with respect to one of the meshes (tagEmptyLattice)
+  DevBuf<int>    pos; // exclusive scan of (tag == 0): lattice index -> index in the live list
+  // the live list: centres that passed the two emptiness tests (CreateClustering.hpp:468-471), ascending lattice index
+  int64_t        nLive = 0;
+  DevBuf<int>    liveIds; // lattice index
+  DevBuf<double> centers; // nLive x 3
+  DevBuf<int>    liveTag; // 1 = tagged for removal (duplicates, empty after the projection)
 
-  void    tagEmpty(const BinGrid &mesh, cudaStream_t s);
-  // the same decision for centres that still sit on the lattice, taken from the vertex side: clears `bit` of tag[c] for
-  // every centre with a vertex of `mesh` inside its sphere (tag != 0 afterwards = tagged)
-  void    tagEmptyLattice(const BinGrid &mesh, const LatticeAxes &axes, int bit, cudaStream_t s);
+  void    initLattice(const LatticeAxes &axes, int tag0, cudaStream_t s);
+  // tagEmptyClusters for centres on the lattice, from the vertex side: clears `bit` of tag[c] for every centre with a
+  // vertex of `mesh` inside its sphere
+  void    tagEmptyLattice(const BinGrid &mesh, int bit, cudaStream_t s);
+  int64_t gatherLive(cudaStream_t s); // builds the live list, returns its length
+  void    tagEmpty(const BinGrid &mesh, cudaStream_t s); // live list, arbitrary (projected) centres
   void    project(const BinGrid &inMesh, cudaStream_t s);
   void    tagDuplicates(const NeighbourOffsets &offs, double threshold, cudaStream_t s);
   int64_t compact(DevBuf<double> &out, cudaStream_t s); // returns the number of surviving centres

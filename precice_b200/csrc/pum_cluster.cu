@@ -152,31 +152,57 @@ __global__ void __launch_bounds__(kBlockThreads) projectKernel(double *__restric
   });
 }
 
-// ---- tagDuplicateCenters ---------------------------------------------------------------------
-// state: 0 = untagged (final), 1 = tagged (final), 2 = undecided
-__global__ void dupInitKernel(const double *__restrict__ centers, const int *__restrict__ tag, int64_t total, NeighbourOffsets offs, double thr2,
-                              int *__restrict__ state, unsigned *__restrict__ lowMask)
+// ---- live list: the lattice centres that survive the two emptiness tests ----------------------
+// Everything after tagEmptyLattice works on this list (ascending lattice index = the reference's visiting order); the
+// full lattice only keeps its tag and the exclusive scan `pos` (lattice index -> list index) for neighbour look-ups.
+__global__ void fillIntKernel(int *__restrict__ p, int64_t n, int v)
 {
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  if (i >= total)
+  if (i < n)
+    p[i] = v;
+}
+
+__global__ void liveListKernel(int64_t total, const int *__restrict__ tag, const int *__restrict__ pos, LatticeAxes L, int *__restrict__ liveIds,
+                               double *__restrict__ centers, int *__restrict__ liveTag)
+{
+  const int64_t id = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (id >= total || tag[id] != 0)
     return;
-  if (tag[i] != 0) {
-    state[i]   = 1;
-    lowMask[i] = 0;
+  // linear index (x * ny + y) * nz + z  (impl/CreateClustering.hpp:36-45)
+  const int     z = static_cast<int>(id % L.n[2]);
+  const int     y = static_cast<int>((id / L.n[2]) % L.n[1]);
+  const int     x = static_cast<int>(id / (static_cast<int64_t>(L.n[2]) * L.n[1]));
+  const int64_t o = pos[id];
+  liveIds[o]         = static_cast<int>(id);
+  centers[3 * o]     = L.a[0][x];
+  centers[3 * o + 1] = L.a[1][y];
+  centers[3 * o + 2] = L.a[2][z];
+  liveTag[o]         = 0;
+}
+
+// ---- tagDuplicateCenters ---------------------------------------------------------------------
+// state: 0 = untagged (final), 1 = tagged (final), 2 = undecided
+__global__ void dupInitKernel(const double *__restrict__ centers, const int *__restrict__ liveIds, int64_t nLive, const int *__restrict__ tag,
+                              const int *__restrict__ pos, int64_t total, NeighbourOffsets offs, double thr2, int *__restrict__ state,
+                              unsigned *__restrict__ lowMask)
+{
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= nLive)
     return;
-  }
-  const double cx = centers[3 * i], cy = centers[3 * i + 1], cz = centers[3 * i + 2];
-  bool         higher = false;
-  unsigned     low    = 0;
+  const long long id = liveIds[i];
+  const double    cx = centers[3 * i], cy = centers[3 * i + 1], cz = centers[3 * i + 2];
+  bool            higher = false;
+  unsigned        low    = 0;
   for (int k = 0; k < offs.n; ++k) {
     const long long off = offs.off[k];
     if (off == 0)
       continue; // CreateClustering.hpp:103-105
-    const long long nb = i + off;
+    const long long nb = id + off;
     if (nb < 0 || nb >= total || tag[nb] != 0)
       continue;
-    if (sqDist3(cx, cy, cz, centers[3 * nb], centers[3 * nb + 1], centers[3 * nb + 2]) < thr2) {
-      if (nb > i)
+    const long long j = pos[nb];
+    if (sqDist3(cx, cy, cz, centers[3 * j], centers[3 * j + 1], centers[3 * j + 2]) < thr2) {
+      if (nb > id)
         higher = true;
       else
         low |= (1u << k);
@@ -188,16 +214,18 @@ __global__ void dupInitKernel(const double *__restrict__ centers, const int *__r
   lowMask[i] = low;
 }
 
-__global__ void dupResolveKernel(int64_t total, NeighbourOffsets offs, int *__restrict__ state, const unsigned *__restrict__ lowMask, int *__restrict__ undecided)
+__global__ void dupResolveKernel(int64_t nLive, const int *__restrict__ liveIds, const int *__restrict__ pos, NeighbourOffsets offs, int *__restrict__ state,
+                                 const unsigned *__restrict__ lowMask, int *__restrict__ undecided)
 {
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  if (i >= total || state[i] != 2)
+  if (i >= nLive || state[i] != 2)
     return;
-  const unsigned low = lowMask[i];
-  bool           anyUntagged = false, anyUndecided = false;
+  const unsigned  low = lowMask[i];
+  const long long id  = liveIds[i];
+  bool            anyUntagged = false, anyUndecided = false;
   for (int k = 0; k < offs.n; ++k)
-    if (low & (1u << k)) {
-      const int s = reinterpret_cast<volatile int *>(state)[i + offs.off[k]];
+    if (low & (1u << k)) { // bit k set: that neighbour is live, pos[] is its list index
+      const int s = reinterpret_cast<volatile int *>(state)[pos[id + offs.off[k]]];
       anyUntagged |= (s == 0);
       anyUndecided |= (s == 2);
     }
@@ -508,13 +536,17 @@ __global__ void bucketScatterKernel(const int *__restrict__ nIn, const int *__re
 } // namespace
 
 // =============================================================================================
-void PumClustering::tagEmpty(const BinGrid &mesh, cudaStream_t s)
+void PumClustering::initLattice(const LatticeAxes &ax, int tag0, cudaStream_t s)
 {
-  tagEmptyKernel<<<divUp(total, kBlockThreads), kBlockThreads, 0, s>>>(centers.p, tag.p, total, mesh.view(), radius);
+  axes  = ax;
+  total = static_cast<int64_t>(ax.n[0]) * ax.n[1] * ax.n[2];
+  nLive = 0;
+  tag.alloc(total);
+  fillIntKernel<<<divUp(total, 256), 256, 0, s>>>(tag.p, total, tag0);
   RBF_LAUNCHED();
 }
 
-void PumClustering::tagEmptyLattice(const BinGrid &mesh, const LatticeAxes &axes, int bit, cudaStream_t s)
+void PumClustering::tagEmptyLattice(const BinGrid &mesh, int bit, cudaStream_t s)
 {
   if (mesh.n == 0)
     return; // every centre keeps its bit = tagged
@@ -522,40 +554,9 @@ void PumClustering::tagEmptyLattice(const BinGrid &mesh, const LatticeAxes &axes
   RBF_LAUNCHED();
 }
 
-void PumClustering::project(const BinGrid &inMesh, cudaStream_t s)
+int64_t PumClustering::gatherLive(cudaStream_t s)
 {
-  projectKernel<<<divUp(total, kBlockThreads), kBlockThreads, 0, s>>>(centers.p, tag.p, total, inMesh.view());
-  RBF_LAUNCHED();
-}
-
-void PumClustering::tagDuplicates(const NeighbourOffsets &offs, double threshold, cudaStream_t s)
-{
-  DevBuf<int>      state, undecided;
-  DevBuf<unsigned> low;
-  state.alloc(total);
-  low.alloc(total);
-  undecided.alloc(1);
-  const int grid = divUp(total, 256);
-  // CreateClustering.hpp:112: squared distance < pow_int<2>(radius)
-  dupInitKernel<<<grid, 256, 0, s>>>(centers.p, tag.p, total, offs, threshold * threshold, state.p, low.p);
-  RBF_LAUNCHED();
-  for (int64_t it = 0; it <= total; ++it) {
-    RBF_CUDA(cudaMemsetAsync(undecided.p, 0, sizeof(int), s));
-    dupResolveKernel<<<grid, 256, 0, s>>>(total, offs, state.p, low.p, undecided.p);
-    RBF_LAUNCHED();
-    int left = 0;
-    RBF_CUDA(cudaMemcpyAsync(&left, undecided.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-    RBF_CUDA(cudaStreamSynchronize(s));
-    if (left == 0)
-      break;
-  }
-  stateToTagKernel<<<grid, 256, 0, s>>>(total, state.p, tag.p);
-  RBF_LAUNCHED();
-}
-
-int64_t PumClustering::compact(DevBuf<double> &out, cudaStream_t s)
-{
-  DevBuf<int> keep, pos;
+  DevBuf<int> keep;
   keep.alloc(total);
   pos.alloc(total + 1);
   const int grid = divUp(total, 256);
@@ -565,9 +566,79 @@ int64_t PumClustering::compact(DevBuf<double> &out, cudaStream_t s)
   int count = 0;
   RBF_CUDA(cudaMemcpyAsync(&count, pos.p + total, sizeof(int), cudaMemcpyDeviceToHost, s));
   RBF_CUDA(cudaStreamSynchronize(s));
+  nLive = count;
+  liveIds.alloc(std::max(count, 1));
+  liveTag.alloc(std::max(count, 1));
+  centers.alloc(3 * static_cast<size_t>(std::max(count, 1)));
+  if (count > 0) {
+    liveListKernel<<<grid, 256, 0, s>>>(total, tag.p, pos.p, axes, liveIds.p, centers.p, liveTag.p);
+    RBF_LAUNCHED();
+  }
+  return nLive;
+}
+
+void PumClustering::tagEmpty(const BinGrid &mesh, cudaStream_t s)
+{
+  if (nLive == 0)
+    return;
+  tagEmptyKernel<<<divUp(nLive, kBlockThreads), kBlockThreads, 0, s>>>(centers.p, liveTag.p, nLive, mesh.view(), radius);
+  RBF_LAUNCHED();
+}
+
+void PumClustering::project(const BinGrid &inMesh, cudaStream_t s)
+{
+  if (nLive == 0)
+    return;
+  projectKernel<<<divUp(nLive, kBlockThreads), kBlockThreads, 0, s>>>(centers.p, liveTag.p, nLive, inMesh.view());
+  RBF_LAUNCHED();
+}
+
+void PumClustering::tagDuplicates(const NeighbourOffsets &offs, double threshold, cudaStream_t s)
+{
+  if (nLive == 0)
+    return;
+  DevBuf<int>      state, undecided;
+  DevBuf<unsigned> low;
+  state.alloc(nLive);
+  low.alloc(nLive);
+  undecided.alloc(1);
+  const int grid = divUp(nLive, 256);
+  // CreateClustering.hpp:112: squared distance < pow_int<2>(radius)
+  dupInitKernel<<<grid, 256, 0, s>>>(centers.p, liveIds.p, nLive, tag.p, pos.p, total, offs, threshold * threshold, state.p, low.p);
+  RBF_LAUNCHED();
+  for (int64_t it = 0; it <= nLive; ++it) {
+    RBF_CUDA(cudaMemsetAsync(undecided.p, 0, sizeof(int), s));
+    dupResolveKernel<<<grid, 256, 0, s>>>(nLive, liveIds.p, pos.p, offs, state.p, low.p, undecided.p);
+    RBF_LAUNCHED();
+    int left = 0;
+    RBF_CUDA(cudaMemcpyAsync(&left, undecided.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    RBF_CUDA(cudaStreamSynchronize(s));
+    if (left == 0)
+      break;
+  }
+  stateToTagKernel<<<grid, 256, 0, s>>>(nLive, state.p, liveTag.p);
+  RBF_LAUNCHED();
+}
+
+int64_t PumClustering::compact(DevBuf<double> &out, cudaStream_t s)
+{
+  if (nLive == 0) {
+    out.alloc(3);
+    return 0;
+  }
+  DevBuf<int> keep, opos;
+  keep.alloc(nLive);
+  opos.alloc(nLive + 1);
+  const int grid = divUp(nLive, 256);
+  keepFlagKernel<<<grid, 256, 0, s>>>(nLive, liveTag.p, keep.p);
+  RBF_LAUNCHED();
+  exclusiveScan(keep.p, opos.p, nLive, s);
+  int count = 0;
+  RBF_CUDA(cudaMemcpyAsync(&count, opos.p + nLive, sizeof(int), cudaMemcpyDeviceToHost, s));
+  RBF_CUDA(cudaStreamSynchronize(s));
   out.alloc(3 * static_cast<size_t>(std::max(count, 1)));
   if (count > 0) {
-    compactKernel<<<grid, 256, 0, s>>>(total, tag.p, pos.p, centers.p, out.p);
+    compactKernel<<<grid, 256, 0, s>>>(nLive, liveTag.p, opos.p, centers.p, out.p);
     RBF_LAUNCHED();
   }
   return count;
