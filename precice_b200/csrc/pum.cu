@@ -101,7 +101,6 @@ public:
     _outXyz.release();
     _centers.release();
     _mem = PumMembership();
-    _mat.release();
     _poly.release();
     _wsum.release();
     _outRec.release();
@@ -146,7 +145,8 @@ private:
   DevBuf<double>  _centers;
   PumMembership   _mem;
   PumScratch      _scratch; // survives clear(), see pum.cuh
-  DevBuf<double>  _mat;
+  ScratchBuf<double> _mat; // packed factors: grow-only, survives clear() like _scratch (a remeshing step changes its size every
+                           // time; through the stream-ordered pool that cost 0.8 - 4 ms per step for a 2 GB buffer)
   DevBuf<PolyRec> _poly;
   DevBuf<double>  _wsum;
   DevBuf<double4> _outRec;
@@ -242,8 +242,13 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
     throw MapError(RBFMAP_ERR_UNSUPPORTED, "mesh too large for 32-bit vertex IDs");
   _inXyz.alloc(3 * std::max<int64_t>(_nIn, 1));
   _outXyz.alloc(3 * std::max<int64_t>(_nOut, 1));
-  if (_nIn > 0)
-    RBF_CUDA(cudaMemcpyAsync(_inXyz.p, srcIn, 3 * _nIn * sizeof(double), kind, _stream));
+  trace.phase("alloc meshes");
+  if (_nIn > 0) {
+    if (kind == cudaMemcpyDeviceToDevice)
+      deviceCopy(_inXyz.p, srcIn, 3 * _nIn, _stream);
+    else
+      RBF_CUDA(cudaMemcpyAsync(_inXyz.p, srcIn, 3 * _nIn * sizeof(double), kind, _stream));
+  }
   // From host memory the outMesh travels on a second stream: bounds, cluster-radius estimate and binning of the inMesh
   // run while it is still in flight; the main stream waits for it (waitForOutMesh) right before its first use.
   struct PendingCopy { // the host buffer must not be in use any more when this call returns, however it returns
@@ -268,6 +273,8 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
       RBF_CUDA(cudaEventRecord(_outReady, _copyStream));
       outCopy.s       = _copyStream;
       outCopy.pending = true;
+    } else if (kind == cudaMemcpyDeviceToDevice) {
+      deviceCopy(_outXyz.p, srcOut, 3 * _nOut, _stream);
     } else {
       RBF_CUDA(cudaMemcpyAsync(_outXyz.p, srcOut, 3 * _nOut * sizeof(double), kind, _stream));
     }
@@ -293,8 +300,9 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
   }
   const int dim = _cfg.dimensions;
   double    bbMin[3], bbMax[3], obMin[3], obMax[3];
+  trace.phase("alloc + copy");
   computeBounds(_inXyz.p, _nIn, bbMin, bbMax, _stream); // :334 (bounds of the inMesh)
-  trace.phase("copy + bounds");
+  trace.phase("bounds");
   auto edge = [&](int d) { return std::abs(bbMax[d] - bbMin[d]); };
 
   BinGrid inGrid, outGrid;
@@ -467,7 +475,10 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
   trace.phase("classify");
   // separated polynomial + assembly/factorisation of all local systems
   _poly.alloc(_nClusters);
-  _mat.alloc(std::max<int64_t>(_mem.sumTri, 1));
+  if (_mat.n < static_cast<size_t>(std::max<int64_t>(_mem.sumTri, 1))) {
+    RBF_CUDA(cudaStreamSynchronize(_stream));
+    _mat.reserve(static_cast<size_t>(_mem.sumTri) + static_cast<size_t>(_mem.sumTri) / 16 + 2);
+  }
   const PumSolveArgs args = solveArgs();
   trace.phase("alloc factors");
   pumPolySetup(args, _nClusters, _cfg.polynomial, _stream);
@@ -491,7 +502,7 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
                                             "Please check if your coupling meshes are correct (e.g. no vertices are duplicated) or reconfigure "
                                             "your basis-function (e.g. reduce the support-radius).");
   }
-  stats.device_bytes       = static_cast<int64_t>(_inXyz.bytes() + _outXyz.bytes() + _centers.bytes() + _mem.bytes() + _mat.bytes() + _poly.bytes() + _wsum.bytes() + _wcount.bytes() + _outRec.bytes() + _inRec.bytes());
+  stats.device_bytes       = static_cast<int64_t>(_inXyz.bytes() + _outXyz.bytes() + _centers.bytes() + _mem.bytes() + static_cast<size_t>(std::max<int64_t>(_mem.sumTri, 1)) * sizeof(double) + _poly.bytes() + _wsum.bytes() + _wcount.bytes() + _outRec.bytes() + _inRec.bytes());
   stats.ms_compute_kernels = whole.stop();
   stats.kernel_launches    = g_launches;
   _computed                = true;

@@ -37,6 +37,8 @@ struct BinGrid {
 };
 
 // bounding box of n points (device AoS); returns min/max on the host (query/Index.cpp:369-391)
+// device -> device copy of n doubles with a kernel (see spatial.cu)
+void deviceCopy(double *dst, const double *src, int64_t n, cudaStream_t s);
 void computeBounds(const double *dXyz, int64_t n, double bbMin[3], double bbMax[3], cudaStream_t s);
 
 // nearest vertex to each of nProbes host points: vertex ID with the smallest squared distance, ties -> lowest ID

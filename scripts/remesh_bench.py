@@ -26,6 +26,7 @@ ap.add_argument("--steps", type=int, default=6)
 ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--oracle-sample", type=int, default=20000)
 ap.add_argument("--out", default=None)
+ap.add_argument("--static", action="store_true", help="diagnostic: same mesh every step")
 a = ap.parse_args()
 
 rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -66,11 +67,14 @@ def run(n, steps, warmup, device):
     res = torch.empty(n, dtype=torch.float64, device=device)
     ev, comp, mp, asm = [], [], [], []
     for s in range(warmup + steps):
-        xin, xout = surface(uv_in, float(s), n), surface(uv_out, float(s), n)
+        t_ = 0.0 if a.static else float(s)
+        xin, xout = surface(uv_in, t_, n), surface(uv_out, t_, n)
         vals = field(xin).contiguous()
         torch.cuda.synchronize()
         if m.hasComputedMapping():
             m.clear()
+        if os.environ.get("REMESH_SYNC_AFTER_CLEAR"):
+            torch.cuda.synchronize()
         m.computeMapping(xin, xout)
         m.map(vals, 1, out=res)
         st = m.stats()

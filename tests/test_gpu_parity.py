@@ -246,6 +246,47 @@ def test_pum_2d_surface_like(pb, orc):
     assert refcases.rel_l2(g.map(vals, 1), o.map(vals, 1)) <= 1e-9
 
 
+def _wavy_surface(uv, t):
+    x, y = uv[:, 0], uv[:, 1]
+    return np.stack([x, y, 0.5 + (0.15 + 0.02 * np.sin(0.5 * t)) * np.sin(2 * np.pi * x) * np.cos(2 * np.pi * y)], axis=1)
+
+
+def test_pum_remeshing_surface(pb, orc):
+    # BASELINE.json configs[4]: repeated computeMapping on a moving curved surface in 3-D. The tentative centre lattice is
+    # almost empty (a few % of its centres survive), which is the case the vertex-side emptiness test and the live list
+    # exist for; cluster sets must stay bit-identical to the oracle's, mapped values within 1e-10.
+    n = 6000
+    uin, uout = refcases.halton(n, (2, 3)), refcases.halton(n + 211, (7, 11))
+    g = pb.PartitionOfUnityMapping("consistent", 3, "compact-polynomial-c6", 0.25, "separate", 30, 0.15, True)
+    o = orc.PumMapping("consistent", 3, "compact-polynomial-c6", 0.25, "separate", 30, 0.15, True)
+    for step in range(3):
+        # last step: the outMesh sticks out of the inMesh's bounding box (by less than a cluster radius), so that some
+        # out-vertices lie beyond the first / last lattice layer
+        inp, out = _wavy_surface(uin, float(step)), _wavy_surface(uout * 1.02 - 0.01 if step == 2 else uout, float(step))
+        if g.hasComputedMapping():
+            g.clear()
+            o.clear()
+        g.compute_mapping(inp, out)
+        o.compute_mapping(inp, out)
+        radius, centers, in_off, out_off, in_ids, out_ids = g.clusters()
+        assert radius == o.cluster_radius
+        assert centers.shape[0] == o.num_clusters
+        for c in range(o.num_clusters):
+            k = o.cluster(c)
+            assert np.array_equal(centers[c], k["center"]), (step, c)
+            assert np.array_equal(in_ids[in_off[c]:in_off[c + 1]], k["in_ids"]), (step, c)
+            assert np.array_equal(out_ids[out_off[c]:out_off[c + 1]], k["out_ids"]), (step, c)
+        vals = np.sin(3 * np.pi * inp[:, 0]) * np.cos(2 * np.pi * inp[:, 1]) + np.exp(inp[:, 2])
+        assert refcases.rel_l2(g.map(vals, 1), o.map(vals, 1)) <= REL_L2_TOL
+
+
+def test_pum_remeshing_surface_without_projection(pb, orc):
+    n = 5000
+    inp, out = _wavy_surface(refcases.halton(n, (2, 3)), 1.0), _wavy_surface(refcases.halton(n, (7, 11)), 1.0)
+    _cluster_compare(pb, orc, inp, out, 3, 30, 0.15, False, support=0.25)
+    _cluster_compare(pb, orc, inp, out, 3, 30, 0.15, False, constraint="conservative", support=0.25)
+
+
 def test_pum_large_clusters(pb, orc):
     # vertices-per-cluster 100 / 300 exercise the 16x16-thread and the global-memory kernels
     n = 5000
