@@ -42,6 +42,12 @@ def _is_torch(x):
     return type(x).__module__.startswith("torch")
 
 
+def _sync_producer(t):
+    """Device-pointer entry points: the tensors must be complete before the library's own stream reads them."""
+    import torch
+    torch.cuda.current_stream(t.device).synchronize()
+
+
 class _Mapping:
     def __init__(self, cfg: Config):
         self._L = _lib.lib()
@@ -73,6 +79,7 @@ class _Mapping:
             a, b = input_xyz.contiguous(), output_xyz.contiguous()
             assert a.dtype.is_floating_point and a.element_size() == 8 and a.shape[-1] == 3 and b.shape[-1] == 3
             self._n_input, self._n_output = a.shape[0], b.shape[0]
+            _sync_producer(a)  # the library's stream is not ordered behind torch's (include/rbfmap.h)
             self._check(self._L.rbfmap_compute_mapping_device(self._h, a.data_ptr(), a.shape[0], b.data_ptr(), b.shape[0]))
             return
         if _is_torch(input_xyz):  # pinned / pageable host tensors
@@ -94,6 +101,7 @@ class _Mapping:
             if v.is_cuda:
                 if out is None:
                     out = torch.empty(self._n_output * dims, dtype=torch.float64, device=v.device)
+                _sync_producer(v)
                 self._check(self._L.rbfmap_map_device(self._h, v.data_ptr(), dims, out.data_ptr()))
                 return out
             if out is None:
