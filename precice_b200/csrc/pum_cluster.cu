@@ -364,19 +364,49 @@ __device__ __forceinline__ int gatherToShared(const BinGridView &g, double cx, d
 }
 
 // ascending rank sort of the n <= kSlotCap distinct ids in stage; dst[rank] = payload of that id (its binned position)
+// 1 if a < b, for vertex IDs (0 <= a, b < 2^30): the sign bit of the difference; ptxas turns the comparison form into a
+// three-instruction select per element, this is a subtraction and a shift-add
+__device__ __forceinline__ int lessThan(int a, int b) { return static_cast<int>((static_cast<unsigned>(a) - static_cast<unsigned>(b)) >> 31); }
+
 __device__ __forceinline__ void rankSortToGlobal(const int *stage, const int *payload, int n, int *__restrict__ dst, int lane)
 {
-  for (int i = lane; i < n; i += 32) {
-    const int v = stage[i];
-    int       rank = 0;
-    int       j = 0;
-    for (; j + 4 <= n; j += 4) {
-      const int4 q = *reinterpret_cast<const int4 *>(stage + j);
-      rank += (q.x < v) + (q.y < v) + (q.z < v) + (q.w < v);
+  // ranks by counting: four independent counters per element (one compare + one predicated increment each; a single
+  // counter compiled to a three-instruction dependent chain per compare), two elements per lane share the loads
+  for (int i = lane; i < n; i += 64) {
+    const int  v = stage[i];
+    const bool two = i + 32 < n;
+    const int  w = two ? stage[i + 32] : 0;
+    int        a0 = 0, a1 = 0, a2 = 0, a3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+    int        j = 0;
+    if (__any_sync(__activemask(), two)) {
+      for (; j + 4 <= n; j += 4) {
+        const int4 q = *reinterpret_cast<const int4 *>(stage + j);
+        a0 += lessThan(q.x, v);
+        a1 += lessThan(q.y, v);
+        a2 += lessThan(q.z, v);
+        a3 += lessThan(q.w, v);
+        b0 += lessThan(q.x, w);
+        b1 += lessThan(q.y, w);
+        b2 += lessThan(q.z, w);
+        b3 += lessThan(q.w, w);
+      }
+    } else {
+      for (; j + 4 <= n; j += 4) {
+        const int4 q = *reinterpret_cast<const int4 *>(stage + j);
+        a0 += lessThan(q.x, v);
+        a1 += lessThan(q.y, v);
+        a2 += lessThan(q.z, v);
+        a3 += lessThan(q.w, v);
+      }
     }
-    for (; j < n; ++j)
-      rank += stage[j] < v;
-    dst[rank] = payload[i];
+    for (; j < n; ++j) {
+      const int q = stage[j];
+      a0 += lessThan(q, v);
+      b0 += lessThan(q, w);
+    }
+    dst[(a0 + a1) + (a2 + a3)] = payload[i];
+    if (two)
+      dst[(b0 + b1) + (b2 + b3)] = payload[i + 32];
   }
 }
 
