@@ -105,9 +105,14 @@ __global__ void __launch_bounds__(32, NB <= 4 ? 20 : NB == 5 ? 16 : NB == 6 ? 14
     double nr0 = 0.0, nr1 = 0.0; // -1/d_k for the two operand columns of this lane: k = q and k = 4 + q
 #pragma unroll 1
     for (int kp = 0; kp < 4; ++kp) { // column pair kp: columns 2kp (held in s0 by the lanes with q == kp) and 2kp + 1 (s1)
+      // padding columns (index >= n, last block column only) are never stored and only touch padding rows: skip them
+      if (kb == NB - 1 && 8 * kb + 2 * kp >= n)
+        break;
 #pragma unroll
       for (int odd = 0; odd < 2; ++odd) {
         const int    k    = 2 * kp + odd;
+        if (kb == NB - 1 && odd == 1 && 8 * kb + k >= n)
+          break;
         const double colk = odd ? s1 : s0;
         const int    srcD = 4 * k + kp; // lane that holds S(k, k)
         const double d    = shfl(colk, srcD);
