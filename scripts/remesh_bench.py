@@ -106,16 +106,25 @@ def run(n, steps, warmup, device):
 
 
 m, st, ev, comp, mp, asm, e2e, err = run(a.n, a.steps, a.warmup, dev)
-t = torch.tensor([sum(ev) / len(ev), sum(e2e) / len(e2e), sum(comp) / len(comp), sum(mp) / len(mp), sum(asm) / len(asm)],
+def median(v):
+    v = sorted(v)
+    return v[len(v) // 2] if len(v) % 2 else 0.5 * (v[len(v) // 2 - 1] + v[len(v) // 2])
+
+
+# medians over the timed steps: one of ~10 runs on the shared GPU boxes showed a single step several times longer than
+# the others (host thread delayed between launches right after another process had exited); min / max are reported too
+t = torch.tensor([median(ev), median(e2e), median(comp), median(mp), median(asm), max(ev), -min(ev)],
                  dtype=torch.float64, device=dev)
 if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-ms_dev, ms_e2e, ms_comp, ms_map, ms_asm = (float(x) for x in t.tolist())
+ms_dev, ms_e2e, ms_comp, ms_map, ms_asm, ms_max, ms_min = (float(x) for x in t.tolist())
+ms_min = -ms_min
 if rank == 0:
     line = {"workload": f"rbf-pum-direct compact-polynomial-c6, remeshing: perturbed 3-D surface z = f(x, y), {a.n}->{a.n} vertices per GPU, "
                         f"clear + computeMapping + map (scalar) per step",
             "relative_overlap": a.overlap, "project_to_input": not a.no_project, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step_device": ms_dev, "ms_compute_mapping": ms_comp, "ms_assembly_factor": ms_asm, "ms_map": ms_map,
+            "statistic": "median over the timed steps, max over ranks", "ms_per_step_device": ms_dev, "ms_per_step_device_min": ms_min,
+            "ms_per_step_device_max": ms_max, "ms_compute_mapping": ms_comp, "ms_assembly_factor": ms_asm, "ms_map": ms_map,
             "vertices_per_s_device": world * a.n / (ms_dev * 1e-3),
             "ms_per_step_host_pointers": ms_e2e, "vertices_per_s_e2e": world * a.n / (ms_e2e * 1e-3),
             "interpolation_error_rel_l2": err,
