@@ -136,7 +136,8 @@ def cpu_baseline(n_sample: int, threads: int):
     the reference parallelises rbf-pum-direct: one rank per core, every rank clusters and maps its own partition with no
     communication (BatchedRBFSolver.hpp:29-31). `threads` partitions of n_sample/threads vertices each."""
     import oracle
-    per = max(2000, n_sample // threads)
+    # at most 500k vertices per partition: a step stays near 5 s of wall clock on hosts with few cores as well
+    per = max(2000, min(n_sample // threads, 500_000))
     ins = [halton_numpy(per, (2, 3, 5), 1 + r * per) for r in range(threads)]
     outs = [halton_numpy(per, (7, 11, 13), 1 + r * per) for r in range(threads)]
     vals = [np.sin(2 * np.pi * a[:, 0]) * np.cos(2 * np.pi * a[:, 1]) + a[:, 2] for a in ins]
@@ -165,7 +166,7 @@ def run_reference(args, rank, world):
     line = {"metric": "mapped vertices/s (computeMapping+map), rbf-pum-direct 3D", "value": v, "unit": "vertices/s", "impl": "reference",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args.n, n_sample_note=n_sample),
+            "config": workload_config(args.n, n_sample_note=cb["total_vertices"]),
             "cpu_baseline": {"value": v, "unit": "vertices/s", "cores": threads, "kind": "port", "sample": cb["sample"]},
             "e2e": {"value": v, "unit": "vertices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
