@@ -56,6 +56,19 @@ enum rbfmap_constraint {
 /* the three XML tags of the hot path (mapping/config/MappingConfiguration.cpp:834-914) */
 enum rbfmap_variant { RBFMAP_GLOBAL_DIRECT = 0, RBFMAP_GLOBAL_ITERATIVE = 1, RBFMAP_PUM_DIRECT = 2 };
 
+/* <executor:cuda execution-mode="minimal-memory|minimal-compute"> (mapping/config/MappingConfiguration.cpp:328-331,
+ * 555-559) = constructor argument computeEvaluationOffline of PartitionOfUnityMapping (PartitionOfUnityMapping.hpp:48-57,
+ * 145; used at BatchedRBFSolver.hpp:196, 239, 324). minimal-memory re-evaluates the evaluation matrix in every map();
+ * minimal-compute stores the per-cluster evaluation operator at computeMapping() and map() becomes an HBM stream. */
+enum rbfmap_execution_mode { RBFMAP_MINIMAL_MEMORY = 0, RBFMAP_MINIMAL_COMPUTE = 1 };
+
+/* How rbf-pum-direct shards ONE mapping over the ranks joined by rbfmap_distributed_init:
+ * DUPLICATE: every rank owns a slab of output vertices and processes every cluster that touches one of them (boundary
+ *            clusters are factorised on both sides of a cut); no collective in map(); consistent constraints only.
+ * EXCHANGE : every cluster belongs to exactly one rank; partial sums of the blend (and, at computeMapping, the partition-
+ *            of-unity weight sums) are all-reduced with NCCL over NVLink; every rank returns the complete result. */
+enum rbfmap_shard_mode { RBFMAP_SHARD_DUPLICATE = 0, RBFMAP_SHARD_EXCHANGE = 1 };
+
 enum rbfmap_status {
   RBFMAP_OK              = 0,
   RBFMAP_ERR_INVALID     = 1, /* bad argument / configuration (PRECICE_CHECK at construction) */
@@ -82,12 +95,18 @@ typedef struct rbfmap_config {
   double   shape_parameter;      /* gaussian, (inverse) multiquadrics */
   int      polynomial;           /* rbfmap_polynomial */
   int      dead_axis[3];         /* x-dead / y-dead / z-dead (global variants only) */
-  unsigned vertices_per_cluster; /* PUM, default 50 */
+  unsigned vertices_per_cluster; /* PUM, default 50; clusters of more than 3900 vertices are rejected by computeMapping
+                                    with RBFMAP_ERR_UNSUPPORTED (shared-memory bound of the per-cluster kernels) */
   double   relative_overlap;     /* PUM, default 0.15 */
   int      project_to_input;     /* PUM, default 1 */
   double   solver_rtol;          /* global-iterative, default 1e-9 */
   int      max_iterations;       /* global-iterative, default 1000000 (GinkgoRadialBasisFctSolver.hpp:337-374) */
   int      device_id;            /* CUDA device ordinal; -1 = current device */
+  int      execution_mode;       /* rbfmap_execution_mode (PUM), default minimal-memory = the constructor default
+                                    computeEvaluationOffline = false (PartitionOfUnityMapping.hpp:57) */
+  int      shard_mode;           /* rbfmap_shard_mode (PUM after rbfmap_distributed_init), default DUPLICATE */
+  int      deterministic;        /* PUM: 1 = blend by a per-vertex gather in ascending cluster order instead of atomics
+                                    (bit-reproducible output), default 0 */
 } rbfmap_config;
 
 typedef struct rbfmap_handle rbfmap_handle;

@@ -22,6 +22,8 @@ BASIS = {
 }
 CONSTRAINT = {"consistent": 0, "conservative": 1, "scaled-consistent-surface": 2, "scaled-consistent-volume": 3}
 VARIANT = {"rbf-global-direct": 0, "rbf-global-iterative": 1, "rbf-pum-direct": 2}
+EXECUTION_MODE = {"minimal-memory": 0, "minimal-compute": 1}
+SHARD_MODE = {"duplicate": 0, "exchange": 1}
 STATUS = {0: "OK", 1: "INVALID", 2: "CUDA", 3: "SINGULAR", 4: "UNASSIGNED", 5: "EMPTY", 6: "STATE", 7: "UNSUPPORTED",
           8: "NOT_CONVERGED"}
 
@@ -43,6 +45,7 @@ class Config(C.Structure):
         ("support_radius", C.c_double), ("shape_parameter", C.c_double), ("polynomial", C.c_int),
         ("dead_axis", C.c_int * 3), ("vertices_per_cluster", C.c_uint), ("relative_overlap", C.c_double),
         ("project_to_input", C.c_int), ("solver_rtol", C.c_double), ("max_iterations", C.c_int), ("device_id", C.c_int),
+        ("execution_mode", C.c_int), ("shard_mode", C.c_int), ("deterministic", C.c_int),
     ]
 
 

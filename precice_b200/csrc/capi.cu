@@ -104,19 +104,29 @@ DeviceMapping::DeviceMapping(const rbfmap_config &cfg)
     cudaGetLastError();
     throw MapError(RBFMAP_ERR_CUDA, "rbfmap: no CUDA device available; this backend has no CPU fallback.");
   }
+  if (cfg.execution_mode != RBFMAP_MINIMAL_MEMORY && cfg.execution_mode != RBFMAP_MINIMAL_COMPUTE)
+    throw MapError(RBFMAP_ERR_INVALID, "unknown execution mode");
+  if (cfg.shard_mode != RBFMAP_SHARD_DUPLICATE && cfg.shard_mode != RBFMAP_SHARD_EXCHANGE)
+    throw MapError(RBFMAP_ERR_INVALID, "unknown shard mode");
   if (cfg.device_id >= 0) {
     if (cfg.device_id >= count)
       throw MapError(RBFMAP_ERR_CUDA, "rbfmap: gpu-device-id out of range.");
-    RBF_CUDA(cudaSetDevice(cfg.device_id));
+    _device = cfg.device_id;
+  } else {
+    RBF_CUDA(cudaGetDevice(&_device));
   }
+  // the creating thread's current device is left untouched: every entry point selects the mapping's device itself
+  DeviceScope scope(_device);
   RBF_CUDA(cudaStreamCreateWithFlags(&_stream, cudaStreamNonBlocking));
   configureMemoryPool();
 }
 
 DeviceMapping::~DeviceMapping()
 {
-  if (_stream)
+  if (_stream) {
+    DeviceScope scope(_device);
     cudaStreamDestroy(_stream);
+  }
 }
 
 double PhaseTrace::now()
@@ -175,6 +185,9 @@ template <typename F>
 int guarded(rbfmap_handle *h, F &&f)
 {
   try {
+    // the mapping lives on one device (gpu-device-id); select it for the duration of the call, whichever thread calls
+    // and whatever device that thread had current, and restore the caller's device afterwards
+    DeviceScope scope(h && h->impl ? h->impl->device() : -1);
     f();
     if (h)
       h->lastError.clear();
@@ -206,6 +219,9 @@ void rbfmap_default_config(rbfmap_config *cfg)
   cfg->solver_rtol          = 1e-9; // :237
   cfg->max_iterations       = 1000000;
   cfg->device_id            = -1;
+  cfg->execution_mode       = RBFMAP_MINIMAL_MEMORY; // PartitionOfUnityMapping.hpp:57 (computeEvaluationOffline = false)
+  cfg->shard_mode           = RBFMAP_SHARD_DUPLICATE;
+  cfg->deterministic        = 0;
 }
 
 int rbfmap_create(const rbfmap_config *cfg, rbfmap_handle **out)
@@ -264,6 +280,7 @@ int rbfmap_compute_mapping(rbfmap_handle *h, const double *input_xyz, int64_t n_
 
 struct rbfmap_cache {
   std::unique_ptr<DeviceMapping::JitCache> impl;
+  int                                      device = -1;
 };
 
 extern "C" {
@@ -284,8 +301,9 @@ int rbfmap_cache_create(rbfmap_handle *h, int dims, rbfmap_cache **out)
   *out = nullptr;
   return guarded(h, [&] {
     auto c  = std::make_unique<rbfmap_cache>();
-    c->impl = h->impl->jitCreateCache(dims);
-    *out    = c.release();
+    c->impl   = h->impl->jitCreateCache(dims);
+    c->device = h->impl->device();
+    *out      = c.release();
   });
 }
 int rbfmap_cache_reset(rbfmap_handle *h, rbfmap_cache *cache)
@@ -294,7 +312,13 @@ int rbfmap_cache_reset(rbfmap_handle *h, rbfmap_cache *cache)
     return RBFMAP_ERR_INVALID;
   return guarded(h, [&] { h->impl->jitResetCache(*cache->impl); });
 }
-void rbfmap_cache_destroy(rbfmap_cache *cache) { delete cache; }
+void rbfmap_cache_destroy(rbfmap_cache *cache)
+{
+  if (!cache)
+    return;
+  DeviceScope scope(cache->device);
+  delete cache;
+}
 int  rbfmap_cache_update(rbfmap_handle *h, rbfmap_cache *cache, const double *values)
 {
   if (!h || !cache)
@@ -324,6 +348,14 @@ int rbfmap_complete_just_in_time_mapping(rbfmap_handle *h, rbfmap_cache *cache, 
 static void mapDeviceImpl(rbfmap_handle *h, int mode /*0 dispatch, 1 consistent, 2 conservative*/, const double *d_in, int dims, double *d_out)
 {
   DeviceMapping *m    = h->impl.get();
+  if (dims < 1)
+    throw MapError(RBFMAP_ERR_INVALID, "data dimension has to be positive");
+  // The reference reaches the two virtuals only through Mapping::map(), which dispatches on the constraint
+  // (Mapping.cpp:158-173): the mapping was computed for one direction (the meshes are swapped for conservative
+  // constraints), so forcing the other one would read and write buffers of the wrong size.
+  if ((mode == 2 && !m->isConservative()) || (mode == 1 && m->isConservative()))
+    throw MapError(RBFMAP_ERR_STATE, std::string("The mapping was computed with a ") + (m->isConservative() ? "conservative" : "consistent") +
+                                         " constraint; " + (mode == 2 ? "mapConservative" : "mapConsistent") + " is not available on it.");
   const bool     cons = mode == 2 || (mode == 0 && m->isConservative());
   if (cons)
     m->mapConservative(d_in, dims, d_out);
@@ -412,7 +444,13 @@ int rbfmap_clear(rbfmap_handle *h)
 
 int rbfmap_has_computed_mapping(const rbfmap_handle *h) { return h && h->impl->hasComputedMapping() ? 1 : 0; }
 
-void rbfmap_destroy(rbfmap_handle *h) { delete h; }
+void rbfmap_destroy(rbfmap_handle *h)
+{
+  if (!h)
+    return;
+  DeviceScope scope(h->impl ? h->impl->device() : -1);
+  delete h;
+}
 
 const char *rbfmap_get_name(const rbfmap_handle *h) { return h ? h->name.c_str() : ""; }
 

@@ -133,9 +133,32 @@ struct ScratchBuf {
   size_t bytes() const { return n * sizeof(T); }
 };
 
+// Makes `device` current for the lifetime of the object and restores the previous device (device < 0: no-op).
+struct DeviceScope {
+  int prev = -1;
+  explicit DeviceScope(int device)
+  {
+    if (device < 0)
+      return;
+    int cur = -1;
+    if (cudaGetDevice(&cur) == cudaSuccess && cur != device) {
+      if (cudaSetDevice(device) != cudaSuccess)
+        throw MapError(RBFMAP_ERR_CUDA, "rbfmap: cannot select the mapping's CUDA device");
+      prev = cur;
+    }
+  }
+  ~DeviceScope()
+  {
+    if (prev >= 0)
+      cudaSetDevice(prev);
+  }
+  DeviceScope(const DeviceScope &)            = delete;
+  DeviceScope &operator=(const DeviceScope &) = delete;
+};
+
 inline int divUp(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / b); }
 
-// number of SMs of the current device (cached)
+// number of SMs of the current device (cached per device)
 int smCount();
 
 // Exclusive prefix sums (own kernels, scan.cu): out has n+1 entries, out[n] = total.

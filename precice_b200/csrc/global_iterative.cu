@@ -429,6 +429,9 @@ public:
     }
     _rank  = rank;
     _world = world;
+    // the kept initial guess has the leading dimension of the previous world size
+    _guess.release();
+    _guessDims = 0;
     if (world > 1) {
       ncclUniqueId id;
       std::memcpy(&id, uniqueId, sizeof(id));

@@ -52,6 +52,7 @@ public:
   bool                 isConservative() const { return _cfg.constraint == RBFMAP_CONSERVATIVE; }
   const rbfmap_config &config() const { return _cfg; }
   cudaStream_t         stream() const { return _stream; }
+  int                  device() const { return _device; }
   int64_t              nInput() const { return _nInput; }
   int64_t              nOutput() const { return _nOutput; }
   rbfmap_stats         stats;
@@ -60,6 +61,7 @@ protected:
   rbfmap_config _cfg;
   RbfParams     _rbf;
   cudaStream_t  _stream   = nullptr;
+  int           _device   = 0; // resolved CUDA device ordinal of this mapping (gpu-device-id)
   bool          _computed = false;
   int64_t       _nInput = 0, _nOutput = 0;
 };

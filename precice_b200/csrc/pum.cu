@@ -473,6 +473,9 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
   stats.n_clusters     = _nClusters;
   stats.cluster_radius = _radius;
   trace.phase("classify");
+  if (stats.max_n > kPumMaxClusterVertices)
+    throw MapError(RBFMAP_ERR_UNSUPPORTED, "rbf-pum-direct: a cluster with " + std::to_string(stats.max_n) + " vertices exceeds the supported cluster size of " +
+                                               std::to_string(kPumMaxClusterVertices) + " vertices; reduce \"vertices-per-cluster\".");
   // separated polynomial + assembly/factorisation of all local systems
   _poly.alloc(_nClusters);
   if (_mat.n < static_cast<size_t>(std::max<int64_t>(_mem.sumTri, 1))) {

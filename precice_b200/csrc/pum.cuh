@@ -116,6 +116,10 @@ struct PumSolveArgs {
 //   bucket  12    : larger clusters, global-memory kernels
 constexpr int    kNumBuckets = 13;
 constexpr size_t kPumMaxSmem = 200 * 1024;
+// Largest supported cluster (in-vertices): the tightest shared-memory bound of the global-memory kernels of bucket 12
+// (conservative map, 3 components: 48 B x (n + 256) + 1 KB <= kPumMaxSmem). Checked at the end of computeMapping so that
+// the caller does not learn about it in the first map() only; documented in include/rbfmap.h.
+constexpr int kPumMaxClusterVertices = 3900;
 __host__ __device__ inline int pumBucketOf(int n)
 {
   if (n <= 64)

@@ -3,6 +3,8 @@
 // Two-level scan: per-block scan of kItems elements, scan of the block totals, uniform add.
 #include "common.cuh"
 
+#include <atomic>
+
 namespace rbfmap {
 
 thread_local int          g_launches    = 0;
@@ -20,13 +22,18 @@ void configureMemoryPool()
 
 int smCount()
 {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0;
-    RBF_CUDA(cudaGetDevice(&dev));
-    RBF_CUDA(cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev));
+  // per device, race-free: the attribute query is idempotent and the slots are atomics
+  static std::atomic<int> cached[64];
+  int                     dev = 0;
+  RBF_CUDA(cudaGetDevice(&dev));
+  const int slot = dev < 64 ? dev : 63;
+  int       v    = dev < 64 ? cached[slot].load(std::memory_order_relaxed) : 0;
+  if (v == 0) {
+    RBF_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+    if (dev < 64)
+      cached[slot].store(v, std::memory_order_relaxed);
   }
-  return cached;
+  return v;
 }
 
 namespace {

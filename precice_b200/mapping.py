@@ -201,7 +201,8 @@ class MappingDataCache:
 
 
 def _config(variant, constraint, dim, basis, param, polynomial, dead_axis=(False, False, False), vpc=50, overlap=0.15,
-            project=True, gauss_support=None, solver_rtol=1e-9, max_iterations=1000000, device_id=-1) -> Config:
+            project=True, gauss_support=None, solver_rtol=1e-9, max_iterations=1000000, device_id=-1,
+            execution_mode="minimal-memory", shard_mode="duplicate", deterministic=False) -> Config:
     cfg = Config()
     _lib.lib().rbfmap_default_config(C.byref(cfg))
     cfg.variant = VARIANT[variant]
@@ -223,6 +224,9 @@ def _config(variant, constraint, dim, basis, param, polynomial, dead_axis=(False
     cfg.solver_rtol = float(solver_rtol)
     cfg.max_iterations = int(max_iterations)
     cfg.device_id = int(device_id)
+    cfg.execution_mode = _lib.EXECUTION_MODE[execution_mode]
+    cfg.shard_mode = _lib.SHARD_MODE[shard_mode]
+    cfg.deterministic = int(bool(deterministic))
     return cfg
 
 
@@ -231,10 +235,14 @@ class PartitionOfUnityMapping(_Mapping):
     relativeOverlap, projectToInput) — PartitionOfUnityMapping.hpp:48-57, XML tag <mapping:rbf-pum-direct>."""
 
     def __init__(self, constraint, dim, basis, param, polynomial="separate", vertices_per_cluster=50,
-                 relative_overlap=0.15, project_to_input=True, gauss_support=None, device_id=-1):
+                 relative_overlap=0.15, project_to_input=True, gauss_support=None, device_id=-1,
+                 execution_mode="minimal-memory", shard_mode="duplicate", deterministic=False):
+        """execution_mode: <executor execution-mode=...> / computeEvaluationOffline (PartitionOfUnityMapping.hpp:57);
+        shard_mode, deterministic: see include/rbfmap.h."""
         super().__init__(_config("rbf-pum-direct", constraint, dim, basis, param, polynomial, vpc=vertices_per_cluster,
                                  overlap=relative_overlap, project=project_to_input, gauss_support=gauss_support,
-                                 device_id=device_id))
+                                 device_id=device_id, execution_mode=execution_mode, shard_mode=shard_mode,
+                                 deterministic=deterministic))
 
     def clusters(self):
         """(radius, centers[nc,3], in_offsets, out_offsets, in_ids, out_ids) — inspection for the parity tests."""

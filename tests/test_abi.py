@@ -39,7 +39,9 @@ def test_struct_layouts_match_header():
     assert cfg.project_to_input == 1
     assert cfg.solver_rtol == 1e-9
     assert cfg.device_id == -1
-    assert C.sizeof(_lib.Config) == 88
+    assert cfg.execution_mode == _lib.EXECUTION_MODE["minimal-memory"]  # PartitionOfUnityMapping.hpp:57
+    assert cfg.shard_mode == _lib.SHARD_MODE["duplicate"] and cfg.deterministic == 0
+    assert C.sizeof(_lib.Config) == 104
     assert C.sizeof(_lib.Stats) == 120
 
 
