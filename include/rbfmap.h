@@ -175,18 +175,35 @@ int rbfmap_map_conservative(rbfmap_handle *h, const double *in, int dims, double
 int rbfmap_compute_mapping_device(rbfmap_handle *h, const double *d_input_xyz, int64_t n_input, const double *d_output_xyz, int64_t n_output);
 int rbfmap_map_device(rbfmap_handle *h, const double *d_in, int dims, double *d_out);
 
-/* Multi-GPU, one process per GPU. rbf-pum-direct shards by mesh partition (one mapping per rank, no
- * communication, exactly the reference's parallel PUM: BatchedRBFSolver.hpp:29-31) and rbf-global-direct stays on one
- * device, so neither needs these calls. rbf-global-iterative shards the rows of its matrix-free CG operator: every rank
- * is given the same (replicated) meshes and values, owns a contiguous slice of the cell-ordered rows, and the library
- * all-gathers the direction vector and all-reduces the dot products with NCCL over NVLink (the role of PETSc's
- * distributed KSP in PetRadialBasisFctMapping.hpp:246-263, 629-633). Rank 0 obtains the 128-byte NCCL id, the host
+/* Multi-GPU, one process per GPU: ONE mapping sharded over the ranks of a group. Every rank is given the
+ * same (replicated) meshes and values and makes the same sequence of calls; rank 0 obtains the 128-byte NCCL id, the host
  * application broadcasts it (MPI / sockets / torch.distributed), then every rank calls rbfmap_distributed_init before
- * computeMapping. All ranks must make the same sequence of calls. */
+ * computeMapping. With host pointers every rank uploads only its 1/world slice over PCIe and the library all-gathers the
+ * slices over NVLink.
+ *  - rbf-pum-direct: every rank runs the (cheap, deterministic) clustering of the whole mesh, so the cluster set is the
+ *    one of the single-device mapping; the clusters are then sharded by slabs along the longest lattice axis
+ *    (rbfmap_config.shard_mode): DUPLICATE - a rank owns a slab of output vertices and processes every cluster that
+ *    reaches into it, map() needs no collective and fills only the owned vertices of `out` (the others are zero; the
+ *    complete result is the sum over the ranks; rbfmap_stats.shard_* describe the slab); EXCHANGE (always used for
+ *    conservative constraints) - every cluster has one owner, the weight sums (computeMapping) and the partial blends
+ *    (map) are all-reduced and every rank returns the complete result. The reference instead maps rank-local partitions
+ *    independently (BatchedRBFSolver.hpp:29-31, halo PartitionOfUnityMapping.hpp:479-533), which changes the clustering
+ *    with the partitioning; here the result does not depend on the number of ranks (1e-10).
+ *  - rbf-global-iterative shards the rows of its matrix-free CG operator: a rank owns a contiguous slice of the
+ *    cell-ordered rows, the direction vector is all-gathered and the dot products all-reduced (the role of PETSc's
+ *    distributed KSP in PetRadialBasisFctMapping.hpp:246-263, 629-633).
+ *  - rbf-global-direct stays on one device (RBFMAP_ERR_UNSUPPORTED). */
 int rbfmap_nccl_unique_id(char id[128]);
+/* id == NULL joins a group WITHOUT communicator: accepted by rbf-pum-direct for consistent constraints in duplicate mode
+ * only, where no collective is needed (the ranks may then even be handles of one process); every rank uploads complete
+ * meshes and raises its own errors. */
 int rbfmap_distributed_init(rbfmap_handle *h, const char id[128], int rank, int world);
 /* The contiguous slice [*begin, *end) of n rows owned by `rank` (host-side helper, no device needed). */
 int rbfmap_partition_rows(int64_t n, int world, int rank, int64_t *begin, int64_t *end);
+/* Host-side helper of the sharded rbf-pum-direct (no device needed): given the histogram of the cluster centres along
+ * the slab axis, the cut positions 0 = cuts[0] <= ... <= cuts[world] = n_bins that minimise the largest number of
+ * centres one rank processes, when rank r processes the bins [cuts[r] - halo_bins, cuts[r+1] + halo_bins). */
+int rbfmap_partition_slabs(const int64_t *histogram, int n_bins, int world, int halo_bins, int *cuts);
 
 /* Mapping::clear() (Mapping.hpp:134), Mapping::hasComputedMapping(), destructor, Mapping::getName(). */
 int         rbfmap_clear(rbfmap_handle *h);
@@ -217,6 +234,15 @@ typedef struct rbfmap_stats {
   float   ms_map_kernels;     /* device time of the last map */
   float   ms_assembly_factor; /* device time of the dominant assembly(+factorisation) kernel(s) of the last computeMapping */
   int     kernel_launches;    /* kernels launched by the last compute + map calls */
+  /* sharded rbf-pum-direct (rbfmap_distributed_init): n_clusters and the sums above describe what THIS rank processes */
+  int64_t n_clusters_global;  /* clusters of the whole mapping */
+  int     shard_axis;         /* axis of the slab decomposition; -1 = not sharded */
+  double  shard_lo, shard_hi; /* this rank owns lo <= x[axis] < hi (output vertices in duplicate mode, cluster centres in exchange mode) */
+  float   ms_replicated;      /* device time of the phases of computeMapping every rank repeats (bounds, radius, binning, clustering) */
+  float   ms_collectives;     /* device time of the NCCL collectives of the last map */
+  /* execution_mode = minimal-compute */
+  int64_t evaluation_bytes;   /* bytes of the stored per-cluster evaluation operators */
+  float   ms_evaluation_offline; /* device time spent building them in the last computeMapping */
 } rbfmap_stats;
 int rbfmap_get_stats(const rbfmap_handle *h, rbfmap_stats *stats);
 
@@ -233,6 +259,10 @@ int rbfmap_eval_basis(int basis, double support_radius, double shape_parameter, 
 
 /* Test hook: the branch-free square root the kernels apply to squared vertex distances (host pointers). */
 int rbfmap_debug_dist_sqrt(const double *x, int64_t n, double *out);
+
+/* sizeof(rbfmap_config) and sizeof(rbfmap_stats) as compiled into the library: lets a binding written in another
+ * language (ctypes, cgo, JNI) verify its mirror of the two structs at load time. */
+void rbfmap_struct_sizes(int *config_bytes, int *stats_bytes);
 
 /* Library / device probe: number of visible CUDA devices (0 if none), compute capability of device 0. */
 int rbfmap_device_count(void);

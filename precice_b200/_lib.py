@@ -34,7 +34,7 @@ EXPORTS = [
     "rbfmap_has_computed_mapping", "rbfmap_destroy", "rbfmap_get_name", "rbfmap_last_error", "rbfmap_get_stats",
     "rbfmap_pum_get_clusters", "rbfmap_pum_get_cluster_ids", "rbfmap_eval_basis", "rbfmap_device_count",
     "rbfmap_device_info", "rbfmap_measure_fp64_peak", "rbfmap_debug_dist_sqrt", "rbfmap_nccl_unique_id", "rbfmap_distributed_init",
-    "rbfmap_partition_rows", "rbfmap_compute_mapping_just_in_time", "rbfmap_cache_create", "rbfmap_cache_reset", "rbfmap_cache_destroy",
+    "rbfmap_partition_rows", "rbfmap_partition_slabs", "rbfmap_struct_sizes", "rbfmap_compute_mapping_just_in_time", "rbfmap_cache_create", "rbfmap_cache_reset", "rbfmap_cache_destroy",
     "rbfmap_cache_update", "rbfmap_map_consistent_at", "rbfmap_map_conservative_at", "rbfmap_complete_just_in_time_mapping",
 ]
 
@@ -56,6 +56,9 @@ class Stats(C.Structure):
         ("max_n", C.c_int64), ("device_bytes", C.c_int64), ("iterations", C.c_int), ("residual", C.c_double),
         ("ms_compute_kernels", C.c_float), ("ms_map_kernels", C.c_float), ("ms_assembly_factor", C.c_float),
         ("kernel_launches", C.c_int),
+        ("n_clusters_global", C.c_int64), ("shard_axis", C.c_int), ("shard_lo", C.c_double), ("shard_hi", C.c_double),
+        ("ms_replicated", C.c_float), ("ms_collectives", C.c_float), ("evaluation_bytes", C.c_int64),
+        ("ms_evaluation_offline", C.c_float),
     ]
 
     def as_dict(self):
@@ -107,6 +110,7 @@ def lib():
         L.rbfmap_nccl_unique_id.argtypes = [C.c_char_p]
         L.rbfmap_distributed_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int]
         L.rbfmap_partition_rows.argtypes = [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.rbfmap_partition_slabs.argtypes = [C.POINTER(C.c_int64), C.c_int, C.c_int, C.c_int, ip]
         L.rbfmap_compute_mapping_just_in_time.argtypes = [vp, vp, C.c_int64]
         L.rbfmap_cache_create.argtypes = [vp, C.c_int, C.POINTER(vp)]
         L.rbfmap_cache_reset.argtypes = [vp, vp]
@@ -116,5 +120,12 @@ def lib():
         L.rbfmap_map_consistent_at.argtypes = [vp, vp, vp, C.c_int64, vp]
         L.rbfmap_map_conservative_at.argtypes = [vp, vp, vp, C.c_int64, vp]
         L.rbfmap_complete_just_in_time_mapping.argtypes = [vp, vp, vp]
+        L.rbfmap_struct_sizes.argtypes = [ip, ip]
+        L.rbfmap_struct_sizes.restype = None
+        a, b = C.c_int(0), C.c_int(0)
+        L.rbfmap_struct_sizes(C.byref(a), C.byref(b))
+        if (a.value, b.value) != (C.sizeof(Config), C.sizeof(Stats)):
+            raise ImportError(f"{LIB_PATH}: struct layout mismatch (library {a.value}/{b.value} bytes, binding "
+                              f"{C.sizeof(Config)}/{C.sizeof(Stats)}); rebuild the library")
         _lib = L
     return _lib

@@ -3,6 +3,7 @@
 #include "nccl_dyn.cuh"
 #include "pum.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -127,6 +128,21 @@ DeviceMapping::~DeviceMapping()
     DeviceScope scope(_device);
     cudaStreamDestroy(_stream);
   }
+}
+
+void DeviceMapping::uploadReplicated(double *dDst, const double *hSrc, int64_t count, cudaStream_t s) const
+{
+  if (count <= 0)
+    return;
+  if (!_group.connected()) {
+    RBF_CUDA(cudaMemcpyAsync(dDst, hSrc, static_cast<size_t>(count) * sizeof(double), cudaMemcpyHostToDevice, s));
+    return;
+  }
+  const int64_t slice = _group.sliceOf(count);
+  const int64_t b = std::min(count, slice * _group.rank), e = std::min(count, b + slice);
+  if (e > b)
+    RBF_CUDA(cudaMemcpyAsync(dDst + b, hSrc + b, static_cast<size_t>(e - b) * sizeof(double), cudaMemcpyHostToDevice, s));
+  _group.allGatherInPlace(dDst, slice, s);
 }
 
 double PhaseTrace::now()
@@ -264,12 +280,11 @@ int rbfmap_compute_mapping(rbfmap_handle *h, const double *input_xyz, int64_t n_
       return;
     cudaStream_t     s = h->impl->stream();
     AllocStreamScope allocScope(s);
-    h->dInXyz.alloc(3 * std::max<int64_t>(n_input, 1));
-    h->dOutXyz.alloc(3 * std::max<int64_t>(n_output, 1));
-    if (n_input > 0)
-      RBF_CUDA(cudaMemcpyAsync(h->dInXyz.p, input_xyz, 3 * n_input * sizeof(double), cudaMemcpyHostToDevice, s));
-    if (n_output > 0)
-      RBF_CUDA(cudaMemcpyAsync(h->dOutXyz.p, output_xyz, 3 * n_output * sizeof(double), cudaMemcpyHostToDevice, s));
+    const ShardGroup &grp = h->impl->group();
+    h->dInXyz.alloc(std::max<int64_t>(grp.padded(3 * n_input), 1));
+    h->dOutXyz.alloc(std::max<int64_t>(grp.padded(3 * n_output), 1));
+    h->impl->uploadReplicated(h->dInXyz.p, input_xyz, 3 * n_input, s);
+    h->impl->uploadReplicated(h->dOutXyz.p, output_xyz, 3 * n_output, s);
     RBF_CUDA(cudaStreamSynchronize(s));
     h->impl->computeMapping(h->dInXyz.p, n_input, h->dOutXyz.p, n_output);
     // the mapping keeps its own copies; release the staging buffers
@@ -378,12 +393,12 @@ static int mapHostImpl(rbfmap_handle *h, int mode, const double *in, int dims, d
     AllocStreamScope allocScope(s);
     const int64_t    nIn  = m->nInput() * dims;
     const int64_t nOut = m->nOutput() * dims;
-    if (h->dIn.n < static_cast<size_t>(std::max<int64_t>(nIn, 1)))
-      h->dIn.alloc(std::max<int64_t>(nIn, 1));
+    const int64_t nInPad = std::max<int64_t>(m->group().padded(nIn), 1);
+    if (h->dIn.n < static_cast<size_t>(nInPad))
+      h->dIn.alloc(nInPad);
     if (h->dOut.n < static_cast<size_t>(std::max<int64_t>(nOut, 1)))
       h->dOut.alloc(std::max<int64_t>(nOut, 1));
-    if (nIn > 0)
-      RBF_CUDA(cudaMemcpyAsync(h->dIn.p, in, nIn * sizeof(double), cudaMemcpyHostToDevice, s));
+    m->uploadReplicated(h->dIn.p, in, nIn, s); // distributed: 1/world of the values per rank over PCIe, all-gather over NVLink
     mapDeviceImpl(h, mode, h->dIn.p, dims, h->dOut.p);
     if (nOut > 0)
       RBF_CUDA(cudaMemcpyAsync(out, h->dOut.p, nOut * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -429,6 +444,15 @@ int rbfmap_partition_rows(int64_t n, int world, int rank, int64_t *begin, int64_
     return RBFMAP_ERR_INVALID;
   int64_t slice;
   partitionRows(n, world, rank, *begin, *end, slice);
+  return RBFMAP_OK;
+}
+
+int rbfmap_partition_slabs(const int64_t *histogram, int n_bins, int world, int halo_bins, int *cuts)
+{
+  if (!histogram || !cuts || n_bins < 1 || world < 1 || halo_bins < 0)
+    return RBFMAP_ERR_INVALID;
+  std::vector<long long> h(histogram, histogram + n_bins);
+  pumPartitionSlabs(h.data(), n_bins, world, halo_bins, cuts);
   return RBFMAP_OK;
 }
 
@@ -538,6 +562,14 @@ int rbfmap_debug_dist_sqrt(const double *x, int64_t n, double *out)
     RBF_CUDA(cudaDeviceSynchronize());
     RBF_CUDA(cudaMemcpy(out, b.p, n * sizeof(double), cudaMemcpyDeviceToHost));
   });
+}
+
+void rbfmap_struct_sizes(int *config_bytes, int *stats_bytes)
+{
+  if (config_bytes)
+    *config_bytes = static_cast<int>(sizeof(rbfmap_config));
+  if (stats_bytes)
+    *stats_bytes = static_cast<int>(sizeof(rbfmap_stats));
 }
 
 int rbfmap_device_count(void)

@@ -414,29 +414,14 @@ public:
   void computeMapping(const double *dInputXyz, int64_t nInput, const double *dOutputXyz, int64_t nOutput) override;
   void mapConsistent(const double *dIn, int dims, double *dOut) override { map(false, dIn, dims, dOut); }
   void mapConservative(const double *dIn, int dims, double *dOut) override { map(true, dIn, dims, dOut); }
-  ~GlobalIterativeMapping() override
-  {
-    if (_comm)
-      ncclApi().CommDestroy(_comm);
-  }
   void distributedInit(const char *uniqueId, int rank, int world) override
   {
-    if (world < 1 || rank < 0 || rank >= world)
-      throw MapError(RBFMAP_ERR_INVALID, "invalid rank / world size");
-    if (_comm) {
-      ncclApi().CommDestroy(_comm);
-      _comm = nullptr;
-    }
-    _rank  = rank;
-    _world = world;
+    if (world > 1 && !uniqueId)
+      throw MapError(RBFMAP_ERR_INVALID, "rbf-global-iterative needs an NCCL id to shard (all-gather / all-reduce per iteration).");
+    _group.init(uniqueId, rank, world);
     // the kept initial guess has the leading dimension of the previous world size
     _guess.release();
     _guessDims = 0;
-    if (world > 1) {
-      ncclUniqueId id;
-      std::memcpy(&id, uniqueId, sizeof(id));
-      RBF_NCCL(ncclApi().CommInitRank(&_comm, world, id, rank));
-    }
   }
   void clear() override
   {
@@ -460,8 +445,6 @@ private:
   void cg(double *b /*in: rhs, out: destroyed*/, double *x /*in: guess, out: solution*/, int nc);
   void setupPolynomial();
 
-  ncclComm_t     _comm  = nullptr;
-  int            _rank = 0, _world = 1;
   int64_t        _ldIn = 0; // leading dimension of the in-mesh vectors: world * slice
   int            _dead = 0;
   int64_t        _nIn = 0, _nOut = 0;
@@ -499,20 +482,20 @@ void GlobalIterativeMapping::apply(const BinGrid &rows, int64_t rb, int64_t re, 
 
 void GlobalIterativeMapping::allGatherSlices(double *v, int64_t ld, int nc, int64_t slice)
 {
-  if (_world == 1)
+  if (_group.world == 1)
     return;
   const NcclApi &n = ncclApi();
   RBF_NCCL(n.GroupStart());
   for (int c = 0; c < nc; ++c)
-    RBF_NCCL(n.AllGather(v + c * ld + _rank * slice, v + c * ld, static_cast<size_t>(slice), ncclDouble, _comm, _stream));
+    RBF_NCCL(n.AllGather(v + c * ld + _group.rank * slice, v + c * ld, static_cast<size_t>(slice), ncclDouble, _group.comm, _stream));
   RBF_NCCL(n.GroupEnd());
 }
 
 void GlobalIterativeMapping::allReduceScalars(double *d, int count)
 {
-  if (_world == 1)
+  if (_group.world == 1)
     return;
-  RBF_NCCL(ncclApi().AllReduce(d, d, static_cast<size_t>(count), ncclDouble, ncclSum, _comm, _stream));
+  RBF_NCCL(ncclApi().AllReduce(d, d, static_cast<size_t>(count), ncclDouble, ncclSum, _group.comm, _stream));
 }
 
 void GlobalIterativeMapping::setupPolynomial()
@@ -655,7 +638,7 @@ void GlobalIterativeMapping::cg(double *b, double *x, int nc)
 {
   const int64_t n = _nIn, ld = _ldIn;
   int64_t       rb, re, slice;
-  partitionRows(n, _world, _rank, rb, re, slice);
+  partitionRows(n, _group.world, _group.rank, rb, re, slice);
   const int64_t     m = re - rb;
   DevBuf<double>    p, Ap;
   DevBuf<CgScalars> sc;
@@ -741,10 +724,10 @@ void GlobalIterativeMapping::map(bool conservative, const double *dIn, int dims,
     RBF_CUDA(cudaMemsetAsync(dOut, 0, static_cast<size_t>(nRes) * dims * sizeof(double), _stream));
   if (_nIn > 0 && _nOut > 0) {
     int64_t ib, ie, islice, ob, oe, oslice;
-    partitionRows(_nIn, _world, _rank, ib, ie, islice);
-    partitionRows(_nOut, _world, _rank, ob, oe, oslice);
-    _ldIn              = islice * _world;
-    const int64_t ldOut = oslice * _world;
+    partitionRows(_nIn, _group.world, _group.rank, ib, ie, islice);
+    partitionRows(_nOut, _group.world, _group.rank, ob, oe, oslice);
+    _ldIn              = islice * _group.world;
+    const int64_t ldOut = oslice * _group.world;
     if (_guessDims != dims) { // initial guess: zero on first use, kept per component afterwards
       _guess.alloc(static_cast<size_t>(_ldIn) * dims);
       RBF_CUDA(cudaMemsetAsync(_guess.p, 0, static_cast<size_t>(_ldIn) * dims * sizeof(double), _stream));

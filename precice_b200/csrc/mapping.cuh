@@ -3,6 +3,7 @@
 
 #include "basis.cuh"
 #include "common.cuh"
+#include "nccl_dyn.cuh"
 
 #include <memory>
 #include <string>
@@ -40,13 +41,17 @@ public:
   virtual void        mapConservative(const double *dIn, int dims, double *dOut)                                       = 0;
   virtual void        clear()                                                                                          = 0;
   virtual std::string name() const                                                                                     = 0;
-  // joins a group of `world` processes (one GPU each) that execute the same calls on replicated inputs and shard the work;
-  // only rbf-global-iterative shards inside one mapping (rows of the CG operator), see global_iterative.cu
+  // joins a group of `world` processes (one GPU each) that execute the same calls on replicated inputs and shard the work:
+  // rbf-global-iterative shards the rows of its CG operator (global_iterative.cu), rbf-pum-direct its clusters (pum.cu)
   virtual void distributedInit(const char * /*ncclUniqueId, 128 bytes*/, int /*rank*/, int /*world*/)
   {
-    throw MapError(RBFMAP_ERR_UNSUPPORTED, "this mapping variant does not shard across devices: rbf-pum-direct shards by mesh partition "
-                                           "(one mapping per rank, no communication), rbf-global-direct stays on one device");
+    throw MapError(RBFMAP_ERR_UNSUPPORTED, "this mapping variant does not shard across devices: rbf-global-direct stays on one device");
   }
+  const ShardGroup &group() const { return _group; }
+  // Host -> device copy of `count` doubles that every rank of the group holds identically: each rank uploads only its
+  // 1/world slice over PCIe and the slices are all-gathered over NVLink. `dDst` must hold group().padded(count) doubles.
+  // Enqueued on `s`; the host buffer may be reused after `s` has been synchronised.
+  void uploadReplicated(double *dDst, const double *hSrc, int64_t count, cudaStream_t s) const;
 
   bool                 hasComputedMapping() const { return _computed; }
   bool                 isConservative() const { return _cfg.constraint == RBFMAP_CONSERVATIVE; }
@@ -60,6 +65,7 @@ public:
 protected:
   rbfmap_config _cfg;
   RbfParams     _rbf;
+  ShardGroup    _group;
   cudaStream_t  _stream   = nullptr;
   int           _device   = 0; // resolved CUDA device ordinal of this mapping (gpu-device-id)
   bool          _computed = false;

@@ -7,6 +7,8 @@
 
 #include "common.cuh"
 
+#include <cstring>
+
 namespace rbfmap {
 
 struct NcclApi {
@@ -29,6 +31,67 @@ const NcclApi &ncclApi();
     if (r_ != ncclSuccess)                                                                                                                \
       throw ::rbfmap::MapError(RBFMAP_ERR_CUDA, std::string("NCCL failure: ") + ::rbfmap::ncclApi().GetErrorString(r_) + " (" #call ")"); \
   } while (0)
+
+// The group of processes (one GPU each) that share one mapping: created by rbfmap_distributed_init from the 128-byte id
+// that rank 0 obtained from rbfmap_nccl_unique_id. world == 1 means "not distributed": every helper is then a no-op.
+struct ShardGroup {
+  ncclComm_t comm = nullptr;
+  int        rank = 0, world = 1;
+
+  ShardGroup()                              = default;
+  ShardGroup(const ShardGroup &)            = delete;
+  ShardGroup &operator=(const ShardGroup &) = delete;
+  ~ShardGroup() { destroy(); }
+  void destroy()
+  {
+    if (comm)
+      ncclApi().CommDestroy(comm);
+    comm  = nullptr;
+    rank  = 0;
+    world = 1;
+  }
+  void init(const char *uniqueId /*128 bytes*/, int rank_, int world_)
+  {
+    if (world_ < 1 || rank_ < 0 || rank_ >= world_)
+      throw MapError(RBFMAP_ERR_INVALID, "invalid rank / world size");
+    destroy();
+    rank  = rank_;
+    world = world_;
+    // uniqueId == nullptr: a group without communicator. The ranks shard the work but cannot exchange anything, so only
+    // collective-free sharding works (rbf-pum-direct, duplicate mode); every helper below is then a no-op.
+    if (world > 1 && uniqueId) {
+      ncclUniqueId id;
+      memcpy(&id, uniqueId, sizeof(id));
+      RBF_NCCL(ncclApi().CommInitRank(&comm, world, id, rank));
+    }
+  }
+  bool active() const { return world > 1; }
+  bool connected() const { return world > 1 && comm != nullptr; }
+  // length of the per-rank slice and of the padded buffer that all-gathers need for `count` elements
+  int64_t sliceOf(int64_t count) const { return (count + world - 1) / world; }
+  int64_t padded(int64_t count) const { return connected() ? sliceOf(count) * world : count; }
+  void    allReduceSum(double *v, int64_t count, cudaStream_t s) const
+  {
+    if (connected() && count > 0)
+      RBF_NCCL(ncclApi().AllReduce(v, v, static_cast<size_t>(count), ncclDouble, ncclSum, comm, s));
+  }
+  void allReduceSum(int *v, int64_t count, cudaStream_t s) const
+  {
+    if (connected() && count > 0)
+      RBF_NCCL(ncclApi().AllReduce(v, v, static_cast<size_t>(count), ncclInt32, ncclSum, comm, s));
+  }
+  void allReduceMin(int *v, int64_t count, cudaStream_t s) const
+  {
+    if (connected() && count > 0)
+      RBF_NCCL(ncclApi().AllReduce(v, v, static_cast<size_t>(count), ncclInt32, ncclMin, comm, s));
+  }
+  // every rank holds its slice [rank * slice, (rank + 1) * slice) of v (padded(count) elements); afterwards all of v
+  void allGatherInPlace(double *v, int64_t slice, cudaStream_t s) const
+  {
+    if (connected() && slice > 0)
+      RBF_NCCL(ncclApi().AllGather(v + rank * slice, v, static_cast<size_t>(slice), ncclDouble, comm, s));
+  }
+};
 
 // contiguous row slice of rank `rank` out of `world` (equal slice length ceil(n / world); the last slices may be short or empty)
 inline void partitionRows(int64_t n, int world, int rank, int64_t &begin, int64_t &end, int64_t &sliceLen)

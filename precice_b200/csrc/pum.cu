@@ -10,6 +10,8 @@
 #include <array>
 #include <climits>
 #include <cmath>
+#include <functional>
+#include <limits>
 #include <numeric>
 #include <sstream>
 
@@ -35,6 +37,16 @@ public:
 
   std::string name() const override { return "partition-of-unity RBF (cuda-executor)"; }
 
+  // one mapping sharded over the ranks of the group, see include/rbfmap.h
+  void distributedInit(const char *uniqueId, int rank, int world) override
+  {
+    if (_computed)
+      throw MapError(RBFMAP_ERR_STATE, "Please clear the mapping before joining a group."); // the shards depend on the group
+    if (world > 1 && !uniqueId && (_cfg.shard_mode == RBFMAP_SHARD_EXCHANGE || isConservative()))
+      throw MapError(RBFMAP_ERR_INVALID, "a group without NCCL id can only shard consistent mappings in duplicate mode (no collective).");
+    _group.init(uniqueId, rank, world);
+  }
+
   void computeMapping(const double *dInputXyz, int64_t nInput, const double *dOutputXyz, int64_t nOutput) override
   {
     computeImpl(dInputXyz, nInput, dOutputXyz, nOutput, cudaMemcpyDeviceToDevice);
@@ -47,6 +59,8 @@ public:
   // ---- just-in-time mapping ----
   void jitComputeMapping(const double *hMeshXyz, int64_t n) override
   {
+    if (_group.active())
+      throw MapError(RBFMAP_ERR_UNSUPPORTED, "just-in-time mapping is not available on a sharded mapping.");
     _jit = true;
     try {
       if (isConservative())
@@ -109,11 +123,14 @@ public:
     _buckets.order.release();
     _buckets.entries.release();
     _centerGrid = BinGrid();
+    _globalIdx.release();
     _jit        = false;
     _nClusters  = 0;
+    _nClustersGlobal = 0;
     _radius    = 0.0;
     _computed  = false;
     stats      = rbfmap_stats{};
+    stats.shard_axis = -1;
   }
 
   // inspection (tests)
@@ -137,11 +154,18 @@ private:
   void   map(bool conservative, const double *dIn, int dims, double *dOut);
   double estimateClusterRadius(const double bbMin[3], const double bbMax[3]);
   PumSolveArgs solveArgs() const;
+  // sharded mapping: replaces the complete centre list by the centres this rank processes
+  void shardClusters(const double bbMin[3], const double bbMax[3], const int latticeCount[3], bool haveLattice);
+  bool exchangeMode() const { return _group.active() && (_cfg.shard_mode == RBFMAP_SHARD_EXCHANGE || isConservative()); }
+  bool duplicateMode() const { return _group.active() && !exchangeMode(); }
 
   DevBuf<double>  _inXyz, _outXyz; // solver-side inMesh / outMesh
   int64_t         _nIn = 0, _nOut = 0;
   double          _radius    = 0.0;
-  int64_t         _nClusters = 0;
+  int64_t         _nClusters = 0; // clusters this rank processes (all of them unless the mapping is sharded)
+  int64_t         _nClustersGlobal = 0;
+  PumSlab         _slab{};        // sharded mapping: what this rank owns
+  DevBuf<int>     _globalIdx;     // sharded mapping: index of each local cluster in the complete list
   DevBuf<double>  _centers;
   PumMembership   _mem;
   PumScratch      _scratch; // survives clear(), see pum.cuh
@@ -221,6 +245,57 @@ double PumMapping::estimateClusterRadius(const double bbMin[3], const double bbM
   return radii[middle];
 }
 
+// SURVEY.md 8(e), include/rbfmap.h: slabs along the lattice axis with the most layers, cut so that the largest number of
+// clusters a rank processes is minimal. Every rank computes the same cuts from the same (complete) centre list.
+void PumMapping::shardClusters(const double bbMin[3], const double bbMax[3], const int latticeCount[3], bool haveLattice)
+{
+  const int    world = _group.world, rank = _group.rank;
+  const double inf   = std::numeric_limits<double>::infinity();
+  const bool   exch  = exchangeMode();
+  int          axis  = 0;
+  for (int d = 1; d < _cfg.dimensions; ++d)
+    if (latticeCount[d] > latticeCount[axis])
+      axis = d;
+  _slab.axis = axis;
+  double lo = -inf, hi = inf;
+  const double edge = bbMax[axis] - bbMin[axis];
+  if (!haveLattice || !(edge > 0.0)) {
+    // single-cluster fallback / degenerate axis: rank 0 takes everything
+    if (rank != 0)
+      lo = hi = inf;
+  } else {
+    constexpr int kBins    = 4096;
+    const double  binWidth = edge / kBins;
+    const auto    hist     = pumCentreHistogram(_centers.p, _nClusters, axis, bbMin[axis], binWidth, kBins, _stream);
+    // duplicate mode: a rank also processes the clusters within one radius of its slab
+    const int        haloBins = exch ? 0 : static_cast<int>(std::ceil(_radius / binWidth)) + 1;
+    std::vector<int> cuts(world + 1);
+    pumPartitionSlabs(hist.data(), kBins, world, haloBins, cuts.data());
+    if (rank > 0)
+      lo = bbMin[axis] + cuts[rank] * binWidth;
+    if (rank < world - 1)
+      hi = bbMin[axis] + cuts[rank + 1] * binWidth;
+    if (rank > 0 && cuts[rank] >= kBins)
+      lo = hi = inf; // more ranks than occupied bins
+    else if (!(lo < hi))
+      lo = hi = inf;
+  }
+  _slab.lo = lo;
+  _slab.hi = hi;
+  stats.shard_axis = axis;
+  stats.shard_lo   = lo;
+  stats.shard_hi   = hi;
+  // centres this rank processes: its own (exchange mode), or every centre whose sphere reaches into the slab (duplicate
+  // mode; |v - c| < r implies |v_a - c_a| < r, the margin covers the rounding of the comparison)
+  const double margin = exch ? 0.0 : _radius * (1.0 + 1e-12) + 1e-300;
+  double       selLo = lo - margin, selHi = hi + margin;
+  if (lo == inf) // empty slab
+    selLo = selHi = inf;
+  DevBuf<double> local;
+  _nClusters = pumSelectSlab(_centers.p, _nClustersGlobal, axis, selLo, selHi, local, _globalIdx, _stream);
+  _centers   = std::move(local);
+}
+
 void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const double *dOutputXyz, int64_t nOutput, cudaMemcpyKind kind)
 {
   if (_computed)
@@ -240,14 +315,17 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
   _nOut                = cons ? nInput : nOutput;
   if (_nIn > INT_MAX / 4 || _nOut > INT_MAX / 4)
     throw MapError(RBFMAP_ERR_UNSUPPORTED, "mesh too large for 32-bit vertex IDs");
-  _inXyz.alloc(3 * std::max<int64_t>(_nIn, 1));
-  _outXyz.alloc(3 * std::max<int64_t>(_nOut, 1));
+  EventTimer replicated(_stream);
+  replicated.start();
+  // sharded mapping: every rank uploads 1/world of each mesh over PCIe, the slices are all-gathered over NVLink
+  _inXyz.alloc(std::max<int64_t>(_group.padded(3 * _nIn), 1));
+  _outXyz.alloc(std::max<int64_t>(_group.padded(3 * _nOut), 1));
   trace.phase("alloc meshes");
   if (_nIn > 0) {
     if (kind == cudaMemcpyDeviceToDevice)
       deviceCopy(_inXyz.p, srcIn, 3 * _nIn, _stream);
     else
-      RBF_CUDA(cudaMemcpyAsync(_inXyz.p, srcIn, 3 * _nIn * sizeof(double), kind, _stream));
+      uploadReplicated(_inXyz.p, srcIn, 3 * _nIn, _stream);
   }
   // From host memory the outMesh travels on a second stream: bounds, cluster-radius estimate and binning of the inMesh
   // run while it is still in flight; the main stream waits for it (waitForOutMesh) right before its first use.
@@ -269,28 +347,39 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
       }
       RBF_CUDA(cudaEventRecord(_allocReady, _stream)); // the buffer comes from the stream-ordered pool of _stream
       RBF_CUDA(cudaStreamWaitEvent(_copyStream, _allocReady, 0));
-      RBF_CUDA(cudaMemcpyAsync(_outXyz.p, srcOut, 3 * _nOut * sizeof(double), kind, _copyStream));
+      if (_group.connected()) { // this rank's slice only; the all-gather is issued on the main stream in waitForOutMesh
+        const int64_t slice = _group.sliceOf(3 * _nOut);
+        const int64_t b = std::min(3 * _nOut, slice * _group.rank), e = std::min(3 * _nOut, b + slice);
+        if (e > b)
+          RBF_CUDA(cudaMemcpyAsync(_outXyz.p + b, srcOut + b, static_cast<size_t>(e - b) * sizeof(double), kind, _copyStream));
+      } else {
+        RBF_CUDA(cudaMemcpyAsync(_outXyz.p, srcOut, 3 * _nOut * sizeof(double), kind, _copyStream));
+      }
       RBF_CUDA(cudaEventRecord(_outReady, _copyStream));
       outCopy.s       = _copyStream;
       outCopy.pending = true;
     } else if (kind == cudaMemcpyDeviceToDevice) {
       deviceCopy(_outXyz.p, srcOut, 3 * _nOut, _stream);
     } else {
-      RBF_CUDA(cudaMemcpyAsync(_outXyz.p, srcOut, 3 * _nOut * sizeof(double), kind, _stream));
+      uploadReplicated(_outXyz.p, srcOut, 3 * _nOut, _stream);
     }
   }
   auto waitForOutMesh = [&] {
     if (outCopy.pending) {
       RBF_CUDA(cudaStreamWaitEvent(_stream, _outReady, 0));
       outCopy.pending = false; // ordered behind _stream from here on; every exit path below synchronises _stream
+      if (_group.connected())
+        _group.allGatherInPlace(_outXyz.p, _group.sliceOf(3 * _nOut), _stream);
     }
   };
 
-  stats       = rbfmap_stats{};
-  stats.n_in  = _nIn;
-  stats.n_out = _nOut;
-  _nClusters  = 0;
-  _radius     = 0.0;
+  stats            = rbfmap_stats{};
+  stats.shard_axis = -1;
+  stats.n_in       = _nIn;
+  stats.n_out      = _nOut;
+  _nClusters       = 0;
+  _nClustersGlobal = 0;
+  _radius          = 0.0;
 
   // impl/CreateClustering.hpp:314-316: nothing to do for empty meshes
   const bool jit = _jit; // CreateClustering.hpp:313: a just-in-time outMesh is empty by construction
@@ -306,6 +395,8 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
   auto edge = [&](int d) { return std::abs(bbMax[d] - bbMin[d]); };
 
   BinGrid inGrid, outGrid;
+  int     latticeCount[3] = {1, 1, 1};
+  bool    haveLattice     = false;
   if (static_cast<uint64_t>(_nIn) < static_cast<uint64_t>(_cfg.vertices_per_cluster) * 2) {
     // single-cluster fallback :352-359
     double cRadius = 0.0;
@@ -427,10 +518,22 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
     trace.phase("compact");
     if (_nClusters == 0)
       throw MapError(RBFMAP_ERR_EMPTY, "Too many vertices have been filtered out."); // :502
+    for (int d = 0; d < 3; ++d)
+      latticeCount[d] = static_cast<int>(nLocal[d]);
+    haveLattice = true;
   }
+  _nClustersGlobal = _nClusters;
+  // ---- everything up to here is repeated by every rank of a sharded mapping (identical, deterministic results) ----
+  stats.ms_replicated = replicated.stop();
+  if (_group.active()) {
+    shardClusters(bbMin, bbMax, latticeCount, haveLattice);
+    trace.phase("shard");
+  }
+  const PumSlab *outSlab = duplicateMode() ? &_slab : nullptr;
 
-  stats.n_clusters     = _nClusters;
-  stats.cluster_radius = _radius;
+  stats.n_clusters        = _nClusters;
+  stats.n_clusters_global = _nClustersGlobal;
+  stats.cluster_radius    = _radius;
 
   // per-cluster vertex sets (SphericalVertexCluster.hpp:153-162)
   _wsum.alloc(_nOut);
@@ -444,12 +547,24 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
     computeBounds(_centers.p, _nClusters, cMin, cMax, _stream);
     _centerGrid.build(_centers.p, _nClusters, cMin, cMax, 0.5 * _radius, _stream);
   }
-  pumBuildMembership(_centers.p, _nClusters, inGrid, outGrid, _radius, _mem, _scratch, _wsum.p, _wcount.p, _inXyz.p, _outXyz.p, _inRec, _outRec, _stream);
+  // sharded mapping, exchange mode: the weight sums of an output vertex span clusters of two ranks at a cut
+  const auto weightsComplete = [&] {
+    _group.allReduceSum(_wsum.p, _nOut, _stream);
+    _group.allReduceSum(_wcount.p, _nOut, _stream);
+  };
+  if (_nClusters > 0) {
+    pumBuildMembership(_centers.p, _nClusters, inGrid, outGrid, _radius, _mem, _scratch, _wsum.p, _wcount.p, _inXyz.p, _outXyz.p, _inRec, _outRec, _stream,
+                       outSlab, exchangeMode() ? std::function<void()>(weightsComplete) : std::function<void()>());
+  } else { // a rank of a sharded mapping without clusters still takes part in the collectives
+    _mem = PumMembership();
+    if (exchangeMode())
+      weightsComplete();
+  }
   trace.phase("membership");
 
   // partition-of-unity weight sums (PartitionOfUnityMapping.hpp:263-276, 290-341)
   {
-    const int64_t bad = pumFirstUnassigned(_wcount.p, _nOut, _stream);
+    const int64_t bad = pumFirstUnassigned(_wcount.p, _nOut, _stream, _outXyz.p, outSlab, _group.active() ? &_group : nullptr);
     if (bad >= 0) {
       double v[3];
       RBF_CUDA(cudaMemcpy(v, _outXyz.p + 3 * bad, sizeof(v), cudaMemcpyDeviceToHost));
@@ -469,22 +584,29 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
 
   trace.phase("weights");
   // size buckets + statistics (device pass over the per-cluster counts)
-  pumClassify(_mem, _nClusters, _buckets, stats, _stream);
-  stats.n_clusters     = _nClusters;
-  stats.cluster_radius = _radius;
+  if (_nClusters > 0) {
+    pumClassify(_mem, _nClusters, _buckets, stats, _stream);
+  } else {
+    for (int b = 0; b <= kNumBuckets; ++b)
+      _buckets.start[b] = 0;
+  }
+  stats.n_clusters        = _nClusters;
+  stats.n_clusters_global = _nClustersGlobal;
+  stats.cluster_radius    = _radius;
   trace.phase("classify");
   if (stats.max_n > kPumMaxClusterVertices)
     throw MapError(RBFMAP_ERR_UNSUPPORTED, "rbf-pum-direct: a cluster with " + std::to_string(stats.max_n) + " vertices exceeds the supported cluster size of " +
                                                std::to_string(kPumMaxClusterVertices) + " vertices; reduce \"vertices-per-cluster\".");
   // separated polynomial + assembly/factorisation of all local systems
-  _poly.alloc(_nClusters);
+  _poly.alloc(std::max<int64_t>(_nClusters, 1));
   if (_mat.n < static_cast<size_t>(std::max<int64_t>(_mem.sumTri, 1))) {
     RBF_CUDA(cudaStreamSynchronize(_stream));
     _mat.reserve(static_cast<size_t>(_mem.sumTri) + static_cast<size_t>(_mem.sumTri) / 16 + 2);
   }
   const PumSolveArgs args = solveArgs();
   trace.phase("alloc factors");
-  pumPolySetup(args, _nClusters, _cfg.polynomial, _stream);
+  if (_nClusters > 0)
+    pumPolySetup(args, _nClusters, _cfg.polynomial, _stream);
   trace.phase("polySetup");
   DevBuf<int> fail;
   fail.alloc(1);
@@ -495,6 +617,9 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
   pumFactor(args, _buckets, fail.p, _stream);
   stats.ms_assembly_factor = tf.stop();
   trace.phase("assembly + factorisation");
+  if (_group.active()) { // every rank raises the error of the failing rank (the next collective would wait for it forever)
+    _group.allReduceMin(fail.p, 1, _stream);
+  }
   int failed = INT_MAX;
   RBF_CUDA(cudaMemcpy(&failed, fail.p, sizeof(int), cudaMemcpyDeviceToHost));
   if (failed != INT_MAX) {
@@ -531,6 +656,13 @@ void PumMapping::map(bool conservative, const double *dIn, int dims, double *dOu
       pumMapConservative(args, _buckets, dIn, dims, dOut, _stream);
     else
       pumMapConsistent(args, _buckets, dIn, dims, dOut, _stream);
+  }
+  stats.ms_collectives = 0.f;
+  if (exchangeMode()) { // every cluster has one owner: the partial blends of the ranks add up to the result
+    EventTimer tc(_stream);
+    tc.start();
+    _group.allReduceSum(dOut, nRes * dims, _stream);
+    stats.ms_collectives = tc.stop();
   }
   stats.ms_map_kernels = t.stop();
   stats.kernel_launches += g_launches - launchesBefore;

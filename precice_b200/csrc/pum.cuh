@@ -2,10 +2,12 @@
 // kernels (pum_cluster.cu), the per-cluster algebra kernels (pum_solve.cu) and the host driver (pum.cu).
 #pragma once
 
+#include <functional>
 #include <vector>
 
 #include "basis.cuh"
 #include "common.cuh"
+#include "nccl_dyn.cuh"
 #include "spatial.cuh"
 
 namespace rbfmap {
@@ -68,12 +70,29 @@ struct PumScratch {
   size_t      bytes() const { return slotIn.bytes() + slotOut.bytes(); }
 };
 
+// Slab of a sharded mapping: this rank owns what lies in lo <= x[axis] < hi
+struct PumSlab {
+  int    axis = 0;
+  double lo = 0.0, hi = 0.0;
+};
+
+// outSlab (may be null): only the output vertices inside the slab are listed and weighted (sharded mapping, duplicate mode).
+// weightsComplete (may be empty) runs after the weight sums of this rank's clusters are accumulated and before the
+// normalised weights are derived from them (sharded mapping, exchange mode: all-reduce of the sums).
 void    pumBuildMembership(const double *dCenters, int64_t nClusters, const BinGrid &inMesh, const BinGrid &outMesh, double radius, PumMembership &m,
                            PumScratch &scratch, double *wsum, int *wcount, const double *inXyz, const double *outXyz, DevBuf<double> &inRec,
-                           DevBuf<double4> &outRec, cudaStream_t s);
+                           DevBuf<double4> &outRec, cudaStream_t s, const PumSlab *outSlab = nullptr,
+                           const std::function<void()> &weightsComplete = {});
+// sharded mapping: histogram of the centre coordinates along `axis`, selection of the centres inside [lo, hi) (order
+// preserved; globalIdx = index in the complete list), and the host-side choice of the cut positions
+std::vector<long long> pumCentreHistogram(const double *dCenters, int64_t n, int axis, double lo, double binWidth, int nBins, cudaStream_t s);
+int64_t pumSelectSlab(const double *dCenters, int64_t n, int axis, double lo, double hi, DevBuf<double> &out, DevBuf<int> &globalIdx, cudaStream_t s);
+void    pumPartitionSlabs(const long long *hist, int nBins, int world, int haloBins, int *cuts /* world + 1 */);
 bool    pumBuildPointMembership(const double *dCenters, int64_t nClusters, const BinGrid &points, double radius, PumScratch &scratch, DevBuf<int> &nPts,
                                 DevBuf<int64_t> &off, DevBuf<int> &ids, double *wsum, int *wcount, cudaStream_t s);
-int64_t pumFirstUnassigned(const int *wcount, int64_t nOut, cudaStream_t s); // -1: every out-vertex lies in a cluster
+// -1: every out-vertex (of the slab, if given) lies in a cluster; with a group the lowest index over all ranks
+int64_t pumFirstUnassigned(const int *wcount, int64_t nOut, cudaStream_t s, const double *outXyz = nullptr, const PumSlab *slab = nullptr,
+                           const ShardGroup *group = nullptr);
 
 // Per-cluster separated-polynomial record (RadialBasisFctSolver.hpp:377-410 condensed).
 //  mode 0: no polynomial

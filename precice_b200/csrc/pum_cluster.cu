@@ -10,6 +10,7 @@
 #include "pum_device.cuh"
 
 #include <algorithm>
+#include <functional>
 
 namespace rbfmap {
 namespace {
@@ -310,10 +311,19 @@ __device__ void warpSortSegment(int *seg, int n, int *stage, int stageCap, int l
 
 constexpr int kSortCap = 1024; // ints staged per warp
 
-__device__ void gatherMembers(const BinGridView &g, double cx, double cy, double cz, double r, int *seg, int lane)
+// slab filter of the sharded mapping (pum.cuh, PumSlab): the vertex at binned position pos belongs to this rank
+__device__ __forceinline__ bool inSlab(const BinGridView &g, int pos, const PumSlab &slab)
+{
+  const double t = g.xyz[3 * static_cast<long long>(pos) + slab.axis];
+  return t >= slab.lo && t < slab.hi;
+}
+
+__device__ void gatherMembers(const BinGridView &g, double cx, double cy, double cz, double r, int *seg, int lane, const PumSlab *slab = nullptr)
 {
   int base = 0;
   forCandidatesWarp<2>(g, cx, cy, cz, lane, [&](int pos, bool valid) {
+    if (slab && valid)
+      valid = inSlab(g, pos, *slab);
     const bool     hit = valid && __dsqrt_rn(sqDist3(cx, cy, cz, g.xyz[3 * pos], g.xyz[3 * pos + 1], g.xyz[3 * pos + 2])) < r;
     const unsigned m   = __ballot_sync(0xffffffffu, hit);
     if (hit)
@@ -333,13 +343,16 @@ constexpr int kSlotCap = 128;
 // WEIGHTS (out-mesh pass): every vertex within rW of the centre also receives this cluster's partition-of-unity weight,
 // PartitionOfUnityMapping.hpp:306-333 seen from the cluster side: w_c = C2(|x - c| / r) is added to the weight sum of
 // the vertex and its cluster count is incremented (the reference loops over the clusters of a vertex instead).
-template <bool WEIGHTS>
+template <bool WEIGHTS, bool SLAB = false>
 __device__ __forceinline__ int gatherToShared(const BinGridView &g, double cx, double cy, double cz, double r, int *stage, int *stagePos, int lane, double rW = 0.0,
-                                              double rinv = 0.0, double *__restrict__ wsum = nullptr, int *__restrict__ wcount = nullptr)
+                                              double rinv = 0.0, double *__restrict__ wsum = nullptr, int *__restrict__ wcount = nullptr,
+                                              const PumSlab *slab = nullptr)
 {
   int base = 0;
   forCandidatesWarp<2>(g, cx, cy, cz, lane, [&](int pos, bool valid) {
     double d = 1.7976931348623157e308;
+    if (SLAB && valid) // sharded mapping: only the output vertices this rank owns are listed and weighted
+      valid = inSlab(g, pos, *slab);
     if (valid) // computeWeight (SphericalVertexCluster.hpp:337-344): squared difference (centre, vertex)
       d = __dsqrt_rn(sqDist3(cx, cy, cz, g.xyz[3 * pos], g.xyz[3 * pos + 1], g.xyz[3 * pos + 2]));
     const bool     hit = d < r;
@@ -410,9 +423,10 @@ __device__ __forceinline__ void rankSortToGlobal(const int *stage, const int *pa
   }
 }
 
+template <bool SLAB>
 __global__ void memberGatherKernel(const double *__restrict__ centers, int64_t nClusters, BinGridView gin, BinGridView gout, double rIn, double rOut,
                                    int *__restrict__ nIn, int *__restrict__ nOut, long long *__restrict__ tri, int *__restrict__ slotIn,
-                                   int *__restrict__ slotOut, int *__restrict__ overflow, double *__restrict__ wsum, int *__restrict__ wcount)
+                                   int *__restrict__ slotOut, int *__restrict__ overflow, double *__restrict__ wsum, int *__restrict__ wcount, PumSlab slab)
 {
   __shared__ __align__(16) int stage[kWarpsPerBlock][kSlotCap];
   __shared__ int               stagePos[kWarpsPerBlock][kSlotCap];
@@ -425,7 +439,7 @@ __global__ void memberGatherKernel(const double *__restrict__ centers, int64_t n
   if (ci <= kSlotCap)
     rankSortToGlobal(stage[w], stagePos[w], ci, slotIn + c * kSlotCap, lane);
   __syncwarp();
-  const int co = gatherToShared<true>(gout, cx, cy, cz, rOut, stage[w], stagePos[w], lane, rIn, 1.0 / rIn, wsum, wcount);
+  const int co = gatherToShared<true, SLAB>(gout, cx, cy, cz, rOut, stage[w], stagePos[w], lane, rIn, 1.0 / rIn, wsum, wcount, &slab);
   if (co <= kSlotCap)
     rankSortToGlobal(stage[w], stagePos[w], co, slotOut + c * kSlotCap, lane);
   if (lane == 0) {
@@ -475,7 +489,8 @@ __global__ void memberPackKernel(int64_t nClusters, const int *__restrict__ nIn,
 }
 
 __global__ void memberFillKernel(const double *__restrict__ centers, int64_t nClusters, BinGridView gin, BinGridView gout, double rIn, double rOut,
-                                 const long long *__restrict__ inOff, const long long *__restrict__ outOff, int *__restrict__ inIds, int *__restrict__ outIds)
+                                 const long long *__restrict__ inOff, const long long *__restrict__ outOff, int *__restrict__ inIds, int *__restrict__ outIds,
+                                 PumSlab slab, bool useSlab)
 {
   __shared__ int stage[kWarpsPerBlock][kSortCap];
   const int64_t  c    = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
@@ -487,16 +502,55 @@ __global__ void memberFillKernel(const double *__restrict__ centers, int64_t nCl
   const int    ni = static_cast<int>(inOff[c + 1] - inOff[c]), no = static_cast<int>(outOff[c + 1] - outOff[c]);
   gatherMembers(gin, cx, cy, cz, rIn, segIn, lane);
   warpSortSegment(segIn, ni, stage[w], kSortCap, lane);
-  gatherMembers(gout, cx, cy, cz, rOut, segOut, lane);
+  gatherMembers(gout, cx, cy, cz, rOut, segOut, lane, useSlab ? &slab : nullptr);
   warpSortSegment(segOut, no, stage[w], kSortCap, lane);
 }
 
 // ---- out-vertices that no cluster covers (PartitionOfUnityMapping.hpp:312-320) ----
-__global__ void unassignedKernel(const int *__restrict__ wcount, int64_t nOut, int *__restrict__ firstUnassigned)
+__global__ void unassignedKernel(const int *__restrict__ wcount, int64_t nOut, int *__restrict__ firstUnassigned, const double *__restrict__ outXyz,
+                                 PumSlab slab, bool useSlab)
 {
   const int64_t v = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  if (v < nOut && wcount[v] == 0)
+  if (v < nOut && wcount[v] == 0) {
+    if (useSlab) { // sharded mapping: only the vertices this rank owns have complete counts
+      const double t = outXyz[3 * v + slab.axis];
+      if (!(t >= slab.lo && t < slab.hi))
+        return;
+    }
     atomicMin(firstUnassigned, static_cast<int>(v));
+  }
+}
+
+// ---- sharded mapping: slab decomposition of the (global) centre list ----
+__global__ void centreHistogramKernel(const double *__restrict__ centers, int64_t n, int axis, double lo, double invBin, int nBins, int *__restrict__ hist)
+{
+  const int64_t c = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (c >= n)
+    return;
+  const double t = floor((centers[3 * c + axis] - lo) * invBin);
+  atomicAdd(&hist[static_cast<int>(fmin(fmax(t, 0.0), static_cast<double>(nBins - 1)))], 1);
+}
+
+__global__ void slabFlagKernel(const double *__restrict__ centers, int64_t n, int axis, double lo, double hi, int *__restrict__ keep)
+{
+  const int64_t c = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (c < n) {
+    const double t = centers[3 * c + axis];
+    keep[c]        = (t >= lo && t < hi) ? 1 : 0;
+  }
+}
+
+__global__ void slabCompactKernel(int64_t n, const int *__restrict__ keep, const int *__restrict__ pos, const double *__restrict__ centers,
+                                  double *__restrict__ out, int *__restrict__ globalIdx)
+{
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < n && keep[i]) {
+    const int64_t o = pos[i];
+    out[3 * o]      = centers[3 * i];
+    out[3 * o + 1]  = centers[3 * i + 1];
+    out[3 * o + 2]  = centers[3 * i + 2];
+    globalIdx[o]    = static_cast<int>(i);
+  }
 }
 
 // ---- size buckets + statistics ----------------------------------------------------------------
@@ -676,8 +730,9 @@ int64_t PumClustering::compact(DevBuf<double> &out, cudaStream_t s)
 
 void pumBuildMembership(const double *dCenters, int64_t nClusters, const BinGrid &inMesh, const BinGrid &outMesh, double radius, PumMembership &m,
                         PumScratch &scratch, double *wsum, int *wcount, const double *inXyz, const double *outXyz, DevBuf<double> &inRec,
-                        DevBuf<double4> &outRec, cudaStream_t s)
+                        DevBuf<double4> &outRec, cudaStream_t s, const PumSlab *outSlab, const std::function<void()> &weightsComplete)
 {
+  const PumSlab slab = outSlab ? *outSlab : PumSlab{};
   const double rOut = radius - kZeroDiff; // SphericalVertexCluster.hpp:155
   DevBuf<int>  nIn, nOut;
   nIn.alloc(nClusters);
@@ -698,9 +753,15 @@ void pumBuildMembership(const double *dCenters, int64_t nClusters, const BinGrid
   DevBuf<int> overflow;
   overflow.alloc(1);
   RBF_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), s));
-  memberGatherKernel<<<warpGrid(nClusters), kBlockThreads, 0, s>>>(dCenters, nClusters, inMesh.view(), outMesh.view(), radius, rOut, m.nIn.p, m.nOut.p,
-                                                                  reinterpret_cast<long long *>(m.tri.p), slotIn.p, slotOut.p, overflow.p, wsum, wcount);
+  if (outSlab)
+    memberGatherKernel<true><<<warpGrid(nClusters), kBlockThreads, 0, s>>>(dCenters, nClusters, inMesh.view(), outMesh.view(), radius, rOut, m.nIn.p, m.nOut.p,
+                                                                          reinterpret_cast<long long *>(m.tri.p), slotIn.p, slotOut.p, overflow.p, wsum, wcount, slab);
+  else
+    memberGatherKernel<false><<<warpGrid(nClusters), kBlockThreads, 0, s>>>(dCenters, nClusters, inMesh.view(), outMesh.view(), radius, rOut, m.nIn.p, m.nOut.p,
+                                                                           reinterpret_cast<long long *>(m.tri.p), slotIn.p, slotOut.p, overflow.p, wsum, wcount, slab);
   RBF_LAUNCHED();
+  if (weightsComplete) // sharded mapping, exchange mode: the weight sums of the other ranks' clusters are added here
+    weightsComplete();
   exclusiveScan(m.nIn.p, m.inOff.p, nClusters, s);
   exclusiveScan(m.nOut.p, m.outOff.p, nClusters, s);
   exclusiveScan(m.tri.p, m.matOff.p, nClusters, s);
@@ -726,7 +787,7 @@ void pumBuildMembership(const double *dCenters, int64_t nClusters, const BinGrid
   } else { // clusters beyond the slot size: two-pass fill with the (exact) sizes counted above, then the records
     memberFillKernel<<<warpGrid(nClusters), kBlockThreads, 0, s>>>(dCenters, nClusters, inMesh.view(), outMesh.view(), radius, rOut,
                                                                   reinterpret_cast<const long long *>(m.inOff.p), reinterpret_cast<const long long *>(m.outOff.p),
-                                                                  m.inIds.p, m.outIds.p);
+                                                                  m.inIds.p, m.outIds.p, slab, outSlab != nullptr);
     RBF_LAUNCHED();
     PumSolveArgs a{};
     a.radius = radius;
@@ -857,15 +918,17 @@ void pumBuildInRecords(const PumSolveArgs &a, int64_t sumIn, double *rec, cudaSt
   RBF_CUDA(cudaGetLastError());
 }
 
-int64_t pumFirstUnassigned(const int *wcount, int64_t nOut, cudaStream_t s)
+int64_t pumFirstUnassigned(const int *wcount, int64_t nOut, cudaStream_t s, const double *outXyz, const PumSlab *slab, const ShardGroup *group)
 {
   DevBuf<int> first;
   first.alloc(1);
   RBF_CUDA(cudaMemsetAsync(first.p, 0x7f, sizeof(int), s));
   if (nOut > 0) {
-    unassignedKernel<<<divUp(nOut, 256), 256, 0, s>>>(wcount, nOut, first.p);
+    unassignedKernel<<<divUp(nOut, 256), 256, 0, s>>>(wcount, nOut, first.p, outXyz, slab ? *slab : PumSlab{}, slab != nullptr);
     RBF_LAUNCHED();
   }
+  if (group) // every rank reports the same (lowest) unassigned vertex, so that all ranks raise the same error
+    group->allReduceMin(first.p, 1, s);
   int f = 0;
   RBF_CUDA(cudaMemcpyAsync(&f, first.p, sizeof(int), cudaMemcpyDeviceToHost, s));
   RBF_CUDA(cudaStreamSynchronize(s));
@@ -875,6 +938,93 @@ int64_t pumFirstUnassigned(const int *wcount, int64_t nOut, cudaStream_t s)
 } // namespace rbfmap
 
 namespace rbfmap {
+std::vector<long long> pumCentreHistogram(const double *dCenters, int64_t n, int axis, double lo, double binWidth, int nBins, cudaStream_t s)
+{
+  DevBuf<int> hist;
+  hist.alloc(nBins);
+  RBF_CUDA(cudaMemsetAsync(hist.p, 0, nBins * sizeof(int), s));
+  if (n > 0) {
+    centreHistogramKernel<<<divUp(n, 256), 256, 0, s>>>(dCenters, n, axis, lo, binWidth > 0 ? 1.0 / binWidth : 0.0, nBins, hist.p);
+    RBF_LAUNCHED();
+  }
+  std::vector<int> h(nBins);
+  RBF_CUDA(cudaMemcpyAsync(h.data(), hist.p, nBins * sizeof(int), cudaMemcpyDeviceToHost, s));
+  RBF_CUDA(cudaStreamSynchronize(s));
+  return std::vector<long long>(h.begin(), h.end());
+}
+
+int64_t pumSelectSlab(const double *dCenters, int64_t n, int axis, double lo, double hi, DevBuf<double> &out, DevBuf<int> &globalIdx, cudaStream_t s)
+{
+  if (n == 0) {
+    out.alloc(3);
+    globalIdx.alloc(1);
+    return 0;
+  }
+  DevBuf<int> keep, pos;
+  keep.alloc(n);
+  pos.alloc(n + 1);
+  const int grid = divUp(n, 256);
+  slabFlagKernel<<<grid, 256, 0, s>>>(dCenters, n, axis, lo, hi, keep.p);
+  RBF_LAUNCHED();
+  exclusiveScan(keep.p, pos.p, n, s);
+  int count = 0;
+  RBF_CUDA(cudaMemcpyAsync(&count, pos.p + n, sizeof(int), cudaMemcpyDeviceToHost, s));
+  RBF_CUDA(cudaStreamSynchronize(s));
+  out.alloc(3 * static_cast<size_t>(std::max(count, 1)));
+  globalIdx.alloc(std::max(count, 1));
+  if (count > 0) {
+    slabCompactKernel<<<grid, 256, 0, s>>>(n, keep.p, pos.p, dCenters, out.p, globalIdx.p);
+    RBF_LAUNCHED();
+  }
+  RBF_CUDA(cudaGetLastError());
+  return count;
+}
+
+// Cut positions (bin indices 0 = c_0 <= c_1 <= ... <= c_world = nBins) of a slab decomposition that minimises the largest
+// number of centres a rank processes: rank r processes the bins [c_r - halo, c_{r+1} + halo).
+void pumPartitionSlabs(const long long *hist, int nBins, int world, int haloBins, int *cuts)
+{
+  std::vector<long long> P(nBins + 1, 0);
+  for (int b = 0; b < nBins; ++b)
+    P[b + 1] = P[b] + hist[b];
+  auto load = [&](int c0, int c1) { return P[std::min(nBins, c1 + haloBins)] - P[std::max(0, c0 - haloBins)]; };
+  auto sweep = [&](long long T, int *out) { // greedy: every rank takes as many bins as T allows
+    int c = 0;
+    if (out)
+      out[0] = 0;
+    for (int r = 0; r < world; ++r) {
+      int lo = c, hi = nBins; // largest e in [c, nBins] with load(c, e) <= T (load is monotone in e)
+      if (load(c, c) > T)
+        return false;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) / 2;
+        if (load(c, mid) <= T)
+          lo = mid;
+        else
+          hi = mid - 1;
+      }
+      c = r == world - 1 ? (lo == nBins ? nBins : -1) : lo;
+      if (c < 0)
+        return false;
+      if (out)
+        out[r + 1] = c;
+    }
+    return true;
+  };
+  long long lo = 0, hi = P[nBins];
+  while (lo < hi) {
+    const long long mid = (lo + hi) / 2;
+    if (sweep(mid, nullptr))
+      hi = mid;
+    else
+      lo = mid + 1;
+  }
+  sweep(lo, cuts);
+  // the greedy sweep fills the first ranks and may leave the last ones short; a backward pass would not change the
+  // maximum, which is what bounds the step time
+  cuts[world] = nBins;
+}
+
 void pumClassify(const PumMembership &m, int64_t nClusters, PumBuckets &b, rbfmap_stats &stats, cudaStream_t s)
 {
   DevBuf<unsigned long long> acc;

@@ -169,9 +169,11 @@ class _Mapping:
     def getName(self) -> str:
         return self._L.rbfmap_get_name(self._h).decode()
 
-    # -- multi-GPU (rbf-global-iterative only, see include/rbfmap.h)
-    def distributedInit(self, unique_id: bytes, rank: int, world: int):
-        assert len(unique_id) == 128
+    # -- multi-GPU: one mapping sharded over a group of ranks (see include/rbfmap.h)
+    def distributedInit(self, unique_id, rank: int, world: int):
+        """unique_id: the 128 bytes of nccl_unique_id() (broadcast from rank 0), or None for a group without communicator
+        (rbf-pum-direct, consistent, duplicate mode only: no collective is needed)."""
+        assert unique_id is None or len(unique_id) == 128
         self._check(self._L.rbfmap_distributed_init(self._h, unique_id, rank, world))
 
     # -- extras

@@ -42,7 +42,10 @@ def test_struct_layouts_match_header():
     assert cfg.execution_mode == _lib.EXECUTION_MODE["minimal-memory"]  # PartitionOfUnityMapping.hpp:57
     assert cfg.shard_mode == _lib.SHARD_MODE["duplicate"] and cfg.deterministic == 0
     assert C.sizeof(_lib.Config) == 104
-    assert C.sizeof(_lib.Stats) == 120
+    assert C.sizeof(_lib.Stats) == 176
+    a, b = C.c_int(0), C.c_int(0)
+    _lib.lib().rbfmap_struct_sizes(C.byref(a), C.byref(b))  # what the compiler laid out
+    assert (a.value, b.value) == (C.sizeof(_lib.Config), C.sizeof(_lib.Stats))
 
 
 def test_enum_values_follow_reference():
@@ -86,6 +89,38 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "rbf_oracle" not in text, os.path.join(dirpath, f)
+
+
+def test_partition_slabs_host_helper():
+    """Slab cuts of the sharded rbf-pum-direct: monotone, cover all bins, and no other choice of cuts has a
+    smaller maximum load (brute force on small cases)."""
+    import itertools
+    from precice_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(5)
+
+    def cuts_of(hist, world, halo):
+        h = np.ascontiguousarray(hist, dtype=np.int64)
+        c = (C.c_int * (world + 1))()
+        assert L.rbfmap_partition_slabs(h.ctypes.data_as(C.POINTER(C.c_int64)), len(h), world, halo, c) == 0
+        return list(c)
+
+    def max_load(hist, cuts, halo):
+        P = np.concatenate([[0], np.cumsum(hist)])
+        n = len(hist)
+        return max(P[min(n, b + halo)] - P[max(0, a - halo)] for a, b in zip(cuts, cuts[1:]))
+
+    for n_bins, world, halo in ((12, 3, 0), (12, 3, 1), (10, 4, 2), (9, 2, 0), (8, 8, 0), (6, 1, 3)):
+        for _ in range(5):
+            hist = rng.integers(0, 20, n_bins)
+            cuts = cuts_of(hist, world, halo)
+            assert cuts[0] == 0 and cuts[-1] == n_bins and all(a <= b for a, b in zip(cuts, cuts[1:]))
+            best = min(max_load(hist, [0, *inner, n_bins], halo)
+                       for inner in itertools.combinations_with_replacement(range(n_bins + 1), world - 1))
+            assert max_load(hist, cuts, halo) == best
+    # uniform histogram: equal slabs
+    cuts = cuts_of(np.full(4096, 230), 8, 0)
+    assert cuts == [512 * r for r in range(9)]
 
 
 def test_partition_rows_host_helper():
