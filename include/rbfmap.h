@@ -158,6 +158,13 @@ int rbfmap_map_conservative_at(rbfmap_handle *h, rbfmap_cache *cache, const doub
  * result to `out` (n*dims doubles on the mesh), like the reference accumulates into its buffer. */
 int rbfmap_complete_just_in_time_mapping(rbfmap_handle *h, rbfmap_cache *cache, double *out);
 
+/* Page-locked host memory for the adapter's staging buffers (cudaHostAlloc / cudaFreeHost): the adapter has to pack
+ * mesh.vertex(i).rawCoords() into a contiguous double[n][3] anyway (the reference's own device path does the same,
+ * BatchedRBFSolver.hpp:250-271); packing into a buffer from rbfmap_host_alloc lets the host-pointer entry points copy
+ * at full PCIe speed and asynchronously. Pageable pointers are accepted everywhere, just slower (driver-staged). */
+int  rbfmap_host_alloc(void **ptr, int64_t bytes);
+void rbfmap_host_free(void *ptr);
+
 /* Mapping::map(Sample, VectorXd&) dispatch (mapping/Mapping.cpp:158-173): conservative ->
  * mapConservative, otherwise mapConsistent. `in` has n_input*dims, `out` n_output*dims doubles.
  * `out` is overwritten with the mapped values (the reference accumulates into a pre-zeroed vector,

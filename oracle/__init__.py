@@ -61,7 +61,7 @@ def lib():
         _lib.orc_pum_cache_create.restype = C.c_void_p
         _lib.orc_global_create.restype = C.c_void_p
         _lib.orc_pum_radius.restype = C.c_double
-        for name in ("orc_pum_compute", "orc_pum_map", "orc_pum_clear", "orc_pum_destroy", "orc_pum_radius",
+        for name in ("orc_pum_compute", "orc_pum_compute_sampled", "orc_pum_map", "orc_pum_clear", "orc_pum_destroy", "orc_pum_radius",
                      "orc_pum_num_clusters", "orc_pum_cluster_sizes", "orc_pum_cluster_data", "orc_global_compute",
                      "orc_global_map", "orc_global_clear", "orc_global_destroy"):
             getattr(_lib, name).argtypes = None
@@ -144,6 +144,15 @@ class PumMapping:
         a, b = as_xyz(input_xyz), as_xyz(output_xyz)
         self._n_in, self._n_out = a.shape[0], b.shape[0]
         _check(self._l.orc_pum_compute(self._h, _dp(a), C.c_int(a.shape[0]), _dp(b), C.c_int(b.shape[0]), C.c_int(threads)))
+
+    def compute_mapping_for_samples(self, input_xyz, output_xyz, samples, threads=1):
+        """Full-size fixtures: builds only the clusters that hold one of the `samples` (vertex IDs of output_xyz, the mesh
+        the result lives on); map() then returns the complete mapping's values at those vertices."""
+        a, b = as_xyz(input_xyz), as_xyz(output_xyz)
+        self._n_in, self._n_out = a.shape[0], b.shape[0]
+        s = np.ascontiguousarray(samples, dtype=np.int32)
+        _check(self._l.orc_pum_compute_sampled(self._h, _dp(a), C.c_int(a.shape[0]), _dp(b), C.c_int(b.shape[0]), _ip(s),
+                                               C.c_int(s.size), C.c_int(threads)))
 
     def map(self, values, dims=1, threads=1) -> np.ndarray:
         v = np.ascontiguousarray(np.asarray(values, dtype=np.float64).reshape(-1))

@@ -82,6 +82,10 @@ int orc_pum_compute(void *h, const double *inXYZ, int nIn, const double *outXYZ,
 {
   return guarded([&] { static_cast<orc::PumMapping *>(h)->computeMapping(inXYZ, nIn, outXYZ, nOut, threads); });
 }
+int orc_pum_compute_sampled(void *h, const double *inXYZ, int nIn, const double *outXYZ, int nOut, const int *samples, int nSamples, int threads)
+{
+  return guarded([&] { static_cast<orc::PumMapping *>(h)->computeMappingForSamples(inXYZ, nIn, outXYZ, nOut, samples, nSamples, threads); });
+}
 int orc_pum_map(void *h, const double *in, int dims, double *out, int threads)
 {
   return guarded([&] { static_cast<orc::PumMapping *>(h)->map(in, dims, out, threads); });

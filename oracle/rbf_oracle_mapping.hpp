@@ -720,6 +720,7 @@ public:
     std::vector<int>    inIDs, outIDs;
     RbfSolver           solver;
     std::vector<double> weights;
+    bool                built = true; // false: placeholder of a cluster outside the sampled region (computeMappingForSamples)
   };
 
   PumMapping(Constraint constraint, int dim, const Rbf &f, Polynomial polynomial, unsigned verticesPerCluster, double relativeOverlap, bool projectToInput)
@@ -855,6 +856,23 @@ public:
     }
   }
 
+  // Test-infrastructure variant for full-size fixtures (tests/golden/make_golden_10m.py): the same mapping, but only the
+  // clusters that contain one of `nSamples` vertices of the RESULT mesh (Mapping::output()) are built. The clustering and
+  // the normalised weights are those of the complete mapping, so map() returns the complete mapping's values at the
+  // sampled vertices (and partial sums elsewhere).
+  void computeMappingForSamples(const double *inputXYZ, int nInput, const double *outputXYZ, int nOutput, const int *samples, int nSamples, int threads = 1)
+  {
+    _samples.assign(samples, samples + nSamples);
+    _sampled = true;
+    try {
+      computeMapping(inputXYZ, nInput, outputXYZ, nOutput, threads);
+    } catch (...) {
+      _sampled = false;
+      throw;
+    }
+    _sampled = false;
+  }
+
   void computeMapping(const double *inputXYZ, int nInput, const double *outputXYZ, int nOutput, int threads = 1)
   {
     if (_computed)
@@ -872,6 +890,17 @@ public:
 
     // SphericalVertexCluster ctor :139-182, one per centre candidate
     std::vector<Cluster> tmp(nc);
+    // computeMappingForSamples: the centres whose cluster holds a sampled vertex of the result mesh (the solver-side
+    // outMesh for consistent, inMesh for conservative constraints; membership radii of SphericalVertexCluster.hpp:155-157)
+    std::vector<char> wanted(nc, _sampled ? 0 : 1);
+    if (_sampled) {
+      PointGrid     allCentres(cl.centers.data(), nc);
+      const double *mesh = cons ? _inXYZ.data() : _outXYZ.data();
+      const double  r    = cons ? _radius : _radius - NUMERICAL_ZERO_DIFFERENCE;
+      for (int sv : _samples)
+        for (int c : allCentres.verticesInsideSphere(mesh + 3 * static_cast<size_t>(sv), r))
+          wanted[c] = 1;
+    }
     const std::array<bool, 3> dead{{false, false, _dim == 2 ? true : false}};
     // NOTE: deadAxis is a std::vector<bool>(dim,false) in the reference (:178): for 2-D meshes only two
     // entries are transformed, the third activeAxis entry stays false (RadialBasisFctSolver.hpp:346-347).
@@ -879,6 +908,12 @@ public:
       Cluster &k = tmp[c];
       for (int d = 0; d < 3; ++d)
         k.center[d] = cl.centers[3 * c + d];
+      if (!wanted[c]) { // placeholder: keeps its slot in the centre list (weights are normalised over ALL clusters)
+        k.built = false;
+        if (inGrid.isAnyVertexInsideSphere(k.center.data(), _radius))
+          k.inIDs.assign(1, -1); // "not empty"
+        return;
+      }
       k.outIDs = outGrid.verticesInsideSphere(k.center.data(), _radius - NUMERICAL_ZERO_DIFFERENCE);
       k.inIDs  = inGrid.verticesInsideSphere(k.center.data(), _radius);
       if (k.inIDs.empty())
@@ -900,7 +935,17 @@ public:
     _centerGrid.reset(new PointGrid(_centerXYZ.data(), static_cast<int>(_clusters.size()))); // kept for just-in-time queries (:285-287)
     PointGrid &centerGrid = *_centerGrid;
     const Rbf weighting = Rbf::make(BasisFunction::WendlandC2, _radius); // SphericalVertexCluster.hpp:146
+    std::vector<char> needsWeight;
+    if (_sampled) { // only the out-vertices of built clusters
+      needsWeight.assign(_nOut, 0);
+      for (const auto &k : _clusters)
+        if (k.built)
+          for (int v : k.outIDs)
+            needsWeight[v] = 1;
+    }
     parallelFor(_nOut, threads, [&](size_t v, int) {
+      if (_sampled && !needsWeight[v])
+        return;
       const double    *x   = &_outXYZ[3 * v];
       std::vector<int> ids = centerGrid.verticesInsideSphere(x, _radius);
       if (ids.empty())
@@ -920,6 +965,8 @@ public:
       }
       for (size_t i = 0; i < ids.size(); ++i) {
         Cluster &k  = _clusters[ids[i]];
+        if (!k.built)
+          continue;
         auto     it = std::lower_bound(k.outIDs.begin(), k.outIDs.end(), static_cast<int>(v)); // setNormalizedWeight :184-199
         if (it != k.outIDs.end() && *it == static_cast<int>(v))
           k.weights[it - k.outIDs.begin()] = w[i] / sum;
@@ -933,6 +980,8 @@ public:
   {
     parallelFor(_clusters.size(), threads, [&](size_t c, int) {
       const Cluster &k = _clusters[c];
+      if (!k.built)
+        return;
       const int      n = static_cast<int>(k.inIDs.size());
       Mat            f(k.solver.inputSize(), dims);
       for (int i = 0; i < n; ++i)
@@ -955,6 +1004,8 @@ public:
   {
     parallelFor(_clusters.size(), threads, [&](size_t c, int) {
       const Cluster &k = _clusters[c];
+      if (!k.built)
+        return;
       Mat            u(k.solver.outputSize(), dims);
       for (size_t i = 0; i < k.outIDs.size(); ++i)
         for (int d = 0; d < dims; ++d)
@@ -1012,6 +1063,8 @@ private:
   std::vector<double>  _inXYZ, _outXYZ;
   std::vector<Cluster> _clusters;
   bool                 _jit = false;
+  bool                 _sampled = false; // inside computeMappingForSamples
+  std::vector<int>     _samples;
   std::vector<double>  _centerXYZ;
   std::unique_ptr<PointGrid> _centerGrid;
 };

@@ -564,6 +564,23 @@ int rbfmap_debug_dist_sqrt(const double *x, int64_t n, double *out)
   });
 }
 
+int rbfmap_host_alloc(void **ptr, int64_t bytes)
+{
+  if (!ptr || bytes < 0)
+    return RBFMAP_ERR_INVALID;
+  *ptr = nullptr;
+  return guarded(nullptr, [&] {
+    if (bytes > 0)
+      RBF_CUDA(cudaHostAlloc(ptr, static_cast<size_t>(bytes), cudaHostAllocPortable));
+  });
+}
+
+void rbfmap_host_free(void *ptr)
+{
+  if (ptr)
+    cudaFreeHost(ptr);
+}
+
 void rbfmap_struct_sizes(int *config_bytes, int *stats_bytes)
 {
   if (config_bytes)

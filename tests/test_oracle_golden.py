@@ -158,3 +158,34 @@ def test_oracle_reproduces_committed_fixtures(idx):
     assert support == pytest.approx(float(data[case[0] + "/support"]), rel=1e-14)
     assert nc == int(data[case[0] + "/clusters"])
     assert refcases.rel_l2(res, data[case[0] + "/result"]) <= 1e-12
+
+
+def test_sampled_oracle_matches_full_oracle():
+    """oracle.compute_mapping_for_samples (used by tests/golden/make_golden_10m.py to produce the full-size fixture bench.py
+    asserts against) is bit-identical to the complete oracle mapping at the sampled vertices."""
+    import bench
+    import oracle
+    n = 12000
+    support = bench.support_radius(n)
+    inp, out = bench.halton_numpy(n, (2, 3, 5), 1), bench.halton_numpy(n, (7, 11, 13), 1)
+    f = np.sin(2 * np.pi * inp[:, 0]) * np.cos(2 * np.pi * inp[:, 1]) + inp[:, 2]
+    v3 = np.stack([f, 2 * f + 1, -f], axis=1).reshape(-1)
+    samples = np.sort(np.random.default_rng(3).choice(n, 300, replace=False)).astype(np.int32)
+    for constraint in ("consistent", "conservative"):
+        full = oracle.PumMapping(constraint, 3, bench.BASIS, support, "separate", bench.VPC, bench.OVERLAP, True)
+        full.compute_mapping(inp, out)
+        part = oracle.PumMapping(constraint, 3, bench.BASIS, support, "separate", bench.VPC, bench.OVERLAP, True)
+        part.compute_mapping_for_samples(inp, out, samples)
+        assert part.num_clusters == full.num_clusters and part.cluster_radius == full.cluster_radius
+        for vals, dims in ((f, 1), (v3, 3)):
+            a = full.map(vals, dims).reshape(n, dims)[samples]
+            b = part.map(vals, dims).reshape(n, dims)[samples]
+            assert np.array_equal(a, b)
+
+
+def test_full_size_fixture_is_committed():
+    import bench
+    g = np.load(bench.GOLDEN_10M)
+    assert int(g["n"]) == 10_000_000 and g["samples"].shape == (10_000,)
+    assert g["consistent_1"].shape == (10_000, 1) and g["conservative_3"].shape == (10_000, 3)
+    assert float(g["support_radius"]) == bench.support_radius(10_000_000)
