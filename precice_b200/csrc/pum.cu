@@ -124,6 +124,8 @@ public:
     _buckets.entries.release();
     _centerGrid = BinGrid();
     _globalIdx.release();
+    _evalOff.release();
+    _evalReady  = false;
     _jit        = false;
     _nClusters  = 0;
     _nClustersGlobal = 0;
@@ -177,6 +179,10 @@ private:
   DevBuf<double>  _inRec;
   DevBuf<int>     _wcount;
   PumBuckets      _buckets;
+  // execution-mode minimal-compute (computeEvaluationOffline, PartitionOfUnityMapping.hpp:57): stored evaluation matrices
+  ScratchBuf<double> _eval; // grow-only like _mat
+  DevBuf<int64_t>    _evalOff;
+  bool               _evalReady = false;
   bool            _jit = false; // the other mesh is a just-in-time mesh
   BinGrid         _centerGrid;  // cluster centres, kept for just-in-time queries (PartitionOfUnityMapping.hpp:285-287)
   // upload of the solver-side outMesh beside the work on the inMesh (computeMappingHost)
@@ -206,6 +212,10 @@ PumSolveArgs PumMapping::solveArgs() const
   a.wcount  = _wcount.p;
   a.outRec  = _outRec.p;
   a.inRec   = _inRec.p;
+  if (_evalReady) {
+    a.eval    = _eval.p;
+    a.evalOff = reinterpret_cast<const long long *>(_evalOff.p);
+  }
   return a;
 }
 
@@ -630,7 +640,24 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
                                             "Please check if your coupling meshes are correct (e.g. no vertices are duplicated) or reconfigure "
                                             "your basis-function (e.g. reduce the support-radius).");
   }
-  stats.device_bytes       = static_cast<int64_t>(_inXyz.bytes() + _outXyz.bytes() + _centers.bytes() + _mem.bytes() + static_cast<size_t>(std::max<int64_t>(_mem.sumTri, 1)) * sizeof(double) + _poly.bytes() + _wsum.bytes() + _wcount.bytes() + _outRec.bytes() + _inRec.bytes());
+  // execution-mode minimal-compute: evaluate and store A_c once (BatchedRBFSolver.hpp:196-239, 324); map() streams them
+  _evalReady = false;
+  if (_cfg.execution_mode == RBFMAP_MINIMAL_COMPUTE && !jit && _nClusters > 0) {
+    EventTimer te(_stream);
+    te.start();
+    const bool    lanesAreOut = !cons; // the side the map kernel assigns to its threads (pum_eval.cu)
+    const int64_t total       = pumEvalOffsets(_mem, _nClusters, lanesAreOut, _evalOff, _stream);
+    if (_eval.n < static_cast<size_t>(std::max<int64_t>(total, 1))) {
+      RBF_CUDA(cudaStreamSynchronize(_stream));
+      _eval.reserve(static_cast<size_t>(total) + static_cast<size_t>(total) / 16 + 2);
+    }
+    pumBuildEvalMatrices(args, _nClusters, lanesAreOut, reinterpret_cast<const long long *>(_evalOff.p), _eval.p, _stream);
+    stats.ms_evaluation_offline = te.stop();
+    stats.evaluation_bytes      = total * static_cast<int64_t>(sizeof(double));
+    _evalReady                  = true;
+    trace.phase("evaluation matrices");
+  }
+  stats.device_bytes       = stats.evaluation_bytes + static_cast<int64_t>(_inXyz.bytes() + _outXyz.bytes() + _centers.bytes() + _mem.bytes() + static_cast<size_t>(std::max<int64_t>(_mem.sumTri, 1)) * sizeof(double) + _poly.bytes() + _wsum.bytes() + _wcount.bytes() + _outRec.bytes() + _inRec.bytes());
   stats.ms_compute_kernels = whole.stop();
   stats.kernel_launches    = g_launches;
   _computed                = true;

@@ -127,6 +127,10 @@ struct PumSolveArgs {
   // cluster-ordered in-vertex coordinates at [(inOff[c] + i) * 3 + d] (factorisation and polynomial set-up read them
   // contiguously instead of ID -> coordinates)
   const double *inRec = nullptr;
+  // execution-mode minimal-compute: stored evaluation matrices (pum_eval.cu), entry (lane vertex l, loop vertex k) of
+  // cluster c at eval[evalOff[c] + k * ld + l]; null = re-evaluate the basis function in every map (minimal-memory)
+  const double    *eval    = nullptr;
+  const long long *evalOff = nullptr;
 };
 
 // Clusters are bucketed by size; every bucket is served by its own kernel instantiation:
@@ -170,6 +174,9 @@ void pumBuildInRecords(const PumSolveArgs &a, int64_t sumIn, double *rec, cudaSt
 // fail = device int (lowest failing cluster index or INT_MAX)
 void pumFactor(const PumSolveArgs &a, const PumBuckets &b, int *fail, cudaStream_t s);
 void pumFactorWarp(const PumSolveArgs &a, int bucket, const PumEntry *list, int64_t count, int *fail, cudaStream_t s);
+// execution-mode minimal-compute (pum_eval.cu): sizes / offsets of the stored evaluation matrices, and their assembly
+int64_t pumEvalOffsets(const PumMembership &m, int64_t nClusters, bool lanesAreOut, DevBuf<int64_t> &evalOff, cudaStream_t s);
+void    pumBuildEvalMatrices(const PumSolveArgs &a, int64_t nClusters, bool lanesAreOut, const long long *evalOff, double *eval, cudaStream_t s);
 void pumMapConsistent(const PumSolveArgs &a, const PumBuckets &b, const double *in, int dims, double *out, cudaStream_t s);
 void pumMapConservative(const PumSolveArgs &a, const PumBuckets &b, const double *in, int dims, double *out, cudaStream_t s);
 // just-in-time mapping (pum_jit.cu)

@@ -10,7 +10,9 @@
 namespace rbfmap {
 namespace {
 
-template <int KIND, int NC, int NT, bool STAGE_M, bool DIM3>
+// STORED: execution-mode minimal-compute, A is read from args.eval (pum_eval.cu; lanes = in-vertices: entry (i, j) at
+// evalOff[c] + i * ld + j) instead of being re-evaluated
+template <int KIND, int NC, int NT, bool STAGE_M, bool DIM3, bool STORED = false>
 __global__ void __launch_bounds__(NT) pumMapConservativeKernel(PumSolveArgs args, const int *__restrict__ list, const double *__restrict__ in, int dims, int c0,
                                                                double *__restrict__ out)
 {
@@ -104,6 +106,28 @@ __global__ void __launch_bounds__(NT) pumMapConservativeKernel(PumSolveArgs args
           acc[cc] = vt[j * LDV + 3 + cc];
         const double  xj = vt[j * LDV], yj = vt[j * LDV + 1], zj = vt[j * LDV + 2];
         const double *op = ot;
+        if (STORED) {
+          const int     ld = (n + 1) & ~1;
+          const double *ap = args.eval + args.evalOff[c] + static_cast<long long>(o0) * ld + j;
+          int           oo = 0;
+          for (; oo + 4 <= chunk; oo += 4, op += 4 * LDV, ap += 4 * static_cast<long long>(ld)) {
+            double a[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              a[u] = __ldg(ap + u * static_cast<long long>(ld));
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+              for (int cc = 0; cc < NC; ++cc)
+                acc[cc] = fma(a[u], op[u * LDV + 3 + cc], acc[cc]);
+          }
+          for (; oo < chunk; ++oo, op += LDV, ap += ld) {
+            const double a = __ldg(ap);
+#pragma unroll
+            for (int cc = 0; cc < NC; ++cc)
+              acc[cc] = fma(a, op[3 + cc], acc[cc]);
+          }
+        } else
 #pragma unroll 2
         for (int oo = 0; oo < chunk; ++oo, op += LDV) {
           const double2 xy  = *reinterpret_cast<const double2 *>(op);
@@ -231,7 +255,10 @@ void launchConservative(const PumSolveArgs &a, const int *list, int64_t count, i
   const size_t sm  = (tri + static_cast<size_t>(TileLd<NC>::value) * (maxN + NT) + 16 * (NT / 32)) * sizeof(double);
   if (sm > kPumMaxSmem)
     throw MapError(RBFMAP_ERR_UNSUPPORTED, "rbf-pum-direct: a cluster with " + std::to_string(maxN) + " vertices exceeds the supported cluster size.");
-  if (a.dim == 3) {
+  if (a.eval && !a.cacheAu) { // execution-mode minimal-compute
+    allowSmem(pumMapConservativeKernel<KIND_RUNTIME, NC, NT, STAGE_M, true, true>, sm);
+    pumMapConservativeKernel<KIND_RUNTIME, NC, NT, STAGE_M, true, true><<<static_cast<unsigned>(count), NT, sm, s>>>(a, list, in, dims, c0, out);
+  } else if (a.dim == 3) {
     allowSmem(pumMapConservativeKernel<KIND, NC, NT, STAGE_M, true>, sm);
     pumMapConservativeKernel<KIND, NC, NT, STAGE_M, true><<<static_cast<unsigned>(count), NT, sm, s>>>(a, list, in, dims, c0, out);
   } else {

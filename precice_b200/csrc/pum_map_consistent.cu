@@ -24,7 +24,9 @@ __device__ unsigned long long g_mapPhase[8]; // cycles: 0 start->gathered, 1 pol
 #endif
 namespace {
 
-template <int KIND, int NC, int NT, bool STAGE_M, bool DIM3>
+// STORED: execution-mode minimal-compute, the evaluation matrix is read from args.eval (pum_eval.cu) instead of being
+// re-evaluated (KIND and DIM3 are then irrelevant: instantiated with KIND_RUNTIME / true only)
+template <int KIND, int NC, int NT, bool STAGE_M, bool DIM3, bool STORED = false>
 __global__ void __launch_bounds__(NT, NT == 32 ? 14 : 1) pumMapConsistentKernel(PumSolveArgs args, const PumEntry *__restrict__ list, const double *__restrict__ in, int dims, int c0,
                                                              double *__restrict__ out)
 {
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(NT, NT == 32 ? 14 : 1) pumMapConsistentKernel(
   // (each takes every 2nd / 4th / 8th in-vertex, partial sums are combined with shuffles) so that no lane idles.
   for (int o0 = 0; o0 < m; o0 += NT) {
     const int rem   = m - o0;
-    const int split = (NT == 32 && rem <= 16) ? (rem <= 4 ? 8 : rem <= 8 ? 4 : 2) : 1;
+    const int split = (!STORED && NT == 32 && rem <= 16) ? (rem <= 4 ? 8 : rem <= 8 ? 4 : 2) : 1;
     const int per   = NT / split;
     const int ol = tid % per, sub = tid / per;
     const bool have = ol < rem;
@@ -182,7 +184,41 @@ __global__ void __launch_bounds__(NT, NT == 32 ? 14 : 1) pumMapConsistentKernel(
 #pragma unroll
     for (int cc = 0; cc < NC; ++cc)
       acc[cc] = 0.0;
-    if (have) {
+    if (STORED) {
+      if (have) { // out_i = sum_j A(i, j) lambda_j with the stored column j at ap[j * ld] (coalesced over the lanes)
+        const int     ld = (m + 1) & ~1;
+        const double *ap = args.eval + args.evalOff[c] + o0 + ol;
+        const double *vp = vt + 3;
+        int           j  = 0;
+        double        acc2[NC];
+#pragma unroll
+        for (int cc = 0; cc < NC; ++cc)
+          acc2[cc] = 0.0;
+        for (; j + 8 <= n; j += 8, ap += 8 * static_cast<long long>(ld), vp += 8 * LDV) {
+          double a[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            a[u] = __ldg(ap + u * static_cast<long long>(ld));
+#pragma unroll
+          for (int u = 0; u < 8; u += 2) {
+#pragma unroll
+            for (int cc = 0; cc < NC; ++cc) {
+              acc[cc]  = fma(a[u], vp[u * LDV + cc], acc[cc]);
+              acc2[cc] = fma(a[u + 1], vp[(u + 1) * LDV + cc], acc2[cc]);
+            }
+          }
+        }
+        for (; j < n; ++j, ap += ld, vp += LDV) {
+          const double a = __ldg(ap);
+#pragma unroll
+          for (int cc = 0; cc < NC; ++cc)
+            acc[cc] = fma(a, vp[cc], acc[cc]);
+        }
+#pragma unroll
+        for (int cc = 0; cc < NC; ++cc)
+          acc[cc] += acc2[cc];
+      }
+    } else if (have) {
       const double *vp = vt + sub * LDV;
       const int     stride = split * LDV;
       int j = sub;
@@ -264,7 +300,10 @@ void launchConsistent(const PumSolveArgs &a, const PumEntry *list, int64_t count
   const size_t sm  = (tri + static_cast<size_t>(TileLd<NC>::value) * maxN + 16 * (NT / 32)) * sizeof(double);
   if (sm > kPumMaxSmem)
     throw MapError(RBFMAP_ERR_UNSUPPORTED, "rbf-pum-direct: a cluster with " + std::to_string(maxN) + " vertices exceeds the supported cluster size.");
-  if (a.dim == 3) {
+  if (a.eval) { // execution-mode minimal-compute
+    allowSmem(pumMapConsistentKernel<KIND_RUNTIME, NC, NT, STAGE_M, true, true>, sm);
+    pumMapConsistentKernel<KIND_RUNTIME, NC, NT, STAGE_M, true, true><<<static_cast<unsigned>(count), NT, sm, s>>>(a, list, in, dims, c0, out);
+  } else if (a.dim == 3) {
     allowSmem(pumMapConsistentKernel<KIND, NC, NT, STAGE_M, true>, sm);
     pumMapConsistentKernel<KIND, NC, NT, STAGE_M, true><<<static_cast<unsigned>(count), NT, sm, s>>>(a, list, in, dims, c0, out);
   } else {
