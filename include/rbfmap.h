@@ -212,6 +212,25 @@ int rbfmap_partition_rows(int64_t n, int world, int rank, int64_t *begin, int64_
  * centres one rank processes, when rank r processes the bins [cuts[r] - halo_bins, cuts[r+1] + halo_bins). */
 int rbfmap_partition_slabs(const int64_t *histogram, int n_bins, int world, int halo_bins, int *cuts);
 
+/* Re-partitioning hooks of a parallel participant (Mapping::tagMeshFirstRound / tagMeshSecondRound, Mapping.hpp:179-182,
+ * called by partition/ReceivedPartition.cpp:921-954): which vertices of the received (remote) mesh does this rank keep?
+ * The remote mesh is Mapping::input() for consistent and Mapping::output() for conservative constraints; `tags` has one
+ * byte per vertex of THAT mesh, the call sets tags[i] = 1 for the vertices to keep and leaves the others untouched
+ * (Vertex::tag()). Host pointers.
+ *  - global variants (RadialBasisFctBaseMapping.hpp:124-190): bounding box of the local mesh, expanded by the support
+ *    radius (all vertices if the basis function has global support); second round: box around the owned vertices
+ *    (`owner[i] != 0`) of the remote mesh, expanded by the support radius.
+ *  - rbf-pum-direct (PartitionOfUnityMapping.hpp:479-539): bounding box of the local mesh, expanded by 2 x the cluster
+ *    radius, which is estimated on the unfiltered remote mesh (rbfmap_estimate_cluster_radius) unless a computed mapping
+ *    already knows it; the second round does nothing. */
+int rbfmap_tag_mesh_first_round(rbfmap_handle *h, const double *input_xyz, int64_t n_input, const double *output_xyz, int64_t n_output,
+                                unsigned char *tags);
+int rbfmap_tag_mesh_second_round(rbfmap_handle *h, const double *mesh_xyz, int64_t n, const unsigned char *owner, unsigned char *tags);
+/* impl::estimateClusterRadius(verticesPerCluster, mesh, boundingBox) (impl/CreateClustering.hpp:223-278): median over
+ * 1 + 2 dim probe points of the distance to the vertices-per-cluster-th nearest vertex. rbf-pum-direct only. */
+int rbfmap_estimate_cluster_radius(rbfmap_handle *h, const double *mesh_xyz, int64_t n, const double bb_min[3], const double bb_max[3],
+                                   double *radius);
+
 /* Mapping::clear() (Mapping.hpp:134), Mapping::hasComputedMapping(), destructor, Mapping::getName(). */
 int         rbfmap_clear(rbfmap_handle *h);
 int         rbfmap_has_computed_mapping(const rbfmap_handle *h);

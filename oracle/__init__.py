@@ -124,6 +124,18 @@ def create_clustering(in_xyz, out_xyz, dim, overlap, vpc, project):
     return radius.value, centers[:min(cap, count.value)].copy(), count.value
 
 
+def estimate_cluster_radius(xyz, dim, vpc, bb_min, bb_max) -> float:
+    """impl::estimateClusterRadius (impl/CreateClustering.hpp:223-278) for an arbitrary bounding box."""
+    a = as_xyz(xyz)
+    lo = np.zeros(3)
+    hi = np.zeros(3)
+    lo[:len(bb_min)] = bb_min
+    hi[:len(bb_max)] = bb_max
+    r = C.c_double(0)
+    _check(lib().orc_estimate_cluster_radius(_dp(a), C.c_int(a.shape[0]), C.c_int(dim), C.c_uint(vpc), _dp(lo), _dp(hi), C.byref(r)))
+    return r.value
+
+
 class PumMapping:
     """Mirror of mapping::PartitionOfUnityMapping (PartitionOfUnityMapping.hpp:48-57) on the oracle."""
 

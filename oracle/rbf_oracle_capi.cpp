@@ -69,6 +69,17 @@ int orc_create_clustering(const double *inXYZ, int nIn, const double *outXYZ, in
   });
 }
 
+// impl::estimateClusterRadius (impl/CreateClustering.hpp:223-278) on an arbitrary mesh / bounding box, as
+// PartitionOfUnityMapping::tagMeshFirstRound calls it (PartitionOfUnityMapping.hpp:520-521)
+int orc_estimate_cluster_radius(const double *xyz, int n, int dim, unsigned vpc, const double *bbMin, const double *bbMax, double *radius)
+{
+  return guarded([&] {
+    orc::PointGrid g(xyz, n);
+    orc::Vec3      lo{{bbMin[0], bbMin[1], bbMin[2]}}, hi{{bbMax[0], bbMax[1], bbMax[2]}};
+    *radius = orc::estimateClusterRadius(vpc, g, dim, lo, hi);
+  });
+}
+
 // ---- partition of unity ----
 void *orc_pum_create(int constraint, int dim, int basis, double param, double gaussSupport, int polynomial, unsigned vpc, double overlap, int project)
 {

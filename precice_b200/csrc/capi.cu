@@ -145,6 +145,100 @@ void DeviceMapping::uploadReplicated(double *dDst, const double *hSrc, int64_t c
   _group.allGatherInPlace(dDst, slice, s);
 }
 
+namespace {
+__global__ void tagBoxKernel(const double *__restrict__ xyz, long long n, int dim, double lx, double ly, double lz, double hx, double hy, double hz,
+                             unsigned char *__restrict__ tags)
+{
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n)
+    return;
+  const double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+  // mesh/BoundingBox.cpp:70-81: outside iff coords[d] < min[d] || coords[d] > max[d]
+  bool inside = !(x < lx || x > hx) && !(y < ly || y > hy);
+  if (dim == 3)
+    inside = inside && !(z < lz || z > hz);
+  if (inside)
+    tags[i] = 1;
+}
+__global__ void ownedBoundsKernel(const double *__restrict__ xyz, long long n, const unsigned char *__restrict__ owner, unsigned long long *__restrict__ keys)
+{
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n || !owner[i])
+    return;
+  for (int d = 0; d < 3; ++d) {
+    atomicMin(&keys[d], encodeOrdered(xyz[3 * i + d]));
+    atomicMax(&keys[3 + d], encodeOrdered(xyz[3 * i + d]));
+  }
+}
+} // namespace
+
+void DeviceMapping::tagInsideBox(const double *dXyz, int64_t n, const double lo[3], const double hi[3], double margin, unsigned char *hTags)
+{
+  if (n <= 0)
+    return;
+  DevBuf<unsigned char> dTags;
+  dTags.alloc(n);
+  RBF_CUDA(cudaMemcpyAsync(dTags.p, hTags, n, cudaMemcpyHostToDevice, _stream));
+  // BoundingBox::expandBy (mesh/BoundingBox.cpp:154-160): min - value, max + value
+  tagBoxKernel<<<divUp(n, 256), 256, 0, _stream>>>(dXyz, n, _cfg.dimensions, lo[0] - margin, lo[1] - margin, lo[2] - margin, hi[0] + margin, hi[1] + margin,
+                                                  hi[2] + margin, dTags.p);
+  RBF_LAUNCHED();
+  RBF_CUDA(cudaGetLastError());
+  RBF_CUDA(cudaMemcpyAsync(hTags, dTags.p, n, cudaMemcpyDeviceToHost, _stream));
+  RBF_CUDA(cudaStreamSynchronize(_stream));
+}
+
+// RadialBasisFctBaseMapping.hpp:124-157
+void DeviceMapping::tagMeshFirstRound(const double *hFilterXyz, int64_t nFilter, const double *hOtherXyz, int64_t nOther, unsigned char *hTags)
+{
+  if (nOther == 0 || nFilter == 0)
+    return; // :137-138 ranks not at the interface never hold interface vertices
+  if (!basisHasCompactSupport(_rbf.kind)) {
+    std::memset(hTags, 1, static_cast<size_t>(nFilter)); // :154 tagAll
+    return;
+  }
+  AllocStreamScope allocScope(_stream);
+  DevBuf<double>   dFilter, dOther;
+  dFilter.alloc(3 * nFilter);
+  dOther.alloc(3 * nOther);
+  RBF_CUDA(cudaMemcpyAsync(dFilter.p, hFilterXyz, 3 * nFilter * sizeof(double), cudaMemcpyHostToDevice, _stream));
+  RBF_CUDA(cudaMemcpyAsync(dOther.p, hOtherXyz, 3 * nOther * sizeof(double), cudaMemcpyHostToDevice, _stream));
+  double lo[3], hi[3];
+  computeBounds(dOther.p, nOther, lo, hi, _stream);
+  tagInsideBox(dFilter.p, nFilter, lo, hi, basisSupportRadius(_rbf), hTags); // :141-151
+}
+
+// RadialBasisFctBaseMapping.hpp:163-190
+void DeviceMapping::tagMeshSecondRound(const double *hFilterXyz, int64_t nFilter, const unsigned char *hOwner, unsigned char *hTags)
+{
+  if (!basisHasCompactSupport(_rbf.kind) || nFilter == 0)
+    return; // :167-168 tags are not changed
+  AllocStreamScope           allocScope(_stream);
+  DevBuf<double>             dFilter;
+  DevBuf<unsigned char>      dOwner;
+  DevBuf<unsigned long long> keys;
+  dFilter.alloc(3 * nFilter);
+  dOwner.alloc(nFilter);
+  keys.alloc(6);
+  unsigned long long init[6] = {~0ull, ~0ull, ~0ull, 0ull, 0ull, 0ull};
+  RBF_CUDA(cudaMemcpyAsync(dFilter.p, hFilterXyz, 3 * nFilter * sizeof(double), cudaMemcpyHostToDevice, _stream));
+  RBF_CUDA(cudaMemcpyAsync(dOwner.p, hOwner, nFilter, cudaMemcpyHostToDevice, _stream));
+  RBF_CUDA(cudaMemcpyAsync(keys.p, init, sizeof(init), cudaMemcpyHostToDevice, _stream));
+  ownedBoundsKernel<<<divUp(nFilter, 256), 256, 0, _stream>>>(dFilter.p, nFilter, dOwner.p, keys.p); // :180-186 box around all owned vertices
+  RBF_LAUNCHED();
+  unsigned long long out[6];
+  RBF_CUDA(cudaMemcpyAsync(out, keys.p, sizeof(out), cudaMemcpyDeviceToHost, _stream));
+  RBF_CUDA(cudaStreamSynchronize(_stream));
+  if (out[0] == ~0ull)
+    return; // no owned vertex: the default box is not expanded (BoundingBox::expandBy), nothing lies inside
+  double lo[3], hi[3];
+  for (int d = 0; d < 3; ++d) {
+    lo[d] = decodeOrdered(out[d]);
+    hi[d] = decodeOrdered(out[3 + d]);
+  }
+  tagInsideBox(dFilter.p, nFilter, lo, hi, basisSupportRadius(_rbf), hTags); // :187-189
+}
+
 double PhaseTrace::now()
 {
   timespec ts;
@@ -418,6 +512,40 @@ int rbfmap_map_device(rbfmap_handle *h, const double *d_in, int dims, double *d_
     if (!h->impl->hasComputedMapping())
       throw MapError(RBFMAP_ERR_STATE, "The mapping has not been computed; call computeMapping() first.");
     mapDeviceImpl(h, 0, d_in, dims, d_out);
+  });
+}
+
+int rbfmap_tag_mesh_first_round(rbfmap_handle *h, const double *input_xyz, int64_t n_input, const double *output_xyz, int64_t n_output, unsigned char *tags)
+{
+  if (!h)
+    return RBFMAP_ERR_INVALID;
+  return guarded(h, [&] {
+    if (n_input < 0 || n_output < 0 || !tags)
+      throw MapError(RBFMAP_ERR_INVALID, "invalid mesh / tag buffer");
+    const bool cons = h->impl->isConservative(); // the remote (filter) mesh is output() for conservative constraints
+    h->impl->tagMeshFirstRound(cons ? output_xyz : input_xyz, cons ? n_output : n_input, cons ? input_xyz : output_xyz, cons ? n_input : n_output, tags);
+  });
+}
+
+int rbfmap_tag_mesh_second_round(rbfmap_handle *h, const double *mesh_xyz, int64_t n, const unsigned char *owner, unsigned char *tags)
+{
+  if (!h)
+    return RBFMAP_ERR_INVALID;
+  return guarded(h, [&] {
+    if (n < 0 || !tags || !owner)
+      throw MapError(RBFMAP_ERR_INVALID, "invalid mesh / owner / tag buffer");
+    h->impl->tagMeshSecondRound(mesh_xyz, n, owner, tags);
+  });
+}
+
+int rbfmap_estimate_cluster_radius(rbfmap_handle *h, const double *mesh_xyz, int64_t n, const double bb_min[3], const double bb_max[3], double *radius)
+{
+  if (!h || !radius)
+    return RBFMAP_ERR_INVALID;
+  return guarded(h, [&] {
+    if (n <= 0 || !mesh_xyz || !bb_min || !bb_max)
+      throw MapError(RBFMAP_ERR_INVALID, "invalid mesh / bounding box");
+    *radius = h->impl->estimateClusterRadiusHost(mesh_xyz, n, bb_min, bb_max);
   });
 }
 

@@ -53,6 +53,19 @@ public:
   // Enqueued on `s`; the host buffer may be reused after `s` has been synchronised.
   void uploadReplicated(double *dDst, const double *hSrc, int64_t count, cudaStream_t s) const;
 
+  // ---- re-partitioning hooks (Mapping::tagMeshFirstRound / tagMeshSecondRound, Mapping.hpp:179-182), host pointers ----
+  // Marks (tags[i] = 1) the vertices of the REMOTE mesh - Mapping::input() for consistent, Mapping::output() for
+  // conservative constraints - that a rank holding the LOCAL (other) mesh needs; untouched entries keep their value.
+  // Default = RadialBasisFctBaseMapping.hpp:124-190 (the two global variants); rbf-pum-direct overrides the first round
+  // (PartitionOfUnityMapping.hpp:479-533) and does nothing in the second (:535-539).
+  virtual void tagMeshFirstRound(const double *hFilterXyz, int64_t nFilter, const double *hOtherXyz, int64_t nOther, unsigned char *hTags);
+  virtual void tagMeshSecondRound(const double *hFilterXyz, int64_t nFilter, const unsigned char *hOwner, unsigned char *hTags);
+  // impl::estimateClusterRadius (impl/CreateClustering.hpp:223-278) on an arbitrary mesh and bounding box; PUM only
+  virtual double estimateClusterRadiusHost(const double * /*hXyz*/, int64_t /*n*/, const double * /*bbMin*/, const double * /*bbMax*/)
+  {
+    throw MapError(RBFMAP_ERR_UNSUPPORTED, "the cluster radius belongs to rbf-pum-direct");
+  }
+
   bool                 hasComputedMapping() const { return _computed; }
   bool                 isConservative() const { return _cfg.constraint == RBFMAP_CONSERVATIVE; }
   const rbfmap_config &config() const { return _cfg; }
@@ -63,6 +76,8 @@ public:
   rbfmap_stats         stats;
 
 protected:
+  // tags the vertices inside [lo - margin, hi + margin] (inclusive, BoundingBox::contains / bgi::intersects), first `dim` axes
+  void tagInsideBox(const double *dXyz, int64_t n, const double lo[3], const double hi[3], double margin, unsigned char *hTags);
   rbfmap_config _cfg;
   RbfParams     _rbf;
   ShardGroup    _group;

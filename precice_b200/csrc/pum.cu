@@ -106,6 +106,33 @@ public:
     if (_copyStream)
       cudaStreamDestroy(_copyStream);
   }
+  double estimateClusterRadiusHost(const double *hXyz, int64_t n, const double *bbMin, const double *bbMax) override
+  {
+    AllocStreamScope allocScope(_stream);
+    DevBuf<double>   d;
+    d.alloc(3 * n);
+    RBF_CUDA(cudaMemcpyAsync(d.p, hXyz, 3 * n * sizeof(double), cudaMemcpyHostToDevice, _stream));
+    return estimateClusterRadius(d.p, n, bbMin, bbMax);
+  }
+  // PartitionOfUnityMapping.hpp:479-533
+  void tagMeshFirstRound(const double *hFilterXyz, int64_t nFilter, const double *hOtherXyz, int64_t nOther, unsigned char *hTags) override
+  {
+    if (nOther == 0 || nFilter == 0)
+      return; // :491-492
+    AllocStreamScope allocScope(_stream);
+    DevBuf<double>   dFilter, dOther;
+    dFilter.alloc(3 * nFilter);
+    dOther.alloc(3 * nOther);
+    RBF_CUDA(cudaMemcpyAsync(dFilter.p, hFilterXyz, 3 * nFilter * sizeof(double), cudaMemcpyHostToDevice, _stream));
+    RBF_CUDA(cudaMemcpyAsync(dOther.p, hOtherXyz, 3 * nOther * sizeof(double), cudaMemcpyHostToDevice, _stream));
+    double lo[3], hi[3];
+    computeBounds(dOther.p, nOther, lo, hi, _stream); // :513 the local bounding box
+    if (_radius == 0) // :520-521: estimated on the unfiltered remote mesh, kept until clear()
+      _radius = estimateClusterRadius(dFilter.p, nFilter, lo, hi);
+    tagInsideBox(dFilter.p, nFilter, lo, hi, 2 * _radius, hTags); // :527-532
+  }
+  void tagMeshSecondRound(const double *, int64_t, const unsigned char *, unsigned char *) override {} // :535-539
+  double clusterRadius() const { return _radius; }
   void mapConsistent(const double *dIn, int dims, double *dOut) override { map(false, dIn, dims, dOut); }
   void mapConservative(const double *dIn, int dims, double *dOut) override { map(true, dIn, dims, dOut); }
   void clear() override
@@ -154,7 +181,7 @@ private:
   void throwUnassigned(const double *dCoords, int64_t bad, bool cons) const;
   void   computeImpl(const double *srcInputXyz, int64_t nInput, const double *srcOutputXyz, int64_t nOutput, cudaMemcpyKind kind);
   void   map(bool conservative, const double *dIn, int dims, double *dOut);
-  double estimateClusterRadius(const double bbMin[3], const double bbMax[3]);
+  double estimateClusterRadius(const double *dXyz, int64_t n, const double bbMin[3], const double bbMax[3]);
   PumSolveArgs solveArgs() const;
   // sharded mapping: replaces the complete centre list by the centres this rank processes
   void shardClusters(const double bbMin[3], const double bbMax[3], const int latticeCount[3], bool haveLattice);
@@ -220,7 +247,7 @@ PumSolveArgs PumMapping::solveArgs() const
 }
 
 // impl/CreateClustering.hpp:223-278
-double PumMapping::estimateClusterRadius(const double bbMin[3], const double bbMax[3])
+double PumMapping::estimateClusterRadius(const double *dXyz, int64_t nXyz, const double bbMin[3], const double bbMax[3])
 {
   const int dim = _cfg.dimensions;
   double    center[3] = {0, 0, 0};
@@ -237,7 +264,7 @@ double PumMapping::estimateClusterRadius(const double bbMin[3], const double bbM
   }
   const int        nProbes = static_cast<int>(probes.size() / 3);
   std::vector<int> samples(nProbes);
-  nearestVertices(_inXyz.p, _nIn, probes.data(), nProbes, samples.data(), _stream);
+  nearestVertices(dXyz, nXyz, probes.data(), nProbes, samples.data(), _stream);
 
   // starting radius for the k-nearest search from the mean density of the bounding box
   double vol  = 1.0;
@@ -247,9 +274,9 @@ double PumMapping::estimateClusterRadius(const double bbMin[3], const double bbM
       vol *= (bbMax[d] - bbMin[d]);
       ++live;
     }
-  const double guess = live > 0 ? 0.8 * std::pow(vol * static_cast<double>(_cfg.vertices_per_cluster) / static_cast<double>(_nIn), 1.0 / live) : 1.0;
+  const double guess = live > 0 ? 0.8 * std::pow(vol * static_cast<double>(_cfg.vertices_per_cluster) / static_cast<double>(nXyz), 1.0 / live) : 1.0;
   std::vector<double> radii(nProbes);
-  kthNeighbourDistance(_inXyz.p, _nIn, samples.data(), nProbes, static_cast<int>(_cfg.vertices_per_cluster), guess, radii.data(), _stream);
+  kthNeighbourDistance(dXyz, nXyz, samples.data(), nProbes, static_cast<int>(_cfg.vertices_per_cluster), guess, radii.data(), _stream);
   const size_t middle = radii.size() / 2;
   std::nth_element(radii.begin(), radii.begin() + middle, radii.end());
   return radii[middle];
@@ -431,7 +458,7 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
         obMin[d] = bbMin[d], obMax[d] = bbMax[d];
     outGrid.build(_outXyz.p, _nOut, obMin, obMax, 0.5 * _radius, _stream);
   } else {
-    _radius = estimateClusterRadius(bbMin, bbMax);
+    _radius = estimateClusterRadius(_inXyz.p, _nIn, bbMin, bbMax);
     trace.phase("estimateClusterRadius");
     if (!(_radius > 0.0))
       throw MapError(RBFMAP_ERR_SINGULAR, "rbf-pum-direct: the estimated cluster radius is zero (duplicated vertices?).");

@@ -36,6 +36,11 @@ __device__ __forceinline__ void bulkLoad(void *dstSmem, const void *srcGlobal, u
                "r"(bytes), "r"(smemAddr(bar))
                : "memory");
 }
+// asks the memory system to bring `bytes` (multiple of 16, 16-byte aligned) from global memory into L2; no completion to wait for
+__device__ __forceinline__ void bulkPrefetchL2(const void *srcGlobal, unsigned bytes)
+{
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(srcGlobal), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void mbarWait(unsigned long long *bar, unsigned phase)
 {
   unsigned done = 0;

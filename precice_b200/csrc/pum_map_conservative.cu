@@ -51,6 +51,8 @@ __global__ void __launch_bounds__(NT) pumMapConservativeKernel(PumSolveArgs args
     if (tid == 0)
       bulkLoad(ms, mg, static_cast<unsigned>(triPad) * 8u, &mbar);
   }
+  if (STORED && tid == 0) // stored evaluation matrix: on its way into L2 while the tiles are gathered
+    bulkPrefetchL2(args.eval + args.evalOff[c], static_cast<unsigned>(((n + 1) & ~1) * m) * 8u);
   for (int i = tid; i < n; i += NT) {
     const double *p = args.inRec + 3 * (inOffC + i); // cluster-ordered coordinates
     vt[i * LDV]     = p[0];

@@ -65,6 +65,10 @@ __global__ void __launch_bounds__(NT, NT == 32 ? 14 : 1) pumMapConsistentKernel(
     if (tid == 0)
       bulkLoad(ms, mg, static_cast<unsigned>(triPad) * 8u, &mbar);
   }
+  // stored evaluation matrix: on its way into L2 while the coefficients are computed (the evaluation loop would
+  // otherwise wait for DRAM once per group of columns)
+  if (STORED && tid == 0)
+    bulkPrefetchL2(args.eval + args.evalOff[c], static_cast<unsigned>(((m + 1) & ~1) * n) * 8u);
 
   // ---- gather (SphericalVertexCluster.hpp:312-320) ----
   for (int i = tid; i < n; i += NT) {

@@ -160,6 +160,34 @@ class _Mapping:
         assert isinstance(out, np.ndarray) and out.dtype == np.float64 and out.flags.c_contiguous and out.size == self._n_mesh * cache.dims
         self._check(self._L.rbfmap_complete_just_in_time_mapping(self._h, cache._c, out.ctypes.data))
 
+    # -- re-partitioning hooks (Mapping.hpp:179-182)
+    def tagMeshFirstRound(self, input_xyz, output_xyz, tags=None) -> np.ndarray:
+        """Tags (1) the vertices of the remote mesh - input() for consistent, output() for conservative constraints - that
+        this rank needs; `tags` (uint8, one per vertex of the remote mesh) is updated in place and returned."""
+        a, b = as_xyz(input_xyz), as_xyz(output_xyz)
+        n_remote = b.shape[0] if self._cfg.constraint == 1 else a.shape[0]
+        if tags is None:
+            tags = np.zeros(n_remote, dtype=np.uint8)
+        assert tags.dtype == np.uint8 and tags.size == n_remote and tags.flags.c_contiguous
+        self._check(self._L.rbfmap_tag_mesh_first_round(self._h, a.ctypes.data, a.shape[0], b.ctypes.data, b.shape[0], tags.ctypes.data))
+        return tags
+
+    def tagMeshSecondRound(self, remote_xyz, owner, tags) -> np.ndarray:
+        a = as_xyz(remote_xyz)
+        owner = np.ascontiguousarray(owner, dtype=np.uint8)
+        assert tags.dtype == np.uint8 and tags.size == a.shape[0] == owner.size
+        self._check(self._L.rbfmap_tag_mesh_second_round(self._h, a.ctypes.data, a.shape[0], owner.ctypes.data, tags.ctypes.data))
+        return tags
+
+    def estimateClusterRadius(self, mesh_xyz, bb_min, bb_max) -> float:
+        """impl::estimateClusterRadius(verticesPerCluster, mesh, bb) (impl/CreateClustering.hpp:223-278); rbf-pum-direct."""
+        a = as_xyz(mesh_xyz)
+        lo = (C.c_double * 3)(*[float(v) for v in list(bb_min) + [0.0] * (3 - len(bb_min))])
+        hi = (C.c_double * 3)(*[float(v) for v in list(bb_max) + [0.0] * (3 - len(bb_max))])
+        r = C.c_double(0)
+        self._check(self._L.rbfmap_estimate_cluster_radius(self._h, a.ctypes.data, a.shape[0], lo, hi, C.byref(r)))
+        return r.value
+
     def clear(self):
         self._check(self._L.rbfmap_clear(self._h))
 

@@ -160,3 +160,62 @@ def test_pum_sharded_two_gpus(pb):
     out = _torchrun(2, "--vertices", "20000", "--oracle")
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "SHARDED PUM OK" in out.stdout, out.stdout[-3000:]
+
+
+# ---------------------------------------------------------------------------------------------- re-partitioning hooks
+def _box_tags(remote, local, margin, dim):
+    lo, hi = local.min(0) - margin, local.max(0) + margin
+    inside = np.ones(len(remote), bool)
+    for d in range(dim):
+        inside &= ~((remote[:, d] < lo[d]) | (remote[:, d] > hi[d]))
+    return inside.astype(np.uint8)
+
+
+@pytest.mark.parametrize("constraint", ["consistent", "conservative"])
+def test_pum_tag_mesh_first_round(pb, constraint):
+    """PartitionOfUnityMapping.hpp:479-533: bounding box of the local mesh expanded by 2 x the cluster radius, the radius
+    estimated on the unfiltered remote mesh with the local box (impl/CreateClustering.hpp:223-278)."""
+    import oracle
+    remote = refcases.halton(30000, (2, 3, 5))
+    local = 0.3 + 0.25 * refcases.halton(2000, (7, 11, 13))  # this rank's partition: a sub-box of the remote mesh
+    m = pb.PartitionOfUnityMapping(constraint, 3, "compact-polynomial-c6", 0.3, "separate", 40, 0.15, True)
+    inp, out = (remote, local) if constraint == "consistent" else (local, remote)
+    radius = m.estimateClusterRadius(remote, local.min(0), local.max(0))
+    assert radius == oracle.estimate_cluster_radius(remote, 3, 40, local.min(0), local.max(0))
+    tags = m.tagMeshFirstRound(inp, out)
+    assert tags.shape == (30000,) and np.array_equal(tags, _box_tags(remote, local, 2 * radius, 3))
+    assert 0 < tags.sum() < 30000
+    # tags are only ever set (Vertex::tag), and the second round leaves them alone (:535-539)
+    pre = np.zeros(30000, np.uint8)
+    pre[:10] = 1
+    assert np.array_equal(m.tagMeshFirstRound(inp, out, pre), np.maximum(tags, pre))
+    before = tags.copy()
+    m.tagMeshSecondRound(remote, np.ones(30000, np.uint8), tags)
+    assert np.array_equal(tags, before)
+    # an empty local mesh tags nothing (:491-492)
+    empty = np.zeros((0, 3))
+    none = m.tagMeshFirstRound(*((remote, empty) if constraint == "consistent" else (empty, remote)))
+    assert none.sum() == 0
+
+
+def test_global_tag_mesh_rounds(pb):
+    """RadialBasisFctBaseMapping.hpp:124-190."""
+    remote = refcases.halton(20000, (2, 3, 5))
+    local = 0.4 + 0.2 * refcases.halton(1500, (7, 11, 13))
+    m = pb.RadialBasisFctMapping("consistent", 3, "compact-polynomial-c2", 0.07)
+    tags = m.tagMeshFirstRound(remote, local)
+    assert np.array_equal(tags, _box_tags(remote, local, 0.07, 3))
+    owner = (tags == 1) & (remote[:, 0] < 0.5)
+    second = m.tagMeshSecondRound(remote, owner.astype(np.uint8), tags.copy())
+    assert np.array_equal(second, np.maximum(tags, _box_tags(remote, remote[owner], 0.07, 3)))
+    # conservative: the remote mesh is output(); 2-D ignores z
+    r2, l2 = remote.copy(), local.copy()
+    r2[:, 2] = 0.0
+    l2[:, 2] = 0.0
+    mc = pb.RadialBasisFctMapping("conservative", 2, "compact-polynomial-c2", 0.07)
+    assert np.array_equal(mc.tagMeshFirstRound(l2, r2), _box_tags(r2, l2, 0.07, 2))
+    # global support: everything is tagged (:153-155), the second round changes nothing (:167-168)
+    mt = pb.RadialBasisFctMapping("consistent", 3, "thin-plate-splines")
+    assert mt.tagMeshFirstRound(remote, local).all()
+    z = np.zeros(20000, np.uint8)
+    assert mt.tagMeshSecondRound(remote, np.ones(20000, np.uint8), z).sum() == 0
