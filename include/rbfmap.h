@@ -158,6 +158,15 @@ int rbfmap_map_conservative_at(rbfmap_handle *h, rbfmap_cache *cache, const doub
  * result to `out` (n*dims doubles on the mesh), like the reference accumulates into its buffer. */
 int rbfmap_complete_just_in_time_mapping(rbfmap_handle *h, rbfmap_cache *cache, double *out);
 
+/* Mesh connectivity for the scaled-consistent constraints (Mapping::scaleConsistentMapping, Mapping.cpp:175-246): the
+ * elements of `mesh` (0 = Mapping::input(), 1 = Mapping::output()) as tuples of vertex IDs, vertices_per_element = 2
+ * (edges: 2-D surface), 3 (triangles: 2-D volume, 3-D surface) or 4 (tetrahedra: 3-D volume) - what Mapping.cpp:190-192
+ * requires for the configured constraint and dimension. Call before computeMapping; rbfmap_map() then multiplies every
+ * data component of the consistent result by integral(input) / integral(output) (mesh::integrateSurface /
+ * integrateVolume, mesh/Utils.cpp:11-70; factor 1 if the output integral is zero). Without connectivity rbfmap_map()
+ * fails with the reference's message ("... connectivity information is missing for the mesh ..."). Host pointer. */
+int rbfmap_set_connectivity(rbfmap_handle *h, int mesh, const int32_t *elements, int64_t n_elements, int vertices_per_element);
+
 /* Page-locked host memory for the adapter's staging buffers (cudaHostAlloc / cudaFreeHost): the adapter has to pack
  * mesh.vertex(i).rawCoords() into a contiguous double[n][3] anyway (the reference's own device path does the same,
  * BatchedRBFSolver.hpp:250-271); packing into a buffer from rbfmap_host_alloc lets the host-pointer entry points copy
@@ -168,8 +177,8 @@ void rbfmap_host_free(void *ptr);
 /* Mapping::map(Sample, VectorXd&) dispatch (mapping/Mapping.cpp:158-173): conservative ->
  * mapConservative, otherwise mapConsistent. `in` has n_input*dims, `out` n_output*dims doubles.
  * `out` is overwritten with the mapped values (the reference accumulates into a pre-zeroed vector,
- * precice/impl/DataContext.cpp:148-150). Scaled-consistent post-scaling (Mapping.cpp:175-246) needs
- * mesh connectivity and stays with the caller. Host pointers. */
+ * precice/impl/DataContext.cpp:148-150). Scaled-consistent constraints: mapConsistent followed by the
+ * post-scaling of Mapping.cpp:175-246 (needs rbfmap_set_connectivity). Host pointers. */
 int rbfmap_map(rbfmap_handle *h, const double *in, int dims, double *out);
 int rbfmap_map_consistent(rbfmap_handle *h, const double *in, int dims, double *out);   /* Mapping.hpp:337 */
 int rbfmap_map_conservative(rbfmap_handle *h, const double *in, int dims, double *out); /* Mapping.hpp:324 */

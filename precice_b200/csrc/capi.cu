@@ -10,6 +10,7 @@
 #include <ctime>
 #include <limits>
 #include <mutex>
+#include <vector>
 
 namespace rbfmap {
 
@@ -288,6 +289,14 @@ struct rbfmap_handle {
   std::string                    name;
   // staging buffers of the host-pointer API
   DevBuf<double> dInXyz, dOutXyz, dIn, dOut;
+  // scaled-consistent constraints (Mapping.cpp:175-246): connectivity of Mapping::input() [0] and output() [1] as the caller
+  // handed it over, and the per-vertex integration weights derived from it at computeMapping
+  struct Connectivity {
+    std::vector<int32_t> elements;
+    int                  verticesPerElement = 0;
+    DevBuf<double>       weights; // integral of the nodal hat function of every vertex: sum over its elements of measure / k
+    int64_t              nVertices = 0;
+  } conn[2];
 };
 
 namespace {
@@ -313,7 +322,165 @@ int guarded(rbfmap_handle *h, F &&f)
 }
 } // namespace
 
+// ---- scaled-consistent mapping (Mapping::scaleConsistentMapping, Mapping.cpp:175-246; mesh::integrateSurface / integrateVolume,
+// mesh/Utils.cpp:11-70; element measures math/geometry.cpp:93-123, mesh/Edge.cpp:23-27) ----
+namespace rbfmap {
+namespace scaled {
+__global__ void elementWeightsKernel(const double *__restrict__ xyz, const int *__restrict__ el, long long nEl, int k, int dim, double *__restrict__ w)
+{
+  const long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (e >= nEl)
+    return;
+  double p[4][3];
+  for (int a = 0; a < k; ++a)
+    for (int d = 0; d < 3; ++d)
+      p[a][d] = (d < dim) ? xyz[3 * static_cast<long long>(el[k * e + a]) + d] : 0.0;
+  double measure;
+  if (k == 2) { // Edge::getLength
+    const double dx = p[1][0] - p[0][0], dy = p[1][1] - p[0][1], dz = p[1][2] - p[0][2];
+    measure         = sqrt(dx * dx + dy * dy + dz * dz);
+  } else if (k == 3) { // triangleArea: 0.5 |A x B|
+    const double ax = p[1][0] - p[0][0], ay = p[1][1] - p[0][1], az = p[1][2] - p[0][2];
+    const double bx = p[2][0] - p[0][0], by = p[2][1] - p[0][1], bz = p[2][2] - p[0][2];
+    if (dim == 2) {
+      measure = 0.5 * fabs(ax * by - ay * bx);
+    } else {
+      const double cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
+      measure         = 0.5 * sqrt(cx * cx + cy * cy + cz * cz);
+    }
+  } else { // tetraVolume: |(a - d) . ((b - d) x (c - d))| / 6
+    double u[3], v[3], t[3];
+    for (int d = 0; d < 3; ++d) {
+      u[d] = p[0][d] - p[3][d];
+      v[d] = p[1][d] - p[3][d];
+      t[d] = p[2][d] - p[3][d];
+    }
+    const double cx = v[1] * t[2] - v[2] * t[1], cy = v[2] * t[0] - v[0] * t[2], cz = v[0] * t[1] - v[1] * t[0];
+    measure         = fabs(u[0] * cx + u[1] * cy + u[2] * cz) / 6.0;
+  }
+  const double share = measure / static_cast<double>(k); // 0.5 length, area / 3, volume / 4 per vertex (mesh/Utils.cpp:24, 34, 65)
+  for (int a = 0; a < k; ++a)
+    atomicAdd(&w[el[k * e + a]], share);
+}
+
+// integral[c] += sum_v w[v] values[v * dims + c]
+__global__ void weightedSumKernel(const double *__restrict__ w, const double *__restrict__ values, long long n, int dims, double *__restrict__ integral)
+{
+  for (int c = 0; c < dims; ++c) {
+    double s = 0.0;
+    for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < n; v += static_cast<long long>(gridDim.x) * blockDim.x)
+      s += w[v] * values[v * dims + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s != 0.0)
+      atomicAdd(&integral[c], s);
+  }
+}
+
+// Mapping.cpp:230-235: factor = integralInput / integralOutput, 1 if the output integral is zero
+__global__ void scaleKernel(double *__restrict__ out, long long n, int dims, const double *__restrict__ integrals /* dims input, dims output */)
+{
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n * dims)
+    return;
+  const int    c   = static_cast<int>(i % dims);
+  const double den = integrals[dims + c];
+  out[i] *= (den == 0.0) ? 1.0 : integrals[c] / den;
+}
+} // namespace scaled
+} // namespace rbfmap
+using namespace rbfmap::scaled;
+
+static bool isScaledConsistent(const DeviceMapping *m)
+{
+  const int c = m->config().constraint;
+  return c == RBFMAP_SCALED_CONSISTENT_SURFACE || c == RBFMAP_SCALED_CONSISTENT_VOLUME;
+}
+
+// vertices per element that Mapping.cpp:190-192 demands: 2-D surface -> edges, 2-D volume / 3-D surface -> triangles, 3-D volume -> tetrahedra
+static int requiredElement(const DeviceMapping *m)
+{
+  const bool volume = m->config().constraint == RBFMAP_SCALED_CONSISTENT_VOLUME;
+  return m->config().dimensions == 2 ? (volume ? 3 : 2) : (volume ? 4 : 3);
+}
+
+// called after a successful computeMapping with the device copies of Mapping::input() / output()
+static void computeIntegrationWeights(rbfmap_handle *h, const double *dInputXyz, int64_t nInput, const double *dOutputXyz, int64_t nOutput)
+{
+  DeviceMapping *m = h->impl.get();
+  if (!isScaledConsistent(m))
+    return;
+  cudaStream_t     s = m->stream();
+  AllocStreamScope allocScope(s);
+  const int        k = requiredElement(m);
+  const double    *xyz[2] = {dInputXyz, dOutputXyz};
+  const int64_t    nv[2]  = {nInput, nOutput};
+  for (int which = 0; which < 2; ++which) {
+    auto &cn     = h->conn[which];
+    cn.nVertices = nv[which];
+    cn.weights.release();
+    if (nv[which] == 0 || cn.verticesPerElement != k || cn.elements.empty())
+      continue; // reported by map() with the reference's message
+    const int64_t nEl = static_cast<int64_t>(cn.elements.size()) / k;
+    for (int32_t v : cn.elements)
+      if (v < 0 || v >= nv[which])
+        throw MapError(RBFMAP_ERR_INVALID, "connectivity refers to a vertex that does not exist");
+    DevBuf<int> dEl;
+    dEl.alloc(cn.elements.size());
+    cn.weights.alloc(nv[which]);
+    RBF_CUDA(cudaMemcpyAsync(dEl.p, cn.elements.data(), cn.elements.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    RBF_CUDA(cudaMemsetAsync(cn.weights.p, 0, nv[which] * sizeof(double), s));
+    elementWeightsKernel<<<divUp(nEl, 256), 256, 0, s>>>(xyz[which], dEl.p, nEl, k, m->config().dimensions, cn.weights.p);
+    RBF_CUDA(cudaGetLastError());
+    RBF_CUDA(cudaStreamSynchronize(s)); // dEl is released on return
+  }
+}
+
+static void scaleConsistentMapping(rbfmap_handle *h, const double *dIn, int dims, double *dOut)
+{
+  DeviceMapping *m = h->impl.get();
+  const int64_t  nIn = m->nInput(), nOut = m->nOutput();
+  if (nIn == 0 || nOut == 0)
+    return; // Mapping.cpp:179-181
+  if (m->group().active())
+    throw MapError(RBFMAP_ERR_UNSUPPORTED, "Scaled-consistent mapping is only supported for serial participants."); // :186-187
+  static const char *kindName[5] = {"", "", "Edges", "Triangles", "Tetrahedra"};
+  const int          k           = requiredElement(m);
+  for (int which = 0; which < 2; ++which)
+    if (!h->conn[which].weights.p || h->conn[which].nVertices != (which == 0 ? nIn : nOut)) // :194-208
+      throw MapError(RBFMAP_ERR_INVALID, std::string(kindName[k]) + " connectivity information is missing for the mesh \"" + (which == 0 ? "input" : "output") +
+                                             "\". Scaled consistent mapping requires connectivity information.");
+  cudaStream_t     s = m->stream();
+  AllocStreamScope allocScope(s);
+  DevBuf<double>   integrals;
+  integrals.alloc(2 * static_cast<size_t>(dims));
+  RBF_CUDA(cudaMemsetAsync(integrals.p, 0, 2 * dims * sizeof(double), s));
+  const int grid = std::min(1024, std::max(1, divUp(std::max(nIn, nOut), 256)));
+  weightedSumKernel<<<grid, 256, 0, s>>>(h->conn[0].weights.p, dIn, nIn, dims, integrals.p);
+  weightedSumKernel<<<grid, 256, 0, s>>>(h->conn[1].weights.p, dOut, nOut, dims, integrals.p + dims);
+  scaleKernel<<<divUp(nOut * dims, 256), 256, 0, s>>>(dOut, nOut, dims, integrals.p);
+  RBF_CUDA(cudaGetLastError());
+  RBF_CUDA(cudaStreamSynchronize(s));
+}
+
 extern "C" {
+
+int rbfmap_set_connectivity(rbfmap_handle *h, int mesh, const int32_t *elements, int64_t n_elements, int vertices_per_element)
+{
+  if (!h)
+    return RBFMAP_ERR_INVALID;
+  return guarded(h, [&] {
+    if ((mesh != 0 && mesh != 1) || n_elements < 0 || vertices_per_element < 2 || vertices_per_element > 4 || (n_elements > 0 && !elements))
+      throw MapError(RBFMAP_ERR_INVALID, "invalid connectivity");
+    if (h->impl->hasComputedMapping())
+      throw MapError(RBFMAP_ERR_STATE, "Set the mesh connectivity before computeMapping() (the integration weights belong to the computed mapping).");
+    auto &cn              = h->conn[mesh];
+    cn.verticesPerElement = vertices_per_element;
+    cn.elements.assign(elements, elements + n_elements * vertices_per_element);
+    cn.weights.release();
+  });
+}
 
 void rbfmap_default_config(rbfmap_config *cfg)
 {
@@ -360,6 +527,7 @@ int rbfmap_compute_mapping_device(rbfmap_handle *h, const double *d_input_xyz, i
     if (n_input < 0 || n_output < 0)
       throw MapError(RBFMAP_ERR_INVALID, "negative mesh size");
     h->impl->computeMapping(d_input_xyz, n_input, d_output_xyz, n_output);
+    computeIntegrationWeights(h, d_input_xyz, n_input, d_output_xyz, n_output);
   });
 }
 
@@ -370,10 +538,22 @@ int rbfmap_compute_mapping(rbfmap_handle *h, const double *input_xyz, int64_t n_
   return guarded(h, [&] {
     if (n_input < 0 || n_output < 0)
       throw MapError(RBFMAP_ERR_INVALID, "negative mesh size");
-    if (h->impl->computeMappingHost(input_xyz, n_input, output_xyz, n_output))
-      return;
     cudaStream_t     s = h->impl->stream();
     AllocStreamScope allocScope(s);
+    if (h->impl->computeMappingHost(input_xyz, n_input, output_xyz, n_output)) {
+      if (isScaledConsistent(h->impl.get())) { // the integration weights need the coordinates once more (small serial meshes)
+        h->dInXyz.alloc(3 * std::max<int64_t>(n_input, 1));
+        h->dOutXyz.alloc(3 * std::max<int64_t>(n_output, 1));
+        if (n_input > 0)
+          RBF_CUDA(cudaMemcpyAsync(h->dInXyz.p, input_xyz, 3 * n_input * sizeof(double), cudaMemcpyHostToDevice, s));
+        if (n_output > 0)
+          RBF_CUDA(cudaMemcpyAsync(h->dOutXyz.p, output_xyz, 3 * n_output * sizeof(double), cudaMemcpyHostToDevice, s));
+        computeIntegrationWeights(h, h->dInXyz.p, n_input, h->dOutXyz.p, n_output);
+        h->dInXyz.release();
+        h->dOutXyz.release();
+      }
+      return;
+    }
     const ShardGroup &grp = h->impl->group();
     h->dInXyz.alloc(std::max<int64_t>(grp.padded(3 * n_input), 1));
     h->dOutXyz.alloc(std::max<int64_t>(grp.padded(3 * n_output), 1));
@@ -381,6 +561,7 @@ int rbfmap_compute_mapping(rbfmap_handle *h, const double *input_xyz, int64_t n_
     h->impl->uploadReplicated(h->dOutXyz.p, output_xyz, 3 * n_output, s);
     RBF_CUDA(cudaStreamSynchronize(s));
     h->impl->computeMapping(h->dInXyz.p, n_input, h->dOutXyz.p, n_output);
+    computeIntegrationWeights(h, h->dInXyz.p, n_input, h->dOutXyz.p, n_output);
     // the mapping keeps its own copies; release the staging buffers
     h->dInXyz.release();
     h->dOutXyz.release();
@@ -471,6 +652,9 @@ static void mapDeviceImpl(rbfmap_handle *h, int mode /*0 dispatch, 1 consistent,
   else
     m->mapConsistent(d_in, dims, d_out);
   RBF_CUDA(cudaStreamSynchronize(m->stream()));
+  // Mapping.cpp:167-169: scaled-consistent = mapConsistent + scaleConsistentMapping (only through the dispatching map())
+  if (mode == 0 && isScaledConsistent(m))
+    scaleConsistentMapping(h, d_in, dims, d_out);
 }
 
 static int mapHostImpl(rbfmap_handle *h, int mode, const double *in, int dims, double *out)

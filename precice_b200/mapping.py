@@ -160,6 +160,13 @@ class _Mapping:
         assert isinstance(out, np.ndarray) and out.dtype == np.float64 and out.flags.c_contiguous and out.size == self._n_mesh * cache.dims
         self._check(self._L.rbfmap_complete_just_in_time_mapping(self._h, cache._c, out.ctypes.data))
 
+    def setConnectivity(self, mesh: str, elements):
+        """Edges / triangles / tetrahedra (rows of vertex IDs) of Mapping::input() ("input") or output() ("output") for the
+        scaled-consistent constraints (Mapping.cpp:175-246); call before computeMapping."""
+        e = np.ascontiguousarray(elements, dtype=np.int32)
+        assert e.ndim == 2 and e.shape[1] in (2, 3, 4)
+        self._check(self._L.rbfmap_set_connectivity(self._h, {"input": 0, "output": 1}[mesh], e.ctypes.data, e.shape[0], e.shape[1]))
+
     # -- re-partitioning hooks (Mapping.hpp:179-182)
     def tagMeshFirstRound(self, input_xyz, output_xyz, tags=None) -> np.ndarray:
         """Tags (1) the vertices of the remote mesh - input() for consistent, output() for conservative constraints - that

@@ -99,3 +99,94 @@ def test_unknown_modes_are_rejected(pb):
         h = C.c_void_p()
         assert L.rbfmap_create(C.byref(cfg), C.byref(h)) == 1  # RBFMAP_ERR_INVALID
         setattr(cfg, field, 0)
+
+
+# ---------------------------------------------------------------------------------------------- scaled-consistent
+def _integral(xyz, elements, values, dims, dim):
+    """mesh::integrateSurface / integrateVolume (mesh/Utils.cpp:11-70) in the reference's element order."""
+    total = np.zeros(dims)
+    v = np.asarray(values).reshape(-1, dims)
+    for e in elements:
+        p = xyz[list(e), :dim]
+        if len(e) == 2:
+            measure = np.linalg.norm(p[1] - p[0])
+        elif len(e) == 3:
+            a, b = p[1] - p[0], p[2] - p[0]
+            measure = 0.5 * abs(a[0] * b[1] - a[1] * b[0]) if dim == 2 else 0.5 * np.linalg.norm(np.cross(a, b))
+        else:
+            measure = abs(np.dot(p[0] - p[3], np.cross(p[1] - p[3], p[2] - p[3]))) / 6.0
+        total += measure / len(e) * v[list(e)].sum(0)
+    return total
+
+
+SCALED_MAPPINGS = [
+    lambda pb, c, d: pb.RadialBasisFctMapping(c, d, "thin-plate-splines", polynomial="separate"),
+    lambda pb, c, d: pb.RadialBasisFctMapping(c, d, "compact-polynomial-c6", 5.0, polynomial="separate"),
+    lambda pb, c, d: pb.RadialBasisFctMapping(c, d, "gaussian", 1.0, polynomial="separate", solver="iterative"),
+    lambda pb, c, d: pb.PartitionOfUnityMapping(c, d, "compact-polynomial-c6", 5.0, "separate", 50, 0.15, True),
+]
+
+
+@pytest.mark.parametrize("make", SCALED_MAPPINGS)
+def test_scaled_consistent_2d(pb, make):
+    """perform2DTestScaledConsistentMapping (mapping/tests/RadialBasisFctHelper.hpp:397-447): edges, scalar data."""
+    inp = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0]], float)
+    out = np.array([[0, 0, 0], [0, 1, 0], [1.1, 1.1, 0], [0.1, 1.1, 0]], float)
+    e_in, e_out = [(0, 1), (1, 2), (2, 3), (0, 3)], [(0, 1), (1, 2), (2, 3), (0, 3)]
+    vals = np.array([1.0, 2.0, 2.0, 1.0])
+    m = make(pb, "scaled-consistent-surface", 2)
+    m.setConnectivity("input", e_in)
+    m.setConnectivity("output", e_out)
+    m.computeMapping(inp, out)
+    res = m.map(vals, 1)
+    assert _integral(out, e_out, res, 1, 2) == pytest.approx(_integral(inp, e_in, vals, 1, 2), rel=1e-12)
+    # the scaling is one factor per component on top of the consistent result
+    plain = make(pb, "consistent", 2)
+    plain.computeMapping(inp, out)
+    ratio = res / plain.map(vals, 1)
+    assert np.allclose(ratio, ratio[0], rtol=1e-12) and abs(ratio[0] - 1.0) > 1e-3
+
+
+@pytest.mark.parametrize("make", SCALED_MAPPINGS)
+def test_scaled_consistent_3d_surface_vector(pb, make):
+    """perform3DTestScaledConsistentMapping (:449-505), with a 2-component field: one factor per component."""
+    inp = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0.5], [2, 0, 0], [0, 2, 0], [0, 2, 1]], float)
+    out = np.array([[0, 0, 0], [1, 0, 0], [0, 1.1, 0.6]], float)
+    t_in, t_out = [(0, 1, 2), (3, 4, 5)], [(0, 1, 2)]
+    vals = np.stack([[1.0, 2.0, 4.0, 6.0, 8.0, 9.0], [3.0, -1.0, 0.5, 2.0, 2.0, 7.0]], axis=1).reshape(-1)
+    m = make(pb, "scaled-consistent-surface", 3)
+    m.setConnectivity("input", t_in)
+    m.setConnectivity("output", t_out)
+    m.computeMapping(inp, out)
+    res = m.map(vals, 2)
+    assert _integral(out, t_out, res, 2, 3) == pytest.approx(_integral(inp, t_in, vals, 2, 3), rel=1e-12)
+
+
+def test_scaled_consistent_volume_and_errors(pb):
+    rng = np.random.default_rng(11)
+    inp, out = rng.random((40, 3)), rng.random((30, 3))
+    tets_in = [tuple(rng.choice(40, 4, replace=False)) for _ in range(25)]
+    tets_out = [tuple(rng.choice(30, 4, replace=False)) for _ in range(20)]
+    vals = rng.random(40) + 1.0
+    m = pb.RadialBasisFctMapping("scaled-consistent-volume", 3, "thin-plate-splines", polynomial="separate")
+    m.setConnectivity("input", tets_in)
+    m.computeMapping(inp, out)
+    with pytest.raises(pb.MappingError) as e:  # Mapping.cpp:204-206
+        m.map(vals, 1)
+    assert 'Tetrahedra connectivity information is missing for the mesh "output"' in str(e.value)
+    with pytest.raises(pb.MappingError) as e:  # the weights belong to the computed mapping
+        m.setConnectivity("output", tets_out)
+    assert e.value.status == "STATE"
+    m.clear()
+    m.setConnectivity("output", tets_out)
+    m.computeMapping(inp, out)
+    res = m.map(vals, 1)
+    assert _integral(out, tets_out, res, 1, 3) == pytest.approx(_integral(inp, tets_in, vals, 1, 3), rel=1e-12)
+    # triangles where tetrahedra are required count as missing
+    m2 = pb.RadialBasisFctMapping("scaled-consistent-volume", 3, "thin-plate-splines", polynomial="separate")
+    m2.setConnectivity("input", [(0, 1, 2)])
+    m2.setConnectivity("output", [(0, 1, 2)])
+    m2.computeMapping(inp, out)
+    with pytest.raises(pb.MappingError) as e:
+        m2.map(vals, 1)
+    assert "Tetrahedra connectivity information is missing" in str(e.value)
