@@ -105,6 +105,11 @@ typedef struct rbfmap_config {
   int      execution_mode;       /* rbfmap_execution_mode (PUM), default minimal-memory = the constructor default
                                     computeEvaluationOffline = false (PartitionOfUnityMapping.hpp:57) */
   int      shard_mode;           /* rbfmap_shard_mode (PUM after rbfmap_distributed_init), default DUPLICATE */
+  int      rescaling;            /* rbf-global-iterative, consistent + polynomial separate: divide the interpolant by the
+                                    interpolant of g(x) = 1 (PetRadialBasisFctMapping.hpp:109, 126-127, 470-490, 663-666);
+                                    default 1 = the reference's hard-wired useRescaling = true */
+  double   output_filter;        /* rbf-global-iterative: mapped values with |x| < output_filter become exactly 0
+                                    (VecFilter(out, 1e-9), PetRadialBasisFctMapping.hpp:25-32, 675, 799); default 1e-9, 0 = off */
   int      deterministic;        /* PUM: 1 = blend by a per-vertex gather in ascending cluster order instead of atomics
                                     (bit-reproducible output), default 0 */
 } rbfmap_config;
@@ -182,6 +187,17 @@ void rbfmap_host_free(void *ptr);
 int rbfmap_map(rbfmap_handle *h, const double *in, int dims, double *out);
 int rbfmap_map_consistent(rbfmap_handle *h, const double *in, int dims, double *out);   /* Mapping.hpp:337 */
 int rbfmap_map_conservative(rbfmap_handle *h, const double *in, int dims, double *out); /* Mapping.hpp:324 */
+
+/* Mapping::map(Sample, VectorXd&, VectorXd &lastSolution) (Mapping.cpp:150-156): the variant for mappings with
+ * Mapping::requiresInitialGuess() (InitialGuessRequirement::Required, PetRadialBasisFctMapping.hpp:176) - the caller
+ * (precice/impl/DataContext.cpp:159-161) owns one `guess` vector per data and hands it to every map() of that data: the
+ * iterative solve starts from it and stores its solution there (loadInitialGuessForDim / storeInitialGuessForDim,
+ * PetRadialBasisFctMapping.hpp:526-561). `guess` holds rbfmap_initial_guess_size(h) * dims doubles, dimension-major;
+ * zero-fill it before the first use and after every computeMapping. Mappings without iterative solver report size 0
+ * and ignore `guess`. rbfmap_map() on an iterative mapping keeps ONE internal guess per handle instead (the behaviour of
+ * GinkgoRadialBasisFctSolver.hpp:218-221, 437). Host pointers. */
+int64_t rbfmap_initial_guess_size(const rbfmap_handle *h);
+int     rbfmap_map_with_initial_guess(rbfmap_handle *h, const double *in, int dims, double *out, double *guess);
 
 /* Same two calls with DEVICE pointers (coordinates / values already resident in HBM); used by
  * device-resident callers and by bench.py's kernel-only figure. The work is enqueued on the

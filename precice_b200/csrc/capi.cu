@@ -499,6 +499,8 @@ void rbfmap_default_config(rbfmap_config *cfg)
   cfg->execution_mode       = RBFMAP_MINIMAL_MEMORY; // PartitionOfUnityMapping.hpp:57 (computeEvaluationOffline = false)
   cfg->shard_mode           = RBFMAP_SHARD_DUPLICATE;
   cfg->deterministic        = 0;
+  cfg->rescaling            = 1;    // PetRadialBasisFctMapping.hpp:126-127 (useRescaling = true)
+  cfg->output_filter        = 1e-9; // PetRadialBasisFctMapping.hpp:675, 799
 }
 
 int rbfmap_create(const rbfmap_config *cfg, rbfmap_handle **out)
@@ -657,7 +659,7 @@ static void mapDeviceImpl(rbfmap_handle *h, int mode /*0 dispatch, 1 consistent,
     scaleConsistentMapping(h, d_in, dims, d_out);
 }
 
-static int mapHostImpl(rbfmap_handle *h, int mode, const double *in, int dims, double *out)
+static int mapHostImpl(rbfmap_handle *h, int mode, const double *in, int dims, double *out, double *guess = nullptr)
 {
   if (!h)
     return RBFMAP_ERR_INVALID;
@@ -677,7 +679,11 @@ static int mapHostImpl(rbfmap_handle *h, int mode, const double *in, int dims, d
     if (h->dOut.n < static_cast<size_t>(std::max<int64_t>(nOut, 1)))
       h->dOut.alloc(std::max<int64_t>(nOut, 1));
     m->uploadReplicated(h->dIn.p, in, nIn, s); // distributed: 1/world of the values per rank over PCIe, all-gather over NVLink
+    if (guess)
+      m->loadInitialGuess(guess, dims);
     mapDeviceImpl(h, mode, h->dIn.p, dims, h->dOut.p);
+    if (guess)
+      m->storeInitialGuess(guess, dims);
     if (nOut > 0)
       RBF_CUDA(cudaMemcpyAsync(out, h->dOut.p, nOut * sizeof(double), cudaMemcpyDeviceToHost, s));
     RBF_CUDA(cudaStreamSynchronize(s));
@@ -687,6 +693,13 @@ static int mapHostImpl(rbfmap_handle *h, int mode, const double *in, int dims, d
 int rbfmap_map(rbfmap_handle *h, const double *in, int dims, double *out) { return mapHostImpl(h, 0, in, dims, out); }
 int rbfmap_map_consistent(rbfmap_handle *h, const double *in, int dims, double *out) { return mapHostImpl(h, 1, in, dims, out); }
 int rbfmap_map_conservative(rbfmap_handle *h, const double *in, int dims, double *out) { return mapHostImpl(h, 2, in, dims, out); }
+
+int64_t rbfmap_initial_guess_size(const rbfmap_handle *h) { return h ? h->impl->initialGuessSize() : 0; }
+
+int rbfmap_map_with_initial_guess(rbfmap_handle *h, const double *in, int dims, double *out, double *guess)
+{
+  return mapHostImpl(h, 0, in, dims, out, (h && h->impl->initialGuessSize() > 0) ? guess : nullptr);
+}
 
 int rbfmap_map_device(rbfmap_handle *h, const double *d_in, int dims, double *d_out)
 {

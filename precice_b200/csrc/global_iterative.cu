@@ -384,6 +384,30 @@ __global__ void projectAxesKernel(double *__restrict__ xyz, long long n, int dea
       xyz[3 * i + d] = 0.0; // (u - v) * 0 of RadialBasisFctSolver.hpp:102-113
 }
 
+// VecPointwiseDivide (PETSc): w[i] = x[i] / y[i], 0 where y[i] == 0 (PetRadialBasisFctMapping.hpp:663-666)
+__global__ void pointwiseDivideKernel(double *__restrict__ x, int64_t ld, int nc, const double *__restrict__ y, int64_t n)
+{
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n)
+    return;
+  const double d = y[i];
+  for (int c = 0; c < nc; ++c)
+    x[c * ld + i] = d != 0.0 ? x[c * ld + i] / d : 0.0;
+}
+// VecFilter / VecChop (PetRadialBasisFctMapping.hpp:25-32): |x| < tol -> 0
+__global__ void filterKernel(double *__restrict__ x, int64_t n, double tol)
+{
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < n && fabs(x[i]) < tol)
+    x[i] = 0.0;
+}
+__global__ void fillKernel(double *__restrict__ x, int64_t n, double v)
+{
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < n)
+    x[i] = v;
+}
+
 inline int reduceGrid(int64_t n) { return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, static_cast<int64_t>(smCount()) * 8))); }
 
 class GlobalIterativeMapping final : public DeviceMapping {
@@ -423,12 +447,35 @@ public:
     _guess.release();
     _guessDims = 0;
   }
+  // Mapping::initialGuess(): caller-owned warm start, one vector per data (PetRadialBasisFctMapping.hpp:176, 526-561)
+  int64_t initialGuessSize() const override { return _computed ? _group.padded(_nIn) : 0; }
+  void    loadInitialGuess(const double *hGuess, int dims) override
+  {
+    AllocStreamScope allocScope(_stream);
+    const size_t     count = static_cast<size_t>(_group.padded(_nIn)) * dims;
+    if (_guessDims != dims || _guess.n != count) {
+      _guess.alloc(count);
+      _guessDims = dims;
+    }
+    if (count > 0)
+      RBF_CUDA(cudaMemcpyAsync(_guess.p, hGuess, count * sizeof(double), cudaMemcpyHostToDevice, _stream));
+  }
+  void storeInitialGuess(double *hGuess, int dims) override
+  {
+    const size_t count = static_cast<size_t>(_group.padded(_nIn)) * dims;
+    if (count > 0 && _guessDims == dims && _guess.n == count) {
+      RBF_CUDA(cudaMemcpyAsync(hGuess, _guess.p, count * sizeof(double), cudaMemcpyDeviceToHost, _stream));
+      RBF_CUDA(cudaStreamSynchronize(_stream));
+    }
+  }
   void clear() override
   {
     _inGrid  = BinGrid();
     _outGrid = BinGrid();
     _guess.release();
     _guessDims = 0;
+    _oneInterpolant.release();
+    _rescale = false;
     _computed  = false;
     stats      = rbfmap_stats{};
   }
@@ -454,6 +501,10 @@ private:
   PolyIt         _poly{};
   DevBuf<double> _guess; // warm start, cell order, one vector per data component
   int            _guessDims = 0;
+  // rescaling (PetRadialBasisFctMapping.hpp:109, 470-490): interpolant of g(x) = 1 at the output sites, cell order
+  DevBuf<double> _oneInterpolant;
+  bool           _rescale = false;
+  void           setupRescaling();
 };
 
 void GlobalIterativeMapping::apply(const BinGrid &rows, int64_t rb, int64_t re, const BinGrid &cols, const double *x, int64_t ldx, double *y, int64_t ldy,
@@ -576,6 +627,41 @@ void GlobalIterativeMapping::setupPolynomial()
       _poly.G[4 * r + s] = (r < p && s < p) ? inv[r][s] : 0.0;
 }
 
+// PetRadialBasisFctMapping.hpp:470-490: rescaling coefficients = C^-1 1 with the system-matrix solver, interpolant of
+// g(x) = 1 at the output sites, entries below 1e-6 set to exactly 0. Only for consistent mappings with a separated
+// polynomial; a solve that does not converge deactivates the rescaling (the reference warns and does the same).
+void GlobalIterativeMapping::setupRescaling()
+{
+  _rescale = false;
+  if (!_cfg.rescaling || isConservative() || _poly.mode != 1 || _nIn == 0 || _nOut == 0)
+    return;
+  int64_t ib, ie, islice, ob, oe, oslice;
+  partitionRows(_nIn, _group.world, _group.rank, ib, ie, islice);
+  partitionRows(_nOut, _group.world, _group.rank, ob, oe, oslice);
+  _ldIn               = islice * _group.world;
+  const int64_t ldOut = oslice * _group.world;
+  DevBuf<double> rhs, coeffs;
+  rhs.alloc(_ldIn);
+  coeffs.alloc(_ldIn);
+  fillKernel<<<divUp(_ldIn, 256), 256, 0, _stream>>>(rhs.p, _ldIn, 1.0);
+  RBF_LAUNCHED();
+  RBF_CUDA(cudaMemsetAsync(coeffs.p, 0, _ldIn * sizeof(double), _stream));
+  try {
+    cg(rhs.p, coeffs.p, 1);
+  } catch (const MapError &e) {
+    if (e.code != RBFMAP_ERR_NOT_CONVERGED)
+      throw;
+    return; // "Deactivating rescaling!"
+  }
+  _oneInterpolant.alloc(ldOut);
+  apply(_outGrid, ob, oe, _inGrid, coeffs.p, _ldIn, _oneInterpolant.p, ldOut, 1, nullptr, 0, nullptr);
+  allGatherSlices(_oneInterpolant.p, ldOut, 1, oslice);
+  filterKernel<<<divUp(ldOut, 256), 256, 0, _stream>>>(_oneInterpolant.p, ldOut, 1e-6);
+  RBF_LAUNCHED();
+  RBF_CUDA(cudaStreamSynchronize(_stream));
+  _rescale = true;
+}
+
 void GlobalIterativeMapping::computeMapping(const double *dInputXyz, int64_t nInput, const double *dOutputXyz, int64_t nOutput)
 {
   g_launches = 0;
@@ -623,7 +709,14 @@ void GlobalIterativeMapping::computeMapping(const double *dInputXyz, int64_t nIn
   _inGrid.build(inXyz.p, _nIn, iMin, iMax, cell, _stream);
   _outGrid.build(outXyz.p, _nOut, oMin, oMax, cell, _stream);
   setupPolynomial();
-  stats.device_bytes       = static_cast<int64_t>(_inGrid.bytes() + _outGrid.bytes());
+  _computed = true; // the operator is complete; the rescaling coefficients are obtained with it
+  try {
+    setupRescaling();
+  } catch (...) {
+    _computed = false;
+    throw;
+  }
+  stats.device_bytes       = static_cast<int64_t>(_inGrid.bytes() + _outGrid.bytes() + _oneInterpolant.bytes());
   stats.ms_compute_kernels = whole.stop();
   stats.kernel_launches    = g_launches;
   _computed                = true;
@@ -759,8 +852,16 @@ void GlobalIterativeMapping::map(bool conservative, const double *dIn, int dims,
         o.alloc(static_cast<size_t>(ldOut) * nc);
         apply(_outGrid, ob, oe, _inGrid, x, _ldIn, o.p, ldOut, nc, nullptr, 0, nullptr); // this rank's evaluation rows
         allGatherSlices(o.p, ldOut, nc, oslice);
+        if (_rescale) { // :663-666
+          pointwiseDivideKernel<<<divUp(_nOut, 256), 256, 0, _stream>>>(o.p, ldOut, nc, _oneInterpolant.p, _nOut);
+          RBF_LAUNCHED();
+        }
         if (_poly.mode == 1) {
           applyItKernel<<<divUp(_nOut, 256), 256, 0, _stream>>>(_outGrid.xyz.p, _nOut, _poly, beta.p, nc, 1.0, o.p, ldOut);
+          RBF_LAUNCHED();
+        }
+        if (_cfg.output_filter > 0.0) { // :675
+          filterKernel<<<divUp(ldOut * nc, 256), 256, 0, _stream>>>(o.p, ldOut * nc, _cfg.output_filter);
           RBF_LAUNCHED();
         }
         scatterInterleavedKernel<<<divUp(_nOut, 256), 256, 0, _stream>>>(o.p, ldOut, nc, _outGrid.ids.p, _nOut, dims, c0, dOut);
@@ -789,6 +890,10 @@ void GlobalIterativeMapping::map(bool conservative, const double *dIn, int dims,
             RBF_LAUNCHED();
           }
           applyItKernel<<<divUp(_nIn, 256), 256, 0, _stream>>>(_inGrid.xyz.p, _nIn, _poly, beta.p, nc, 1.0, o.p, _ldIn);
+          RBF_LAUNCHED();
+        }
+        if (_cfg.output_filter > 0.0) { // :799
+          filterKernel<<<divUp(_ldIn * nc, 256), 256, 0, _stream>>>(o.p, _ldIn * nc, _cfg.output_filter);
           RBF_LAUNCHED();
         }
         scatterInterleavedKernel<<<divUp(_nIn, 256), 256, 0, _stream>>>(o.p, _ldIn, nc, _inGrid.ids.p, _nIn, dims, c0, dOut);

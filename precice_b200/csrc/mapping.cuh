@@ -66,6 +66,11 @@ public:
     throw MapError(RBFMAP_ERR_UNSUPPORTED, "the cluster radius belongs to rbf-pum-direct");
   }
 
+  // ---- caller-owned initial guess of iterative mappings (Mapping::requiresInitialGuess / initialGuess, Mapping.hpp) ----
+  virtual int64_t initialGuessSize() const { return 0; }                      // per data dimension; 0 = none needed
+  virtual void    loadInitialGuess(const double * /*hGuess*/, int /*dims*/) {} // before map()
+  virtual void    storeInitialGuess(double * /*hGuess*/, int /*dims*/) {}      // after map()
+
   bool                 hasComputedMapping() const { return _computed; }
   bool                 isConservative() const { return _cfg.constraint == RBFMAP_CONSERVATIVE; }
   const rbfmap_config &config() const { return _cfg; }

@@ -119,6 +119,21 @@ class _Mapping:
         """Mapping::map(Sample, VectorXd&): dispatch on the constraint (Mapping.cpp:158-173)."""
         return self._map(self._L.rbfmap_map, values, dims, out)
 
+    def initialGuessSize(self) -> int:
+        """Per-dimension length of the caller-owned initial guess (0: the mapping needs none, Mapping::requiresInitialGuess)."""
+        return int(self._L.rbfmap_initial_guess_size(self._h))
+
+    def mapWithInitialGuess(self, values, dims, guess, out=None):
+        """Mapping::map(input, output, lastSolution) (Mapping.cpp:150-156): `guess` (float64, initialGuessSize() * dims,
+        zero before the first use) is read as the start of the iterative solve and overwritten with its solution."""
+        v = np.ascontiguousarray(np.asarray(values, dtype=np.float64).reshape(-1))
+        assert v.size == self._n_input * dims
+        assert guess.dtype == np.float64 and guess.flags.c_contiguous and guess.size == self.initialGuessSize() * dims
+        if out is None:
+            out = np.zeros(self._n_output * dims)
+        self._check(self._L.rbfmap_map_with_initial_guess(self._h, v.ctypes.data, dims, out.ctypes.data, guess.ctypes.data))
+        return out
+
     def mapConsistent(self, values, dims=1, out=None):
         return self._map(self._L.rbfmap_map_consistent, values, dims, out)
 
@@ -239,7 +254,8 @@ class MappingDataCache:
 
 def _config(variant, constraint, dim, basis, param, polynomial, dead_axis=(False, False, False), vpc=50, overlap=0.15,
             project=True, gauss_support=None, solver_rtol=1e-9, max_iterations=1000000, device_id=-1,
-            execution_mode="minimal-memory", shard_mode="duplicate", deterministic=False) -> Config:
+            execution_mode="minimal-memory", shard_mode="duplicate", deterministic=False, rescaling=True,
+            output_filter=1e-9) -> Config:
     cfg = Config()
     _lib.lib().rbfmap_default_config(C.byref(cfg))
     cfg.variant = VARIANT[variant]
@@ -264,6 +280,8 @@ def _config(variant, constraint, dim, basis, param, polynomial, dead_axis=(False
     cfg.execution_mode = _lib.EXECUTION_MODE[execution_mode]
     cfg.shard_mode = _lib.SHARD_MODE[shard_mode]
     cfg.deterministic = int(bool(deterministic))
+    cfg.rescaling = int(bool(rescaling))
+    cfg.output_filter = float(output_filter)
     return cfg
 
 
@@ -301,11 +319,14 @@ class RadialBasisFctMapping(_Mapping):
     (<mapping:rbf-global-iterative>, matrix-free CG)."""
 
     def __init__(self, constraint, dim, basis, param=0.0, dead_axis=(False, False, False), polynomial="separate",
-                 gauss_support=None, solver="direct", solver_rtol=1e-9, max_iterations=1000000, device_id=-1):
+                 gauss_support=None, solver="direct", solver_rtol=1e-9, max_iterations=1000000, device_id=-1,
+                 rescaling=True, output_filter=1e-9):
+        """rescaling / output_filter: semantics of the reference's iterative path (PetRadialBasisFctMapping.hpp:126-127,
+        470-490, 663-666 and VecFilter :675, :799); ignored by the direct solver."""
         variant = "rbf-global-direct" if solver == "direct" else "rbf-global-iterative"
         super().__init__(_config(variant, constraint, dim, basis, param, polynomial, dead_axis=dead_axis,
                                  gauss_support=gauss_support, solver_rtol=solver_rtol, max_iterations=max_iterations,
-                                 device_id=device_id))
+                                 device_id=device_id, rescaling=rescaling, output_filter=output_filter))
 
 
 def eval_basis(basis: str, param: float, radii, gauss_support=None) -> np.ndarray:

@@ -41,7 +41,8 @@ def test_struct_layouts_match_header():
     assert cfg.device_id == -1
     assert cfg.execution_mode == _lib.EXECUTION_MODE["minimal-memory"]  # PartitionOfUnityMapping.hpp:57
     assert cfg.shard_mode == _lib.SHARD_MODE["duplicate"] and cfg.deterministic == 0
-    assert C.sizeof(_lib.Config) == 104
+    assert cfg.rescaling == 1 and cfg.output_filter == 1e-9  # PetRadialBasisFctMapping.hpp:126-127, 675
+    assert C.sizeof(_lib.Config) == 120
     assert C.sizeof(_lib.Stats) == 176
     a, b = C.c_int(0), C.c_int(0)
     _lib.lib().rbfmap_struct_sizes(C.byref(a), C.byref(b))  # what the compiler laid out

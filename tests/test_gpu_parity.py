@@ -481,7 +481,10 @@ def test_global_iterative_vs_direct_oracle(pb, orc, basis, param, polynomial, co
     out = refcases.halton(m, (7, 11, 13))
     a, b = (inp, out) if constraint == "consistent" else (out, inp)
     vals = refcases.field(a)
-    g = pb.RadialBasisFctMapping(constraint, 3, basis, param, polynomial=polynomial, solver="iterative", solver_rtol=1e-12)
+    # the oracle restates the direct (Eigen) path: the PETSc-only post-processing (rescaling, VecFilter) is switched off
+    # here and tested on its own in test_global_iterative_petsc_semantics
+    g = pb.RadialBasisFctMapping(constraint, 3, basis, param, polynomial=polynomial, solver="iterative", solver_rtol=1e-12,
+                                 rescaling=False, output_filter=0.0)
     o = orc.GlobalMapping(constraint, 3, basis, param, polynomial=polynomial)
     g.compute_mapping(a, b)
     o.compute_mapping(a, b)
@@ -502,10 +505,68 @@ def test_global_iterative_matches_device_direct(pb):
     out = refcases.halton(n, (7, 11, 13))
     vals = refcases.field(inp)
     d = pb.RadialBasisFctMapping("consistent", 3, "compact-polynomial-c4", 0.25, polynomial="separate")
-    i = pb.RadialBasisFctMapping("consistent", 3, "compact-polynomial-c4", 0.25, polynomial="separate", solver="iterative", solver_rtol=1e-11)
+    i = pb.RadialBasisFctMapping("consistent", 3, "compact-polynomial-c4", 0.25, polynomial="separate", solver="iterative", solver_rtol=1e-11,
+                                 rescaling=False, output_filter=0.0)
     d.compute_mapping(inp, out)
     i.compute_mapping(inp, out)
     assert refcases.rel_l2(i.map(vals, 1), d.map(vals, 1)) <= 1e-7
+
+
+def test_global_iterative_petsc_semantics(pb, orc):
+    """PetRadialBasisFctMapping.hpp: rescaling by the interpolant of 1 (:470-490, 663-666; consistent + separate polynomial
+    only), VecFilter(out, 1e-9) (:675, :799) and the caller-owned initial guess (:526-561), against a dense numpy
+    restatement (basis function values from the oracle)."""
+    n, m = 1500, 1300
+    inp, out = refcases.halton(n, (2, 3, 5)), refcases.halton(m, (7, 11, 13))
+    vals = refcases.field(inp) - 0.8  # crosses zero: some mapped values are tiny
+    basis, support = "compact-polynomial-c2", 0.3
+    dist = lambda a, b: np.sqrt(((a[:, None, :] - b[None, :, :]) ** 2).sum(-1))
+    C = orc.basis_eval(basis, support, dist(inp, inp).reshape(-1)).reshape(n, n)
+    A = orc.basis_eval(basis, support, dist(out, inp).reshape(-1)).reshape(m, n)
+    Q, V = np.concatenate([np.ones((n, 1)), inp], 1), np.concatenate([np.ones((m, 1)), out], 1)
+    one = A @ np.linalg.solve(C, np.ones(n))
+    one[np.abs(one) < 1e-6] = 0.0
+    beta = np.linalg.lstsq(Q, vals, rcond=None)[0]
+    plain = A @ np.linalg.solve(C, vals - Q @ beta)
+    expected = np.where(one != 0.0, plain / np.where(one != 0.0, one, 1.0), 0.0) + V @ beta
+    g = pb.RadialBasisFctMapping("consistent", 3, basis, support, polynomial="separate", solver="iterative", solver_rtol=1e-12)
+    g.compute_mapping(inp, out)
+    res = g.map(vals, 1)
+    assert refcases.rel_l2(res, expected) <= 1e-8
+    assert refcases.rel_l2(res, plain + V @ beta) > 1e-6  # the rescaling is not a no-op on this mesh
+    # VecFilter: a field whose image is below the tolerance everywhere except for exact zeros
+    tiny = g.map(vals * 1e-12, 1)
+    assert np.all((tiny == 0.0) | (np.abs(tiny) >= 1e-9)) and np.count_nonzero(tiny) == 0
+    unfiltered = pb.RadialBasisFctMapping("consistent", 3, basis, support, polynomial="separate", solver="iterative", solver_rtol=1e-12,
+                                          output_filter=0.0)
+    unfiltered.compute_mapping(inp, out)
+    assert np.count_nonzero(unfiltered.map(vals * 1e-12, 1)) > 0.9 * m
+    # conservative mappings and polynomial="off" are not rescaled (:470)
+    for kw in (dict(constraint="conservative"), dict(constraint="consistent", polynomial="off")):
+        kw = {"polynomial": "separate", **kw}
+        a = pb.RadialBasisFctMapping(kw["constraint"], 3, basis, support, polynomial=kw["polynomial"], solver="iterative", solver_rtol=1e-12)
+        b = pb.RadialBasisFctMapping(kw["constraint"], 3, basis, support, polynomial=kw["polynomial"], solver="iterative", solver_rtol=1e-12,
+                                     rescaling=False)
+        a.compute_mapping(inp, inp[:m] if kw["constraint"] == "conservative" else out)
+        b.compute_mapping(inp, inp[:m] if kw["constraint"] == "conservative" else out)
+        assert refcases.rel_l2(a.map(vals, 1), b.map(vals, 1)) <= 1e-10  # two CG runs at rtol 1e-12 (atomic dot products)
+    # caller-owned initial guess, one per data: the second map of the SAME data starts converged, another data does not
+    # inherit it, and the two guesses do not disturb each other
+    assert g.initialGuessSize() == n
+    guess_a, guess_b = np.zeros(n), np.zeros(2 * n)
+    other = np.stack([np.cos(3 * inp[:, 0]), inp[:, 1] ** 2], 1).reshape(-1)
+    r1 = g.mapWithInitialGuess(vals, 1, guess_a)
+    it_first = g.stats()["iterations"]
+    assert it_first > 5 and np.any(guess_a != 0.0) and refcases.rel_l2(r1, expected) <= 1e-8
+    g.mapWithInitialGuess(other, 2, guess_b)
+    assert g.stats()["iterations"] > 5
+    r2 = g.mapWithInitialGuess(vals, 1, guess_a)
+    assert g.stats()["iterations"] <= 2 and refcases.rel_l2(r2, r1) <= 1e-10
+    # mappings without iterative solver need no guess and ignore it
+    d = pb.RadialBasisFctMapping("consistent", 3, basis, support, polynomial="separate")
+    d.compute_mapping(inp, out)
+    assert d.initialGuessSize() == 0
+    assert refcases.rel_l2(d.mapWithInitialGuess(vals, 1, np.zeros(0)), plain + V @ beta) <= 1e-9
 
 
 def test_global_iterative_not_converged_error(pb):
