@@ -30,9 +30,9 @@ public:
       throw MapError(RBFMAP_ERR_INVALID, "The relative overlap has to be smaller than one.");
     if (cfg.vertices_per_cluster == 0)
       throw MapError(RBFMAP_ERR_INVALID, "The number of vertices per cluster has to be greater zero.");
-    if (!basisIsSpd(cfg.basis))
-      throw MapError(RBFMAP_ERR_UNSUPPORTED, "rbf-pum-direct on the device requires a strictly positive definite basis function "
-                                             "(compact polynomials, compact thin-plate splines, gaussian, inverse multiquadrics).");
+    // thin-plate splines, multiquadrics, volume splines: the reference factorises with ColPivHouseholderQR
+    // (RadialBasisFctSolver.hpp:354-358); here the explicit inverse of every cluster matrix (pum_inverse.cu)
+    _inverse = !basisIsSpd(cfg.basis);
   }
 
   std::string name() const override { return "partition-of-unity RBF (cuda-executor)"; }
@@ -61,6 +61,8 @@ public:
   {
     if (_group.active())
       throw MapError(RBFMAP_ERR_UNSUPPORTED, "just-in-time mapping is not available on a sharded mapping.");
+    if (_inverse)
+      throw MapError(RBFMAP_ERR_UNSUPPORTED, "just-in-time mapping requires a strictly positive definite basis function.");
     _jit = true;
     try {
       if (isConservative())
@@ -210,6 +212,7 @@ private:
   ScratchBuf<double> _eval; // grow-only like _mat
   DevBuf<int64_t>    _evalOff;
   bool               _evalReady = false;
+  bool            _inverse = false; // basis function not strictly positive definite: explicit inverses instead of factors
   bool            _jit = false; // the other mesh is a just-in-time mesh
   BinGrid         _centerGrid;  // cluster centres, kept for just-in-time queries (PartitionOfUnityMapping.hpp:285-287)
   // upload of the solver-side outMesh beside the work on the inMesh (computeMappingHost)
@@ -239,6 +242,7 @@ PumSolveArgs PumMapping::solveArgs() const
   a.wcount  = _wcount.p;
   a.outRec  = _outRec.p;
   a.inRec   = _inRec.p;
+  a.inverse = _inverse;
   if (_evalReady) {
     a.eval    = _eval.p;
     a.evalOff = reinterpret_cast<const long long *>(_evalOff.p);
@@ -591,7 +595,7 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
   };
   if (_nClusters > 0) {
     pumBuildMembership(_centers.p, _nClusters, inGrid, outGrid, _radius, _mem, _scratch, _wsum.p, _wcount.p, _inXyz.p, _outXyz.p, _inRec, _outRec, _stream,
-                       outSlab, exchangeMode() ? std::function<void()>(weightsComplete) : std::function<void()>());
+                       outSlab, exchangeMode() ? std::function<void()>(weightsComplete) : std::function<void()>(), _inverse);
   } else { // a rank of a sharded mapping without clusters still takes part in the collectives
     _mem = PumMembership();
     if (exchangeMode())
@@ -651,7 +655,10 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
   RBF_CUDA(cudaMemcpyAsync(fail.p, &noFail, sizeof(int), cudaMemcpyHostToDevice, _stream));
   EventTimer tf(_stream);
   tf.start();
-  pumFactor(args, _buckets, fail.p, _stream);
+  if (_inverse)
+    pumInverse(args, _buckets, fail.p, _stream);
+  else
+    pumFactor(args, _buckets, fail.p, _stream);
   stats.ms_assembly_factor = tf.stop();
   trace.phase("assembly + factorisation");
   if (_group.active()) { // every rank raises the error of the failing rank (the next collective would wait for it forever)

@@ -82,7 +82,7 @@ struct PumSlab {
 void    pumBuildMembership(const double *dCenters, int64_t nClusters, const BinGrid &inMesh, const BinGrid &outMesh, double radius, PumMembership &m,
                            PumScratch &scratch, double *wsum, int *wcount, const double *inXyz, const double *outXyz, DevBuf<double> &inRec,
                            DevBuf<double4> &outRec, cudaStream_t s, const PumSlab *outSlab = nullptr,
-                           const std::function<void()> &weightsComplete = {});
+                           const std::function<void()> &weightsComplete = {}, bool fullMatrices = false);
 // sharded mapping: histogram of the centre coordinates along `axis`, selection of the centres inside [lo, hi) (order
 // preserved; globalIdx = index in the complete list), and the host-side choice of the cut positions
 std::vector<long long> pumCentreHistogram(const double *dCenters, int64_t n, int axis, double lo, double binWidth, int nBins, cudaStream_t s);
@@ -131,7 +131,12 @@ struct PumSolveArgs {
   // cluster c at eval[evalOff[c] + k * ld + l]; null = re-evaluate the basis function in every map (minimal-memory)
   const double    *eval    = nullptr;
   const long long *evalOff = nullptr;
+  // basis functions that are not strictly positive definite (pum_inverse.cu): `mat` holds the explicit inverse of every
+  // cluster matrix, n x n doubles with S[j n + i] = (C^-1)(i, j), instead of the packed factor
+  bool inverse = false;
 };
+// doubles per cluster in `mat` (even count: 16-byte aligned for the TMA bulk copy)
+__host__ __device__ inline long long pumMatSize(long long n, bool inverse) { return ((inverse ? n * n : n * (n + 1) / 2) + 1) & ~1LL; }
 
 // Clusters are bucketed by size; every bucket is served by its own kernel instantiation:
 //   buckets 0..7  : n <= 64,  8x8 threads,  NB = ceil(n/8)  = 1..8 register blocks per thread and dimension
@@ -143,6 +148,8 @@ constexpr size_t kPumMaxSmem = 200 * 1024;
 // (conservative map, 3 components: 48 B x (n + 256) + 1 KB <= kPumMaxSmem). Checked at the end of computeMapping so that
 // the caller does not learn about it in the first map() only; documented in include/rbfmap.h.
 constexpr int kPumMaxClusterVertices = 3900;
+// basis functions that are not strictly positive definite: the explicit inverse is built in shared memory (pum_inverse.cu)
+constexpr int kPumMaxInverseVertices = 128;
 __host__ __device__ inline int pumBucketOf(int n)
 {
   if (n <= 64)
@@ -173,6 +180,7 @@ void pumBuildOutRecords(const PumSolveArgs &a, int64_t nClusters, double4 *rec, 
 void pumBuildInRecords(const PumSolveArgs &a, int64_t sumIn, double *rec, cudaStream_t s);
 // fail = device int (lowest failing cluster index or INT_MAX)
 void pumFactor(const PumSolveArgs &a, const PumBuckets &b, int *fail, cudaStream_t s);
+void pumInverse(const PumSolveArgs &a, const PumBuckets &b, int *fail, cudaStream_t s); // explicit inverses (pum_inverse.cu)
 void pumFactorWarp(const PumSolveArgs &a, int bucket, const PumEntry *list, int64_t count, int *fail, cudaStream_t s);
 // execution-mode minimal-compute (pum_eval.cu): sizes / offsets of the stored evaluation matrices, and their assembly
 int64_t pumEvalOffsets(const PumMembership &m, int64_t nClusters, bool lanesAreOut, DevBuf<int64_t> &evalOff, cudaStream_t s);

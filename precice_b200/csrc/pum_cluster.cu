@@ -426,7 +426,8 @@ __device__ __forceinline__ void rankSortToGlobal(const int *stage, const int *pa
 template <bool SLAB>
 __global__ void memberGatherKernel(const double *__restrict__ centers, int64_t nClusters, BinGridView gin, BinGridView gout, double rIn, double rOut,
                                    int *__restrict__ nIn, int *__restrict__ nOut, long long *__restrict__ tri, int *__restrict__ slotIn,
-                                   int *__restrict__ slotOut, int *__restrict__ overflow, double *__restrict__ wsum, int *__restrict__ wcount, PumSlab slab)
+                                   int *__restrict__ slotOut, int *__restrict__ overflow, double *__restrict__ wsum, int *__restrict__ wcount, PumSlab slab,
+                                   bool fullMatrices)
 {
   __shared__ __align__(16) int stage[kWarpsPerBlock][kSlotCap];
   __shared__ int               stagePos[kWarpsPerBlock][kSlotCap];
@@ -445,7 +446,7 @@ __global__ void memberGatherKernel(const double *__restrict__ centers, int64_t n
   if (lane == 0) {
     nIn[c]  = ci;
     nOut[c] = co;
-    tri[c]  = (static_cast<long long>(ci) * (ci + 1) / 2 + 1) & ~1LL; // even count: 16-byte aligned factors for the TMA bulk copy
+    tri[c]  = pumMatSize(ci, fullMatrices); // even count: 16-byte aligned factors for the TMA bulk copy
     if (ci > kSlotCap || co > kSlotCap)
       atomicOr(overflow, 1);
   }
@@ -730,7 +731,7 @@ int64_t PumClustering::compact(DevBuf<double> &out, cudaStream_t s)
 
 void pumBuildMembership(const double *dCenters, int64_t nClusters, const BinGrid &inMesh, const BinGrid &outMesh, double radius, PumMembership &m,
                         PumScratch &scratch, double *wsum, int *wcount, const double *inXyz, const double *outXyz, DevBuf<double> &inRec,
-                        DevBuf<double4> &outRec, cudaStream_t s, const PumSlab *outSlab, const std::function<void()> &weightsComplete)
+                        DevBuf<double4> &outRec, cudaStream_t s, const PumSlab *outSlab, const std::function<void()> &weightsComplete, bool fullMatrices)
 {
   const PumSlab slab = outSlab ? *outSlab : PumSlab{};
   const double rOut = radius - kZeroDiff; // SphericalVertexCluster.hpp:155
@@ -755,10 +756,10 @@ void pumBuildMembership(const double *dCenters, int64_t nClusters, const BinGrid
   RBF_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), s));
   if (outSlab)
     memberGatherKernel<true><<<warpGrid(nClusters), kBlockThreads, 0, s>>>(dCenters, nClusters, inMesh.view(), outMesh.view(), radius, rOut, m.nIn.p, m.nOut.p,
-                                                                          reinterpret_cast<long long *>(m.tri.p), slotIn.p, slotOut.p, overflow.p, wsum, wcount, slab);
+                                                                          reinterpret_cast<long long *>(m.tri.p), slotIn.p, slotOut.p, overflow.p, wsum, wcount, slab, fullMatrices);
   else
     memberGatherKernel<false><<<warpGrid(nClusters), kBlockThreads, 0, s>>>(dCenters, nClusters, inMesh.view(), outMesh.view(), radius, rOut, m.nIn.p, m.nOut.p,
-                                                                           reinterpret_cast<long long *>(m.tri.p), slotIn.p, slotOut.p, overflow.p, wsum, wcount, slab);
+                                                                           reinterpret_cast<long long *>(m.tri.p), slotIn.p, slotOut.p, overflow.p, wsum, wcount, slab, fullMatrices);
   RBF_LAUNCHED();
   if (weightsComplete) // sharded mapping, exchange mode: the weight sums of the other ranks' clusters are added here
     weightsComplete();

@@ -263,6 +263,47 @@ __device__ __forceinline__ void warpSolve(const double *__restrict__ mp, int n, 
   }
 }
 
+// lambda = C^-1 f with the explicit inverse of pum_inverse.cu (S[j n + i] = (C^-1)(i, j), in shared or global memory):
+// dense matrix-vector product in place of the two triangular solves. All threads of the CTA; v rows as in warpSolve.
+template <int NC, int LDV>
+__device__ __forceinline__ void inverseApply(const double *__restrict__ S, int n, double *v, int tid, int nThreads)
+{
+  constexpr int kRows = 4; // rows per thread and pass (n <= 4 * nThreads is guaranteed by the callers: n <= 128, >= 32 threads)
+  double        acc[kRows][NC];
+#pragma unroll
+  for (int r = 0; r < kRows; ++r)
+#pragma unroll
+    for (int cc = 0; cc < NC; ++cc)
+      acc[r][cc] = 0.0;
+  for (int j = 0; j < n; ++j) {
+    double f[NC];
+#pragma unroll
+    for (int cc = 0; cc < NC; ++cc)
+      f[cc] = v[j * LDV + cc];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      const int i = tid + r * nThreads;
+      if (i < n) {
+        const double s = S[static_cast<long long>(j) * n + i];
+#pragma unroll
+        for (int cc = 0; cc < NC; ++cc)
+          acc[r][cc] = fma(s, f[cc], acc[r][cc]);
+      }
+    }
+  }
+  __syncthreads(); // every thread has read all of f
+#pragma unroll
+  for (int r = 0; r < kRows; ++r) {
+    const int i = tid + r * nThreads;
+    if (i < n) {
+#pragma unroll
+      for (int cc = 0; cc < NC; ++cc)
+        v[i * LDV + cc] = acc[r][cc];
+    }
+  }
+  __syncthreads();
+}
+
 template <typename K>
 inline void allowSmem(K kernel, size_t bytes)
 {

@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(NT) pumMapConservativeKernel(PumSolveArgs args
   const double    cx = args.centers[3 * c], cy = args.centers[3 * c + 1], cz = args.centers[3 * c + 2];
   const double    rinv = 1.0 / args.radius;
   const double    invR2 = rbf.p1 * rbf.p1;
-  const int       triPad = STAGE_M ? static_cast<int>(paddedTri(n)) : 0;
+  const int       triPad = STAGE_M ? static_cast<int>(pumMatSize(n, args.inverse)) : 0;
 
   double *ms  = dyn;
   double *vt  = dyn + triPad;       // in-vertices: x, y, z, Au / mu
@@ -154,7 +154,11 @@ __global__ void __launch_bounds__(NT) pumMapConservativeKernel(PumSolveArgs args
   __syncthreads();
 
   // ---- mu = C^-1 Au ----
-  if (STAGE_M) {
+  if (args.inverse) { // basis function not strictly positive definite: explicit inverse (pum_inverse.cu), uniform branch
+    if (STAGE_M)
+      mbarWait(&mbar, 0);
+    inverseApply<NC, LDV>(STAGE_M ? ms : mg, n, vt + 3, tid, NT);
+  } else if (STAGE_M) {
     if (tid < 32) { // one warp solves; the others wait at the barrier
       mbarWait(&mbar, 0);
       warpSolve<NC, LDV, (NT == 32 ? 2 : NT / 32)>(ms, n, vt + 3, tid);
@@ -253,7 +257,7 @@ __global__ void __launch_bounds__(NT) pumMapConservativeKernel(PumSolveArgs args
 template <int KIND, int NC, int NT, bool STAGE_M>
 void launchConservative(const PumSolveArgs &a, const int *list, int64_t count, int maxN, const double *in, int dims, int c0, double *out, cudaStream_t s)
 {
-  const size_t tri = STAGE_M ? static_cast<size_t>(paddedTri(maxN)) : 0;
+  const size_t tri = STAGE_M ? static_cast<size_t>(pumMatSize(maxN, a.inverse)) : 0;
   const size_t sm  = (tri + static_cast<size_t>(TileLd<NC>::value) * (maxN + NT) + 16 * (NT / 32)) * sizeof(double);
   if (sm > kPumMaxSmem)
     throw MapError(RBFMAP_ERR_UNSUPPORTED, "rbf-pum-direct: a cluster with " + std::to_string(maxN) + " vertices exceeds the supported cluster size.");

@@ -190,3 +190,52 @@ def test_scaled_consistent_volume_and_errors(pb):
     with pytest.raises(pb.MappingError) as e:
         m2.map(vals, 1)
     assert "Tetrahedra connectivity information is missing" in str(e.value)
+
+
+# ---------------------------------------------------------------------------------------------- non-SPD basis functions in PUM
+@pytest.mark.parametrize("constraint", ["consistent", "conservative"])
+@pytest.mark.parametrize("dim,basis,param,polynomial,dims,vpc", [
+    (3, "thin-plate-splines", 0.0, "separate", 1, 40),
+    (3, "multiquadrics", 0.05, "separate", 3, 30),
+    (3, "volume-splines", 0.0, "off", 1, 50),
+    (2, "thin-plate-splines", 0.0, "separate", 2, 35),
+    (3, "volume-splines", 0.0, "separate", 1, 90),   # clusters of 64 < n <= 128 vertices
+])
+def test_pum_with_functions_that_are_not_positive_definite(pb, constraint, dim, basis, param, polynomial, dims, vpc):
+    """RadialBasisFctSolver.hpp:354-358: thin-plate splines, multiquadrics and volume splines take the ColPivHouseholderQR
+    branch in every cluster (SphericalVertexCluster.hpp:139-182); the device builds the explicit inverse instead
+    (pum_inverse.cu). Tolerance 1e-7: the one the global variants use for the same functions (cond(C_c) up to ~1e8;
+    test_extended_precision_bounds_the_tolerances shows the oracle itself is no closer to the exact solution)."""
+    import oracle
+    n_in, n_out = 3500, 3100
+    inp, out, vals = _case(dim, n_in, n_out, dims)
+    args = (constraint, dim, basis, param, polynomial, vpc, 0.15, True)
+    for mode in ("minimal-memory", "minimal-compute"):
+        m = pb.PartitionOfUnityMapping(*args, execution_mode=mode)
+        m.computeMapping(inp, out)
+        res = m.map(vals, dims)
+        if mode == "minimal-memory":
+            orc = oracle.PumMapping(*args)
+            orc.compute_mapping(inp, out)
+            ref = orc.map(vals, dims)
+            assert m.stats()["n_clusters"] == orc.num_clusters
+        assert refcases.rel_l2(res, ref) <= 1e-7, (mode, refcases.rel_l2(res, ref))
+        if constraint == "conservative" and polynomial == "separate":
+            assert np.allclose(res.reshape(-1, dims).sum(0), vals.reshape(-1, dims).sum(0), rtol=1e-9)
+
+
+def test_pum_not_positive_definite_limits(pb):
+    inp, out, vals = _case(3, 1200, 1200, 1)
+    m = pb.PartitionOfUnityMapping("consistent", 3, "thin-plate-splines", 0.0, "separate", 300, 0.15, True)
+    with pytest.raises(pb.MappingError) as e:
+        m.computeMapping(inp, out)
+    assert e.value.status == "UNSUPPORTED" and "128 vertices" in str(e.value)
+    # duplicated vertices make the cluster matrices singular: the reference's message (RadialBasisFctSolver.hpp:360-365)
+    dup = np.concatenate([inp, inp[:40]])
+    m = pb.PartitionOfUnityMapping("consistent", 3, "volume-splines", 0.0, "separate", 40, 0.15, True)
+    with pytest.raises(pb.MappingError) as e:
+        m.computeMapping(dup, out)
+    assert e.value.status == "SINGULAR" and "is not invertable" in str(e.value)
+    with pytest.raises(pb.MappingError) as e:
+        pb.PartitionOfUnityMapping("consistent", 3, "multiquadrics", 0.1).computeMappingJustInTime(inp)
+    assert e.value.status == "UNSUPPORTED"
