@@ -308,6 +308,14 @@ int rbfmap_pum_get_cluster_ids(const rbfmap_handle *h, int32_t *in_ids /* sum_n 
  * (mapping/impl/BasisFunctions.hpp) for bit-exact parity tests. */
 int rbfmap_eval_basis(int basis, double support_radius, double shape_parameter, const double *radii, int64_t n, double *values);
 
+/* Test hook: phi(|a_i - b_i|) for n vertex pairs (n x 3 each, z ignored for dimensions = 2) computed by the PAIR
+ * evaluation of the per-cluster algebra kernels (pairBasis / pairBasisBatch, precice_b200/csrc/pum_device.cuh): for the
+ * compact polynomials fused multiply-adds, a reciprocal-root seed with a second-order correction and an integer clamp at
+ * the support, a few ulp of phi(0) away from the operation-by-operation functors that rbfmap_eval_basis exposes;
+ * batched != 0 selects the four-wide staged form. Host pointers. */
+int rbfmap_debug_pair_basis(int basis, double support_radius, double shape_parameter, int dimensions, const double *a, const double *b, int64_t n,
+                            int batched, double *values);
+
 /* Test hook: the branch-free square root the kernels apply to squared vertex distances (host pointers). */
 int rbfmap_debug_dist_sqrt(const double *x, int64_t n, double *out);
 

@@ -33,7 +33,7 @@ EXPORTS = [
     "rbfmap_map_conservative", "rbfmap_compute_mapping_device", "rbfmap_map_device", "rbfmap_clear",
     "rbfmap_has_computed_mapping", "rbfmap_destroy", "rbfmap_get_name", "rbfmap_last_error", "rbfmap_get_stats",
     "rbfmap_pum_get_clusters", "rbfmap_pum_get_cluster_ids", "rbfmap_eval_basis", "rbfmap_device_count",
-    "rbfmap_device_info", "rbfmap_measure_fp64_peak", "rbfmap_debug_dist_sqrt", "rbfmap_nccl_unique_id", "rbfmap_distributed_init",
+    "rbfmap_device_info", "rbfmap_measure_fp64_peak", "rbfmap_debug_dist_sqrt", "rbfmap_debug_pair_basis", "rbfmap_nccl_unique_id", "rbfmap_distributed_init",
     "rbfmap_partition_rows", "rbfmap_partition_slabs", "rbfmap_struct_sizes", "rbfmap_tag_mesh_first_round", "rbfmap_tag_mesh_second_round",
     "rbfmap_estimate_cluster_radius", "rbfmap_set_connectivity", "rbfmap_initial_guess_size", "rbfmap_map_with_initial_guess", "rbfmap_host_alloc", "rbfmap_host_free", "rbfmap_compute_mapping_just_in_time", "rbfmap_cache_create", "rbfmap_cache_reset", "rbfmap_cache_destroy",
     "rbfmap_cache_update", "rbfmap_map_consistent_at", "rbfmap_map_conservative_at", "rbfmap_complete_just_in_time_mapping",
@@ -109,6 +109,7 @@ def lib():
         L.rbfmap_device_info.argtypes = [C.c_int, ip, ip, ip, C.POINTER(C.c_int64)]
         L.rbfmap_measure_fp64_peak.argtypes = [dp, dp]
         L.rbfmap_debug_dist_sqrt.argtypes = [dp, C.c_int64, dp]
+        L.rbfmap_debug_pair_basis.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, dp, dp, C.c_int64, C.c_int, dp]
         L.rbfmap_nccl_unique_id.argtypes = [C.c_char_p]
         L.rbfmap_distributed_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int]
         L.rbfmap_partition_rows.argtypes = [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]

@@ -268,6 +268,7 @@ void PhaseTrace::phase(const char *name)
 
 bool pumInspect(DeviceMapping *m, int64_t &nClusters, const double *&centers, const PumMembership *&mem);
 void debugDistSqrt(const double *dX, long long n, double *dOut);
+void debugPairBasis(const RbfParams &f, bool dim3, const double *dA, const double *dB, long long n, int batched, double *dOut);
 
 namespace {
 __global__ void evalBasisKernel(RbfParams f, const double *__restrict__ r, long long n, double *__restrict__ out)
@@ -871,6 +872,27 @@ int rbfmap_eval_basis(int basis, double support_radius, double shape_parameter, 
     evalBasisKernel<<<divUp(n, 256), 256>>>(f, r.p, n, v.p);
     RBF_CUDA(cudaGetLastError());
     RBF_CUDA(cudaMemcpy(values, v.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+  });
+}
+
+int rbfmap_debug_pair_basis(int basis, double support_radius, double shape_parameter, int dimensions, const double *a, const double *b, int64_t n, int batched,
+                            double *values)
+{
+  return guarded(nullptr, [&] {
+    const RbfParams f = makeRbfParams(basis, support_radius, shape_parameter);
+    if (dimensions != 2 && dimensions != 3)
+      throw MapError(RBFMAP_ERR_INVALID, "dimensions has to be 2 or 3");
+    if (n <= 0)
+      return;
+    DevBuf<double> da, db, dv;
+    da.alloc(3 * n);
+    db.alloc(3 * n);
+    dv.alloc(n);
+    RBF_CUDA(cudaMemcpy(da.p, a, 3 * n * sizeof(double), cudaMemcpyHostToDevice));
+    RBF_CUDA(cudaMemcpy(db.p, b, 3 * n * sizeof(double), cudaMemcpyHostToDevice));
+    debugPairBasis(f, dimensions == 3, da.p, db.p, n, batched, dv.p);
+    RBF_CUDA(cudaDeviceSynchronize());
+    RBF_CUDA(cudaMemcpy(values, dv.p, n * sizeof(double), cudaMemcpyDeviceToHost));
   });
 }
 

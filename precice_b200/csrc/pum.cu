@@ -155,6 +155,7 @@ public:
     _globalIdx.release();
     _evalOff.release();
     _evalReady  = false;
+    _blendIndex = PumVertexIndex();
     _jit        = false;
     _nClusters  = 0;
     _nClustersGlobal = 0;
@@ -212,6 +213,8 @@ private:
   ScratchBuf<double> _eval; // grow-only like _mat
   DevBuf<int64_t>    _evalOff;
   bool               _evalReady = false;
+  // deterministic blend (rbfmap_config.deterministic)
+  PumVertexIndex  _blendIndex;
   bool            _inverse = false; // basis function not strictly positive definite: explicit inverses instead of factors
   bool            _jit = false; // the other mesh is a just-in-time mesh
   BinGrid         _centerGrid;  // cluster centres, kept for just-in-time queries (PartitionOfUnityMapping.hpp:285-287)
@@ -623,6 +626,21 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
     }
   }
 
+  // deterministic mode: the weight sums (accumulated with atomics above) are recomputed per vertex in cluster order and
+  // the normalised weights of the records rebuilt from them; the blend of map() uses the same vertex -> entries index
+  if (_cfg.deterministic && _nClusters > 0 && !jit) {
+    if (exchangeMode())
+      throw MapError(RBFMAP_ERR_UNSUPPORTED, "the deterministic blend is not available in the exchange shard mode (the all-reduce order is NCCL's).");
+    PumVertexIndex outIndex;
+    pumBuildVertexIndex(_mem.outIds.p, _mem.sumOut, _nOut, outIndex, _stream);
+    PumSolveArgs a0 = solveArgs();
+    pumDeterministicWeightSums(a0, _nClusters, outIndex, _wsum.p, _stream);
+    pumBuildOutRecords(a0, _nClusters, _outRec.p, _stream);
+    if (cons)
+      pumBuildVertexIndex(_mem.inIds.p, _mem.sumIn, _nIn, _blendIndex, _stream); // the result lives on the in-vertices
+    else
+      _blendIndex = std::move(outIndex);
+  }
   trace.phase("weights");
   // size buckets + statistics (device pass over the per-cluster counts)
   if (_nClusters > 0) {
@@ -712,11 +730,21 @@ void PumMapping::map(bool conservative, const double *dIn, int dims, double *dOu
   if (nRes > 0)
     RBF_CUDA(cudaMemsetAsync(dOut, 0, static_cast<size_t>(nRes) * dims * sizeof(double), _stream));
   if (_nClusters > 0) {
-    const PumSolveArgs args = solveArgs();
+    PumSolveArgs   args = solveArgs();
+    DevBuf<double> stage;
+    const bool     det = _cfg.deterministic && _blendIndex.nVertices > 0;
+    if (det) {
+      stage.alloc(static_cast<size_t>(std::max<int64_t>(conservative ? _mem.sumIn : _mem.sumOut, 1)) * dims);
+      args.blendStage = stage.p;
+    }
     if (conservative)
       pumMapConservative(args, _buckets, dIn, dims, dOut, _stream);
     else
       pumMapConsistent(args, _buckets, dIn, dims, dOut, _stream);
+    if (det) {
+      pumBlendGather(stage.p, _blendIndex, dims, dOut, _stream);
+      RBF_CUDA(cudaStreamSynchronize(_stream)); // `stage` is released on return
+    }
   }
   stats.ms_collectives = 0.f;
   if (exchangeMode()) { // every cluster has one owner: the partial blends of the ranks add up to the result

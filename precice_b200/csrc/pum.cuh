@@ -134,6 +134,10 @@ struct PumSolveArgs {
   // basis functions that are not strictly positive definite (pum_inverse.cu): `mat` holds the explicit inverse of every
   // cluster matrix, n x n doubles with S[j n + i] = (C^-1)(i, j), instead of the packed factor
   bool inverse = false;
+  // deterministic blend (rbfmap_config.deterministic): the map kernels store the weighted result of CSR entry e (out-vertex
+  // entries for consistent, in-vertex entries for conservative constraints) at blendStage[e * dims + d] instead of adding
+  // it to the output with atomics; pumBlendGather then sums every vertex's entries in ascending cluster order
+  double *blendStage = nullptr;
 };
 // doubles per cluster in `mat` (even count: 16-byte aligned for the TMA bulk copy)
 __host__ __device__ inline long long pumMatSize(long long n, bool inverse) { return ((inverse ? n * n : n * (n + 1) / 2) + 1) & ~1LL; }
@@ -182,6 +186,18 @@ void pumBuildInRecords(const PumSolveArgs &a, int64_t sumIn, double *rec, cudaSt
 void pumFactor(const PumSolveArgs &a, const PumBuckets &b, int *fail, cudaStream_t s);
 void pumInverse(const PumSolveArgs &a, const PumBuckets &b, int *fail, cudaStream_t s); // explicit inverses (pum_inverse.cu)
 void pumFactorWarp(const PumSolveArgs &a, int bucket, const PumEntry *list, int64_t count, int *fail, cudaStream_t s);
+// Deterministic blend: for every vertex the CSR entries that refer to it, ascending (= ascending
+// cluster index = the order in which the reference's loop over the clusters adds to the output vector).
+struct PumVertexIndex {
+  DevBuf<int64_t> off;     // nVertices + 1
+  DevBuf<int64_t> entries; // sum of cluster sizes
+  int64_t         nVertices = 0;
+};
+void pumBuildVertexIndex(const int *ids, int64_t nEntries, int64_t nVertices, PumVertexIndex &ix, cudaStream_t s);
+// weight sums of the out-vertices recomputed from the (sorted) entries, so that they do not depend on the order of atomics
+void pumDeterministicWeightSums(const PumSolveArgs &a, int64_t nClusters, const PumVertexIndex &ix, double *wsum, cudaStream_t s);
+void pumBlendGather(const double *stage, const PumVertexIndex &ix, int dims, double *out, cudaStream_t s);
+
 // execution-mode minimal-compute (pum_eval.cu): sizes / offsets of the stored evaluation matrices, and their assembly
 int64_t pumEvalOffsets(const PumMembership &m, int64_t nClusters, bool lanesAreOut, DevBuf<int64_t> &evalOff, cudaStream_t s);
 void    pumBuildEvalMatrices(const PumSolveArgs &a, int64_t nClusters, bool lanesAreOut, const long long *evalOff, double *eval, cudaStream_t s);

@@ -939,6 +939,130 @@ int64_t pumFirstUnassigned(const int *wcount, int64_t nOut, cudaStream_t s, cons
 } // namespace rbfmap
 
 namespace rbfmap {
+// ---- deterministic blend: vertex -> CSR entries ----
+namespace {
+__global__ void vertexCountKernel(const int *__restrict__ ids, long long n, int *__restrict__ count)
+{
+  const long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (e < n)
+    atomicAdd(&count[ids[e]], 1);
+}
+__global__ void vertexFillKernel(const int *__restrict__ ids, long long n, const long long *__restrict__ off, int *__restrict__ cursor,
+                                 long long *__restrict__ entries)
+{
+  const long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (e < n) {
+    const int v                              = ids[e];
+    entries[off[v] + atomicAdd(&cursor[v], 1)] = e;
+  }
+}
+__global__ void vertexSortKernel(long long nVertices, const long long *__restrict__ off, long long *__restrict__ entries)
+{
+  const long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (v >= nVertices)
+    return;
+  const long long beg = off[v], end = off[v + 1];
+  for (long long a = beg + 1; a < end; ++a) { // a handful of entries per vertex
+    const long long x = entries[a];
+    long long       b = a - 1;
+    while (b >= beg && entries[b] > x) {
+      entries[b + 1] = entries[b];
+      --b;
+    }
+    entries[b + 1] = x;
+  }
+}
+// entry e -> its cluster: the largest c with outOff[c] <= e
+__device__ __forceinline__ long long clusterOfEntry(const long long *__restrict__ offs, long long nClusters, long long e)
+{
+  long long lo = 0, hi = nClusters - 1;
+  while (lo < hi) {
+    const long long mid = (lo + hi + 1) >> 1;
+    if (offs[mid] <= e)
+      lo = mid;
+    else
+      hi = mid - 1;
+  }
+  return lo;
+}
+__global__ void detWeightSumKernel(PumSolveArgs a, long long nClusters, long long nVertices, const long long *__restrict__ off,
+                                   const long long *__restrict__ entries, double *__restrict__ wsum)
+{
+  const long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (v >= nVertices)
+    return;
+  const double rinv = 1.0 / a.radius;
+  double       s    = 0.0;
+  for (long long k = off[v]; k < off[v + 1]; ++k) {
+    const long long e = entries[k];
+    const long long c = clusterOfEntry(a.outOff, nClusters, e);
+    const double4   r = a.outRec[e];
+    // computeWeight (SphericalVertexCluster.hpp:337-344): squared difference (centre, vertex)
+    s += pumWeight(__dsqrt_rn(sqDist3(a.centers[3 * c], a.centers[3 * c + 1], a.centers[3 * c + 2], r.x, r.y, r.z)), rinv);
+  }
+  if (off[v + 1] > off[v])
+    wsum[v] = s;
+}
+__global__ void blendGatherKernel(const double *__restrict__ stage, long long nVertices, const long long *__restrict__ off,
+                                  const long long *__restrict__ entries, int dims, double *__restrict__ out)
+{
+  const long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (v >= nVertices)
+    return;
+  for (int d = 0; d < dims; ++d) {
+    double s = 0.0; // PartitionOfUnityMapping.hpp:352, 371: the output starts from zero, the clusters add in index order
+    for (long long k = off[v]; k < off[v + 1]; ++k)
+      s += stage[entries[k] * dims + d];
+    out[v * dims + d] = s;
+  }
+}
+} // namespace
+
+void pumBuildVertexIndex(const int *ids, int64_t nEntries, int64_t nVertices, PumVertexIndex &ix, cudaStream_t s)
+{
+  ix.nVertices = nVertices;
+  ix.off.alloc(nVertices + 1);
+  ix.entries.alloc(std::max<int64_t>(nEntries, 1));
+  DevBuf<int> count;
+  count.alloc(std::max<int64_t>(nVertices, 1));
+  RBF_CUDA(cudaMemsetAsync(count.p, 0, std::max<int64_t>(nVertices, 1) * sizeof(int), s));
+  if (nEntries > 0) {
+    vertexCountKernel<<<divUp(nEntries, 256), 256, 0, s>>>(ids, nEntries, count.p);
+    RBF_LAUNCHED();
+  }
+  exclusiveScan(count.p, ix.off.p, nVertices, s);
+  if (nEntries > 0) {
+    RBF_CUDA(cudaMemsetAsync(count.p, 0, std::max<int64_t>(nVertices, 1) * sizeof(int), s));
+    vertexFillKernel<<<divUp(nEntries, 256), 256, 0, s>>>(ids, nEntries, reinterpret_cast<const long long *>(ix.off.p), count.p,
+                                                         reinterpret_cast<long long *>(ix.entries.p));
+    RBF_LAUNCHED();
+    vertexSortKernel<<<divUp(nVertices, 256), 256, 0, s>>>(nVertices, reinterpret_cast<const long long *>(ix.off.p), reinterpret_cast<long long *>(ix.entries.p));
+    RBF_LAUNCHED();
+  }
+  RBF_CUDA(cudaGetLastError());
+  RBF_CUDA(cudaStreamSynchronize(s)); // `count` is released on return
+}
+
+void pumDeterministicWeightSums(const PumSolveArgs &a, int64_t nClusters, const PumVertexIndex &ix, double *wsum, cudaStream_t s)
+{
+  if (ix.nVertices <= 0 || nClusters <= 0)
+    return;
+  detWeightSumKernel<<<divUp(ix.nVertices, 256), 256, 0, s>>>(a, nClusters, ix.nVertices, reinterpret_cast<const long long *>(ix.off.p),
+                                                             reinterpret_cast<const long long *>(ix.entries.p), wsum);
+  RBF_LAUNCHED();
+  RBF_CUDA(cudaGetLastError());
+}
+
+void pumBlendGather(const double *stage, const PumVertexIndex &ix, int dims, double *out, cudaStream_t s)
+{
+  if (ix.nVertices <= 0)
+    return;
+  blendGatherKernel<<<divUp(ix.nVertices, 256), 256, 0, s>>>(stage, ix.nVertices, reinterpret_cast<const long long *>(ix.off.p),
+                                                            reinterpret_cast<const long long *>(ix.entries.p), dims, out);
+  RBF_LAUNCHED();
+  RBF_CUDA(cudaGetLastError());
+}
+
 std::vector<long long> pumCentreHistogram(const double *dCenters, int64_t n, int axis, double lo, double binWidth, int nBins, cudaStream_t s)
 {
   DevBuf<int> hist;

@@ -248,9 +248,15 @@ __global__ void __launch_bounds__(NT) pumMapConservativeKernel(PumSolveArgs args
       }
     }
     // SphericalVertexCluster.hpp:233-239
+    if (args.blendStage && !fromCache) { // deterministic blend (pumBlendGather)
 #pragma unroll
-    for (int cc = 0; cc < NC; ++cc)
-      atomicAdd(&out[gid * dims + c0 + cc], res[cc]);
+      for (int cc = 0; cc < NC; ++cc)
+        args.blendStage[(inOffC + i) * dims + c0 + cc] = res[cc];
+    } else {
+#pragma unroll
+      for (int cc = 0; cc < NC; ++cc)
+        atomicAdd(&out[gid * dims + c0 + cc], res[cc]);
+    }
   }
 }
 

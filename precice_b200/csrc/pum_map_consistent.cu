@@ -289,9 +289,15 @@ __global__ void __launch_bounds__(NT, NT == 32 ? 14 : 1) pumMapConsistentKernel(
             acc[cc] += q[k] * beta[k][cc];
       }
       const double w = wNorm;
+      if (args.blendStage) { // deterministic blend: summed per vertex in cluster order afterwards (pumBlendGather)
 #pragma unroll
-      for (int cc = 0; cc < NC; ++cc)
-        atomicAdd(&out[gid * dims + c0 + cc], acc[cc] * w);
+        for (int cc = 0; cc < NC; ++cc)
+          args.blendStage[(en.outOff + o0 + ol) * dims + c0 + cc] = acc[cc] * w;
+      } else {
+#pragma unroll
+        for (int cc = 0; cc < NC; ++cc)
+          atomicAdd(&out[gid * dims + c0 + cc], acc[cc] * w);
+      }
     }
   }
   RBF_STAMP(3);

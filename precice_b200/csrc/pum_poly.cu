@@ -411,6 +411,48 @@ __global__ void distSqrtKernel(const double *__restrict__ x, long long n, double
 }
 } // namespace
 
+// Test hook: the pair evaluation the per-cluster algebra kernels use (pairBasis / pairBasisBatch of pum_device.cuh: fused
+// multiply-adds, reciprocal-root seed, integer clamp at the support), NOT the operation-by-operation evalBasis.
+template <int KIND, bool DIM3>
+__global__ void pairBasisDebugKernel(RbfParams f, const double *__restrict__ a, const double *__restrict__ b, long long n, int batched, double *__restrict__ out)
+{
+  const double    invR2 = f.p1 * f.p1;
+  const long long t     = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (!batched) {
+    if (t < n)
+      out[t] = pairBasis<KIND, DIM3>(a[3 * t], a[3 * t + 1], a[3 * t + 2], b[3 * t], b[3 * t + 1], b[3 * t + 2], f, invR2);
+    return;
+  }
+  // four consecutive pairs per thread through the staged batch form (what the evaluation loops of the map kernels call)
+  const long long i0 = 4 * t;
+  if (i0 >= n)
+    return;
+  double ax[4], ay[4], az[4], bx[4], by[4], bz[4], phi[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const long long i = min(i0 + u, n - 1);
+    ax[u] = a[3 * i], ay[u] = a[3 * i + 1], az[u] = a[3 * i + 2];
+    bx[u] = b[3 * i], by[u] = b[3 * i + 1], bz[u] = b[3 * i + 2];
+  }
+  pairBasisBatch<KIND, DIM3, 4>(ax, ay, az, bx, by, bz, f, invR2, phi);
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    if (i0 + u < n)
+      out[i0 + u] = phi[u];
+}
+
+void debugPairBasis(const RbfParams &f, bool dim3, const double *dA, const double *dB, long long n, int batched, double *dOut)
+{
+  const int grid = divUp(batched ? (n + 3) / 4 : n, 256);
+  RBF_DISPATCH_HOT_BASIS(f.kind, {
+    if (dim3)
+      pairBasisDebugKernel<KIND, true><<<grid, 256>>>(f, dA, dB, n, batched, dOut);
+    else
+      pairBasisDebugKernel<KIND, false><<<grid, 256>>>(f, dA, dB, n, batched, dOut);
+  });
+  RBF_CUDA(cudaGetLastError());
+}
+
 void debugDistSqrt(const double *dX, long long n, double *dOut)
 {
   distSqrtKernel<<<divUp(n, 256), 256>>>(dX, n, dOut);

@@ -239,3 +239,53 @@ def test_pum_not_positive_definite_limits(pb):
     with pytest.raises(pb.MappingError) as e:
         pb.PartitionOfUnityMapping("consistent", 3, "multiquadrics", 0.1).computeMappingJustInTime(inp)
     assert e.value.status == "UNSUPPORTED"
+
+
+# ---------------------------------------------------------------------------------------------- deterministic blend
+@pytest.mark.parametrize("constraint", ["consistent", "conservative"])
+@pytest.mark.parametrize("execution_mode", ["minimal-memory", "minimal-compute"])
+def test_deterministic_blend_is_bit_reproducible(pb, constraint, execution_mode):
+    """rbfmap_config.deterministic: weight sums and blend are gathered per vertex in ascending cluster order (the order of
+    the reference's loop over the clusters, SphericalVertexCluster.hpp:237, 332) instead of atomics: two independent
+    mappings give bit-identical results, which the atomic version does not guarantee."""
+    import oracle
+    inp, out, vals = _case(3, 9000, 8000, 3)
+    args = (constraint, 3, "compact-polynomial-c6", 2.0 * (3.0 * 40 / (4.0 * np.pi * 9000)) ** (1.0 / 3.0), "separate", 40, 0.15, True)
+    runs = []
+    for _ in range(3):
+        m = pb.PartitionOfUnityMapping(*args, deterministic=True, execution_mode=execution_mode)
+        m.computeMapping(inp, out)
+        runs.append((m.map(vals, 3), m.map(vals[::3].copy(), 1)))
+        del m
+    for a, b in runs[1:]:
+        assert np.array_equal(a, runs[0][0]) and np.array_equal(b, runs[0][1])
+    plain = pb.PartitionOfUnityMapping(*args)
+    plain.computeMapping(inp, out)
+    assert refcases.rel_l2(runs[0][0], plain.map(vals, 3)) <= 1e-12
+    orc = oracle.PumMapping(*args)
+    orc.compute_mapping(inp, out)
+    assert refcases.rel_l2(runs[0][0], orc.map(vals, 3)) <= REL_L2_TOL
+
+
+def test_deterministic_blend_sharded(pb):
+    inp, out, vals = _case(3, 6000, 6000, 1)
+    args = ("consistent", 3, "compact-polynomial-c6", 2.0 * (3.0 * 30 / (4.0 * np.pi * 6000)) ** (1.0 / 3.0), "separate", 30, 0.15, True)
+    single = pb.PartitionOfUnityMapping(*args, deterministic=True)
+    single.computeMapping(inp, out)
+    ref = single.map(vals, 1)
+    total = np.zeros_like(ref)
+    for r in range(3):
+        m = pb.PartitionOfUnityMapping(*args, deterministic=True)
+        m.distributedInit(None, r, 3)
+        m.computeMapping(inp, out)
+        total += m.map(vals, 1)
+    # every vertex is owned by one rank, which sums the same clusters in the same order; inside a boundary cluster the
+    # evaluation loop splits its lanes by the number of (owned) output vertices, so the last bits may differ
+    assert refcases.rel_l2(total, ref) <= 1e-15
+    again = np.zeros_like(ref)
+    for r in range(3):
+        m = pb.PartitionOfUnityMapping(*args, deterministic=True)
+        m.distributedInit(None, r, 3)
+        m.computeMapping(inp, out)
+        again += m.map(vals, 1)
+    assert np.array_equal(again, total)  # ... but the sharded mapping itself is bit-reproducible

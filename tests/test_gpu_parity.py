@@ -789,3 +789,49 @@ def test_against_committed_fixtures(pb, idx):
     res = m.map(vals, dims)
     tol = 1e-10 if constraint == "consistent" else 1e-9
     assert refcases.rel_l2(res, data[name + "/result"]) <= tol, refcases.rel_l2(res, data[name + "/result"])
+
+
+# ---------------------------------------------------------------------------------------------- a1 as the hot kernels evaluate it
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("basis,phi0", [("compact-polynomial-c0", 1.0), ("compact-polynomial-c2", 1.0), ("compact-polynomial-c4", 3.0),
+                                        ("compact-polynomial-c6", 1.0), ("compact-polynomial-c8", 15.0)])
+def test_pair_basis_of_the_algebra_kernels(pb, orc, basis, phi0, dim):
+    """The factor / map / just-in-time kernels do not call the bit-exact functors of test_basis_bit_exact but pairBasis /
+    pairBasisBatch (pum_device.cuh): fused multiply-adds, rsqrt seed + second-order correction, integer clamp at the
+    support. Bounded here against the oracle functor (impl/BasisFunctions.hpp) over r in [0, 1.5 R], at r = 0 and at
+    r = R -/+ 1 ulp: within 16 ulp of phi(0), at most ~1e-30 (instead of exactly 0) beyond the support, and the
+    four-wide staged form equals the single form bit for bit."""
+    import ctypes as C
+    from precice_b200 import _lib
+    R = 0.0371
+    rng = np.random.default_rng(17)
+    n = 40000
+    a = rng.random((n, 3))
+    direction = rng.normal(size=(n, 3))
+    if dim == 2:
+        a[:, 2] = 0.0
+        direction[:, 2] = 0.0
+    direction /= np.linalg.norm(direction, axis=1)[:, None]
+    r = rng.random(n) * 1.5 * R
+    r[:8] = [0.0, R, np.nextafter(R, 0), np.nextafter(R, 1), 1e-200, R * (1 - 1e-9), R * (1 + 1e-9), 0.5 * R]
+    b = a + direction * r[:, None]
+    dist = np.sqrt(((a - b) ** 2).sum(1))  # what the kernels see (the rounding of a + d r is part of the input)
+    exact = orc.basis_eval(basis, R, dist)
+    L = _lib.lib()
+    dp = C.POINTER(C.c_double)
+    got = {}
+    for batched in (0, 1):
+        out = np.empty(n)
+        rc = L.rbfmap_debug_pair_basis(_lib.BASIS[basis], R, 0.0, dim, np.ascontiguousarray(a).ctypes.data_as(dp),
+                                       np.ascontiguousarray(b).ctypes.data_as(dp), n, batched, out.ctypes.data_as(dp))
+        assert rc == 0
+        got[batched] = out
+    assert np.array_equal(got[0], got[1])
+    err = np.abs(got[0] - exact)
+    inside = dist < R * (1 - 1e-12)
+    assert err[inside].max() <= 16 * np.finfo(float).eps * phi0, err[inside].max() / (np.finfo(float).eps * phi0)
+    outside = dist >= R
+    assert np.all(exact[outside] == 0.0) and np.abs(got[0][outside]).max() <= 1e-28 * phi0
+    near = ~inside & ~outside  # within 1e-12 R of the support: both are ~ (1e-12)^2 phi0 or smaller
+    assert np.all(np.abs(got[0][near]) <= 1e-20 * phi0)
+    assert abs(got[0][0] - phi0) <= 4 * np.finfo(float).eps * phi0  # r = 0: the matrix diagonal
