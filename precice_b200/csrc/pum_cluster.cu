@@ -10,10 +10,28 @@
 #include "pum_device.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <functional>
+#include <limits>
 
 namespace rbfmap {
 namespace {
+
+// The sphere queries of the reference are strict comparisons of the ROUNDED distance: sqrt(d2) < r (query/Index.cpp:235).
+// IEEE square root is monotone, so {d2 : sqrt(d2) < r} = {d2 <= t} with t the largest double whose root is below r; the
+// kernels compare squared distances with t instead of taking a correctly rounded square root per candidate (a dozen
+// FP64 instructions in kernels that are issue-bound).
+inline double strictRadiusBound(double r)
+{
+  if (!(r > 0.0))
+    return -1.0; // no squared distance qualifies
+  double t = r * r;
+  while (std::sqrt(t) >= r)
+    t = std::nextafter(t, 0.0);
+  while (std::sqrt(std::nextafter(t, std::numeric_limits<double>::infinity())) < r)
+    t = std::nextafter(t, std::numeric_limits<double>::infinity());
+  return t;
+}
 
 constexpr int kWarpsPerBlock = 8;
 constexpr int kBlockThreads  = kWarpsPerBlock * 32;
@@ -50,24 +68,51 @@ __device__ __forceinline__ void forLiveCentres(const int *__restrict__ tag, int6
 }
 
 // ---- tagEmptyClusters on arbitrary (projected) centres: one warp per live centre -------------
-__global__ void __launch_bounds__(kBlockThreads) tagEmptyKernel(const double *__restrict__ centers, int *__restrict__ tag, int64_t total, BinGridView g, double radius)
+// is any binned vertex strictly inside the sphere (squared-distance bound r2Bound, see strictRadiusBound)? The 3x3x3 cells
+// around the centre are searched first: they hold the vertices closest to the centre, and in a populated region the
+// first batch of 32 candidates already contains a hit; only otherwise the full 5x5x5 neighbourhood is walked.
+__device__ __forceinline__ bool anyVertexInside(const BinGridView &g, double cx, double cy, double cz, double r2Bound, int lane)
+{
+  bool found = false;
+  auto test  = [&](int pos, bool valid) {
+    bool hit = false;
+    if (valid)
+      hit = sqDist3(cx, cy, cz, g.xyz[3 * pos], g.xyz[3 * pos + 1], g.xyz[3 * pos + 2]) <= r2Bound;
+    if (__any_sync(0xffffffffu, hit)) {
+      found = true;
+      return true;
+    }
+    return false;
+  };
+  forCandidatesWarp<1>(g, cx, cy, cz, lane, test);
+  if (!found)
+    forCandidatesWarp<2>(g, cx, cy, cz, lane, test);
+  return found;
+}
+
+__global__ void __launch_bounds__(kBlockThreads) tagEmptyKernel(const double *__restrict__ centers, int *__restrict__ tag, int64_t total, BinGridView g, double r2Bound)
 {
   forLiveCentres(tag, total, [&](int64_t c, int lane) {
     const double cx = centers[3 * c], cy = centers[3 * c + 1], cz = centers[3 * c + 2];
-    bool         found = false;
-    forCandidatesWarp<2>(g, cx, cy, cz, lane, [&](int pos, bool valid) {
-      bool hit = false;
-      if (valid)
-        hit = __dsqrt_rn(sqDist3(cx, cy, cz, g.xyz[3 * pos], g.xyz[3 * pos + 1], g.xyz[3 * pos + 2])) < radius;
-      if (__any_sync(0xffffffffu, hit)) {
-        found = true;
-        return true;
-      }
-      return false;
-    });
-    if (!found && lane == 0)
+    if (!anyVertexInside(g, cx, cy, cz, r2Bound, lane) && lane == 0)
       tag[c] = 1;
   });
+}
+
+// ---- tagEmptyClusters on the regular lattice, from the centre side (dense lattices) ----
+// One warp per lattice centre and mesh; the same distance expression on the same operands as markLatticeKernel.
+__global__ void __launch_bounds__(kBlockThreads) latticeEmptyKernel(LatticeAxes L, int64_t total, BinGridView g, double r2Bound, int *__restrict__ tag, int bit)
+{
+  const int64_t id   = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int     lane = threadIdx.x & 31;
+  if (id >= total)
+    return;
+  const int    z = static_cast<int>(id % L.n[2]);
+  const int    y = static_cast<int>((id / L.n[2]) % L.n[1]);
+  const int    x = static_cast<int>(id / (static_cast<int64_t>(L.n[2]) * L.n[1]));
+  const double cx = L.a[0][x], cy = L.a[1][y], cz = L.a[2][z];
+  if (anyVertexInside(g, cx, cy, cz, r2Bound, lane) && lane == 0)
+    atomicAnd(&tag[id], ~bit);
 }
 
 // ---- tagEmptyClusters on the regular lattice, from the vertex side ---------------------------
@@ -94,7 +139,7 @@ __device__ __forceinline__ void latticeAxisRange(const double *__restrict__ ax, 
     --hi;
 }
 
-__global__ void __launch_bounds__(256) markLatticeKernel(const double *__restrict__ xyz, int64_t n, LatticeAxes L, double radius, int *tag, int bit)
+__global__ void __launch_bounds__(256) markLatticeKernel(const double *__restrict__ xyz, int64_t n, LatticeAxes L, double radius, double r2Bound, int *tag, int bit)
 {
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i >= n)
@@ -111,7 +156,7 @@ __global__ void __launch_bounds__(256) markLatticeKernel(const double *__restric
       for (int z = z0; z <= z1; ++z) {
         const int64_t id = (static_cast<int64_t>(x) * L.n[1] + y) * L.n[2] + z; // impl/CreateClustering.hpp:36-45
         // most centres have long been cleared by another vertex (a stale read only costs a redundant test)
-        if ((tag[id] & bit) && __dsqrt_rn(sqDist3(cx, cy, L.a[2][z], vx, vy, vz)) < radius)
+        if ((tag[id] & bit) && sqDist3(cx, cy, L.a[2][z], vx, vy, vz) <= r2Bound)
           atomicAnd(&tag[id], ~bit);
       }
     }
@@ -125,7 +170,7 @@ __global__ void __launch_bounds__(kBlockThreads) projectKernel(double *__restric
     const double cx = centers[3 * c], cy = centers[3 * c + 1], cz = centers[3 * c + 2];
     double       best = 1.7976931348623157e308;
     int          bestId = 0x7fffffff, bestPos = -1;
-    forCandidatesWarp<2>(g, cx, cy, cz, lane, [&](int pos, bool valid) {
+    auto visit = [&](int pos, bool valid) {
       if (valid) {
         const double d2 = sqDist3(cx, cy, cz, g.xyz[3 * pos], g.xyz[3 * pos + 1], g.xyz[3 * pos + 2]);
         const int    id = g.ids[pos];
@@ -136,17 +181,32 @@ __global__ void __launch_bounds__(kBlockThreads) projectKernel(double *__restric
         }
       }
       return false;
-    });
+    };
+    auto reduce = [&] {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const int    oi = __shfl_xor_sync(0xffffffffu, bestId, o);
-      const int    op = __shfl_xor_sync(0xffffffffu, bestPos, o);
-      if (ob < best || (ob == best && oi < bestId)) {
-        best    = ob;
-        bestId  = oi;
-        bestPos = op;
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int    oi = __shfl_xor_sync(0xffffffffu, bestId, o);
+        const int    op = __shfl_xor_sync(0xffffffffu, bestPos, o);
+        if (ob < best || (ob == best && oi < bestId)) {
+          best    = ob;
+          bestId  = oi;
+          bestPos = op;
+        }
       }
+    };
+    // The 3x3x3 cells around the centre first: every vertex outside of them is at least one cell edge away, so a vertex
+    // found closer than that (with a margin for the rounding of the squared distances) is the nearest one of the mesh,
+    // ties included (they lie inside the block as well). Otherwise the full 5x5x5 neighbourhood is searched.
+    forCandidatesWarp<1>(g, cx, cy, cz, lane, visit);
+    reduce();
+    const double edge = 1.0 / fmax(g.ihx, fmax(g.ihy, g.ihz));
+    if (!(best < edge * edge * (1.0 - 1e-9))) { // warp-uniform after the reduction
+      best    = 1.7976931348623157e308;
+      bestId  = 0x7fffffff;
+      bestPos = -1;
+      forCandidatesWarp<2>(g, cx, cy, cz, lane, visit);
+      reduce();
     }
     if (lane < 3 && bestPos >= 0)
       centers[3 * c + lane] = g.xyz[3 * bestPos + lane];
@@ -318,13 +378,13 @@ __device__ __forceinline__ bool inSlab(const BinGridView &g, int pos, const PumS
   return t >= slab.lo && t < slab.hi;
 }
 
-__device__ void gatherMembers(const BinGridView &g, double cx, double cy, double cz, double r, int *seg, int lane, const PumSlab *slab = nullptr)
+__device__ void gatherMembers(const BinGridView &g, double cx, double cy, double cz, double r2Bound, int *seg, int lane, const PumSlab *slab = nullptr)
 {
   int base = 0;
   forCandidatesWarp<2>(g, cx, cy, cz, lane, [&](int pos, bool valid) {
     if (slab && valid)
       valid = inSlab(g, pos, *slab);
-    const bool     hit = valid && __dsqrt_rn(sqDist3(cx, cy, cz, g.xyz[3 * pos], g.xyz[3 * pos + 1], g.xyz[3 * pos + 2])) < r;
+    const bool     hit = valid && sqDist3(cx, cy, cz, g.xyz[3 * pos], g.xyz[3 * pos + 1], g.xyz[3 * pos + 2]) <= r2Bound;
     const unsigned m   = __ballot_sync(0xffffffffu, hit);
     if (hit)
       seg[base + __popc(m & ((1u << lane) - 1u))] = g.ids[pos];
@@ -344,29 +404,29 @@ constexpr int kSlotCap = 128;
 // PartitionOfUnityMapping.hpp:306-333 seen from the cluster side: w_c = C2(|x - c| / r) is added to the weight sum of
 // the vertex and its cluster count is incremented (the reference loops over the clusters of a vertex instead).
 template <bool WEIGHTS, bool SLAB = false>
-__device__ __forceinline__ int gatherToShared(const BinGridView &g, double cx, double cy, double cz, double r, int *stage, int *stagePos, int lane, double rW = 0.0,
-                                              double rinv = 0.0, double *__restrict__ wsum = nullptr, int *__restrict__ wcount = nullptr,
+__device__ __forceinline__ int gatherToShared(const BinGridView &g, double cx, double cy, double cz, double r2Bound, int *stage, int *stagePos, int lane,
+                                              double rW2Bound = 0.0, double rinv = 0.0, double *__restrict__ wsum = nullptr, int *__restrict__ wcount = nullptr,
                                               const PumSlab *slab = nullptr)
 {
   int base = 0;
   forCandidatesWarp<2>(g, cx, cy, cz, lane, [&](int pos, bool valid) {
-    double d = 1.7976931348623157e308;
+    double d2 = 1.7976931348623157e308;
     if (SLAB && valid) // sharded mapping: only the output vertices this rank owns are listed and weighted
       valid = inSlab(g, pos, *slab);
     if (valid) // computeWeight (SphericalVertexCluster.hpp:337-344): squared difference (centre, vertex)
-      d = __dsqrt_rn(sqDist3(cx, cy, cz, g.xyz[3 * pos], g.xyz[3 * pos + 1], g.xyz[3 * pos + 2]));
-    const bool     hit = d < r;
+      d2 = sqDist3(cx, cy, cz, g.xyz[3 * pos], g.xyz[3 * pos + 1], g.xyz[3 * pos + 2]);
+    const bool     hit = d2 <= r2Bound; // sqrt(d2) < r, see strictRadiusBound
     const unsigned m   = __ballot_sync(0xffffffffu, hit);
     const int      at  = base + __popc(m & ((1u << lane) - 1u));
     int            id  = 0;
-    if (hit || (WEIGHTS && d < rW))
+    if (hit || (WEIGHTS && d2 <= rW2Bound))
       id = g.ids[pos];
     if (hit && at < kSlotCap) {
       stage[at]    = id;
       stagePos[at] = pos; // position in the binned arrays: neighbouring hits share cache lines there
     }
-    if (WEIGHTS && d < rW) {
-      atomicAdd(wsum + id, pumWeight(d, rinv));
+    if (WEIGHTS && d2 <= rW2Bound) {
+      atomicAdd(wsum + id, pumWeight(__dsqrt_rn(d2), rinv));
       atomicAdd(wcount + id, 1);
     }
     base += __popc(m);
@@ -424,7 +484,8 @@ __device__ __forceinline__ void rankSortToGlobal(const int *stage, const int *pa
 }
 
 template <bool SLAB>
-__global__ void memberGatherKernel(const double *__restrict__ centers, int64_t nClusters, BinGridView gin, BinGridView gout, double rIn, double rOut,
+__global__ void memberGatherKernel(const double *__restrict__ centers, int64_t nClusters, BinGridView gin, BinGridView gout, double rIn, double rInBound,
+                                   double rOutBound,
                                    int *__restrict__ nIn, int *__restrict__ nOut, long long *__restrict__ tri, int *__restrict__ slotIn,
                                    int *__restrict__ slotOut, int *__restrict__ overflow, double *__restrict__ wsum, int *__restrict__ wcount, PumSlab slab,
                                    bool fullMatrices)
@@ -436,11 +497,11 @@ __global__ void memberGatherKernel(const double *__restrict__ centers, int64_t n
   if (c >= nClusters)
     return;
   const double cx = centers[3 * c], cy = centers[3 * c + 1], cz = centers[3 * c + 2];
-  const int    ci = gatherToShared<false>(gin, cx, cy, cz, rIn, stage[w], stagePos[w], lane);
+  const int    ci = gatherToShared<false>(gin, cx, cy, cz, rInBound, stage[w], stagePos[w], lane);
   if (ci <= kSlotCap)
     rankSortToGlobal(stage[w], stagePos[w], ci, slotIn + c * kSlotCap, lane);
   __syncwarp();
-  const int co = gatherToShared<true, SLAB>(gout, cx, cy, cz, rOut, stage[w], stagePos[w], lane, rIn, 1.0 / rIn, wsum, wcount, &slab);
+  const int co = gatherToShared<true, SLAB>(gout, cx, cy, cz, rOutBound, stage[w], stagePos[w], lane, rInBound, 1.0 / rIn, wsum, wcount, &slab);
   if (co <= kSlotCap)
     rankSortToGlobal(stage[w], stagePos[w], co, slotOut + c * kSlotCap, lane);
   if (lane == 0) {
@@ -489,7 +550,7 @@ __global__ void memberPackKernel(int64_t nClusters, const int *__restrict__ nIn,
   }
 }
 
-__global__ void memberFillKernel(const double *__restrict__ centers, int64_t nClusters, BinGridView gin, BinGridView gout, double rIn, double rOut,
+__global__ void memberFillKernel(const double *__restrict__ centers, int64_t nClusters, BinGridView gin, BinGridView gout, double rInBound, double rOutBound,
                                  const long long *__restrict__ inOff, const long long *__restrict__ outOff, int *__restrict__ inIds, int *__restrict__ outIds,
                                  PumSlab slab, bool useSlab)
 {
@@ -501,9 +562,9 @@ __global__ void memberFillKernel(const double *__restrict__ centers, int64_t nCl
   const double cx = centers[3 * c], cy = centers[3 * c + 1], cz = centers[3 * c + 2];
   int         *segIn = inIds + inOff[c], *segOut = outIds + outOff[c];
   const int    ni = static_cast<int>(inOff[c + 1] - inOff[c]), no = static_cast<int>(outOff[c + 1] - outOff[c]);
-  gatherMembers(gin, cx, cy, cz, rIn, segIn, lane);
+  gatherMembers(gin, cx, cy, cz, rInBound, segIn, lane);
   warpSortSegment(segIn, ni, stage[w], kSortCap, lane);
-  gatherMembers(gout, cx, cy, cz, rOut, segOut, lane, useSlab ? &slab : nullptr);
+  gatherMembers(gout, cx, cy, cz, rOutBound, segOut, lane, useSlab ? &slab : nullptr);
   warpSortSegment(segOut, no, stage[w], kSortCap, lane);
 }
 
@@ -635,7 +696,13 @@ void PumClustering::tagEmptyLattice(const BinGrid &mesh, int bit, cudaStream_t s
 {
   if (mesh.n == 0)
     return; // every centre keeps its bit = tagged
-  markLatticeKernel<<<divUp(mesh.n, 256), 256, 0, s>>>(mesh.xyz.p, mesh.n, axes, radius, tag.p, bit);
+  // dense lattice (volume meshes: a centre per ~vertices-per-cluster / 5 vertices): one warp per centre, which finds a
+  // vertex in its first batch of candidates; sparse lattice (surface meshes in 3-D: 97 % of the lattice is empty): from
+  // the vertex side, work proportional to the mesh. Both decide every centre with the same distance test.
+  if (total * 8 <= mesh.n)
+    latticeEmptyKernel<<<warpGrid(total), kBlockThreads, 0, s>>>(axes, total, mesh.view(), strictRadiusBound(radius), tag.p, bit);
+  else
+    markLatticeKernel<<<divUp(mesh.n, 256), 256, 0, s>>>(mesh.xyz.p, mesh.n, axes, radius, strictRadiusBound(radius), tag.p, bit);
   RBF_LAUNCHED();
 }
 
@@ -666,7 +733,7 @@ void PumClustering::tagEmpty(const BinGrid &mesh, cudaStream_t s)
 {
   if (nLive == 0)
     return;
-  tagEmptyKernel<<<divUp(nLive, kBlockThreads), kBlockThreads, 0, s>>>(centers.p, liveTag.p, nLive, mesh.view(), radius);
+  tagEmptyKernel<<<divUp(nLive, kBlockThreads), kBlockThreads, 0, s>>>(centers.p, liveTag.p, nLive, mesh.view(), strictRadiusBound(radius));
   RBF_LAUNCHED();
 }
 
@@ -735,6 +802,7 @@ void pumBuildMembership(const double *dCenters, int64_t nClusters, const BinGrid
 {
   const PumSlab slab = outSlab ? *outSlab : PumSlab{};
   const double rOut = radius - kZeroDiff; // SphericalVertexCluster.hpp:155
+  const double rInBound = strictRadiusBound(radius), rOutBound = strictRadiusBound(rOut);
   DevBuf<int>  nIn, nOut;
   nIn.alloc(nClusters);
   nOut.alloc(nClusters);
@@ -755,10 +823,10 @@ void pumBuildMembership(const double *dCenters, int64_t nClusters, const BinGrid
   overflow.alloc(1);
   RBF_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), s));
   if (outSlab)
-    memberGatherKernel<true><<<warpGrid(nClusters), kBlockThreads, 0, s>>>(dCenters, nClusters, inMesh.view(), outMesh.view(), radius, rOut, m.nIn.p, m.nOut.p,
+    memberGatherKernel<true><<<warpGrid(nClusters), kBlockThreads, 0, s>>>(dCenters, nClusters, inMesh.view(), outMesh.view(), radius, rInBound, rOutBound, m.nIn.p, m.nOut.p,
                                                                           reinterpret_cast<long long *>(m.tri.p), slotIn.p, slotOut.p, overflow.p, wsum, wcount, slab, fullMatrices);
   else
-    memberGatherKernel<false><<<warpGrid(nClusters), kBlockThreads, 0, s>>>(dCenters, nClusters, inMesh.view(), outMesh.view(), radius, rOut, m.nIn.p, m.nOut.p,
+    memberGatherKernel<false><<<warpGrid(nClusters), kBlockThreads, 0, s>>>(dCenters, nClusters, inMesh.view(), outMesh.view(), radius, rInBound, rOutBound, m.nIn.p, m.nOut.p,
                                                                            reinterpret_cast<long long *>(m.tri.p), slotIn.p, slotOut.p, overflow.p, wsum, wcount, slab, fullMatrices);
   RBF_LAUNCHED();
   if (weightsComplete) // sharded mapping, exchange mode: the weight sums of the other ranks' clusters are added here
@@ -786,7 +854,7 @@ void pumBuildMembership(const double *dCenters, int64_t nClusters, const BinGrid
                                                                   dCenters, radius, inMesh.view(), outMesh.view(), wsum, wcount, inRec.p, outRec.p);
     RBF_LAUNCHED();
   } else { // clusters beyond the slot size: two-pass fill with the (exact) sizes counted above, then the records
-    memberFillKernel<<<warpGrid(nClusters), kBlockThreads, 0, s>>>(dCenters, nClusters, inMesh.view(), outMesh.view(), radius, rOut,
+    memberFillKernel<<<warpGrid(nClusters), kBlockThreads, 0, s>>>(dCenters, nClusters, inMesh.view(), outMesh.view(), rInBound, rOutBound,
                                                                   reinterpret_cast<const long long *>(m.inOff.p), reinterpret_cast<const long long *>(m.outOff.p),
                                                                   m.inIds.p, m.outIds.p, slab, outSlab != nullptr);
     RBF_LAUNCHED();
@@ -805,7 +873,7 @@ void pumBuildMembership(const double *dCenters, int64_t nClusters, const BinGrid
 // ---- membership of arbitrary points (just-in-time read mapping): the points within the cluster radius of every centre,
 // sorted ascending per cluster, plus their partition-of-unity weight sums; PartitionOfUnityMapping.hpp:290-341 seen
 // from the cluster side. Returns false if a cluster holds more than kSlotCap points (the caller falls back). ----
-__global__ void memberGatherPointsKernel(const double *__restrict__ centers, int64_t nClusters, BinGridView gpts, double radius, int *__restrict__ nPts,
+__global__ void memberGatherPointsKernel(const double *__restrict__ centers, int64_t nClusters, BinGridView gpts, double radius, double rBound, int *__restrict__ nPts,
                                          int *__restrict__ slot, int *__restrict__ overflow, double *__restrict__ wsum, int *__restrict__ wcount)
 {
   __shared__ __align__(16) int stage[kWarpsPerBlock][kSlotCap];
@@ -815,7 +883,7 @@ __global__ void memberGatherPointsKernel(const double *__restrict__ centers, int
     return;
   const double cx = centers[3 * c], cy = centers[3 * c + 1], cz = centers[3 * c + 2];
   __shared__ int stagePos[kWarpsPerBlock][kSlotCap];
-  const int      co = gatherToShared<true>(gpts, cx, cy, cz, radius, stage[w], stagePos[w], lane, radius, 1.0 / radius, wsum, wcount);
+  const int      co = gatherToShared<true>(gpts, cx, cy, cz, rBound, stage[w], stagePos[w], lane, rBound, 1.0 / radius, wsum, wcount);
   if (co <= kSlotCap)
     rankSortToGlobal(stage[w], stage[w], co, slot + c * kSlotCap, lane); // payload = the point ID itself
   if (lane == 0) {
@@ -852,7 +920,7 @@ bool pumBuildPointMembership(const double *dCenters, int64_t nClusters, const Bi
   DevBuf<int> overflow;
   overflow.alloc(1);
   RBF_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), s));
-  memberGatherPointsKernel<<<warpGrid(nClusters), kBlockThreads, 0, s>>>(dCenters, nClusters, points.view(), radius, nPts.p, scratch.slotOut.p, overflow.p, wsum,
+  memberGatherPointsKernel<<<warpGrid(nClusters), kBlockThreads, 0, s>>>(dCenters, nClusters, points.view(), radius, strictRadiusBound(radius), nPts.p, scratch.slotOut.p, overflow.p, wsum,
                                                                         wcount);
   RBF_LAUNCHED();
   exclusiveScan(nPts.p, off.p, nClusters, s);
