@@ -212,8 +212,10 @@ int rbfmap_map_device(rbfmap_handle *h, const double *d_in, int dims, double *d_
  * application broadcasts it (MPI / sockets / torch.distributed), then every rank calls rbfmap_distributed_init before
  * computeMapping. With host pointers every rank uploads only its 1/world slice over PCIe and the library all-gathers the
  * slices over NVLink.
- *  - rbf-pum-direct: every rank runs the (cheap, deterministic) clustering of the whole mesh, so the cluster set is the
- *    one of the single-device mapping; the clusters are then sharded by slabs along the longest lattice axis
+ *  - rbf-pum-direct: the lattice of cluster centres is that of the whole mesh (bounding box and cluster radius are
+ *    computed by every rank from the complete input mesh), so the cluster set is the one of the single-device mapping.
+ *    The lattice is cut into slabs along its longest axis, balanced by the vertex density; every rank bins, clusters,
+ *    factorises and maps only its own slab plus a halo of a few cluster radii
  *    (rbfmap_config.shard_mode): DUPLICATE - a rank owns a slab of output vertices and processes every cluster that
  *    reaches into it, map() needs no collective and fills only the owned vertices of `out` (the others are zero; the
  *    complete result is the sum over the ranks; rbfmap_stats.shard_* describe the slab); EXCHANGE (always used for
@@ -286,7 +288,7 @@ typedef struct rbfmap_stats {
   float   ms_assembly_factor; /* device time of the dominant assembly(+factorisation) kernel(s) of the last computeMapping */
   int     kernel_launches;    /* kernels launched by the last compute + map calls */
   /* sharded rbf-pum-direct (rbfmap_distributed_init): n_clusters and the sums above describe what THIS rank processes */
-  int64_t n_clusters_global;  /* clusters of the whole mapping */
+  int64_t n_clusters_global;  /* clusters of the whole mapping (-1: unknown, a sharded mapping joined without communicator) */
   int     shard_axis;         /* axis of the slab decomposition; -1 = not sharded */
   double  shard_lo, shard_hi; /* this rank owns lo <= x[axis] < hi (output vertices in duplicate mode, cluster centres in exchange mode) */
   float   ms_replicated;      /* device time of the phases of computeMapping every rank repeats (bounds, radius, binning, clustering) */

@@ -187,7 +187,9 @@ private:
   double estimateClusterRadius(const double *dXyz, int64_t n, const double bbMin[3], const double bbMax[3]);
   PumSolveArgs solveArgs() const;
   // sharded mapping: replaces the complete centre list by the centres this rank processes
-  void shardClusters(const double bbMin[3], const double bbMax[3], const int latticeCount[3], bool haveLattice);
+  // sharded mapping: chooseSlab before the clustering (cuts, region), selectClusters after it
+  void chooseSlab(const double bbMin[3], const double bbMax[3], const int latticeCount[3], bool haveLattice);
+  void selectClusters();
   bool exchangeMode() const { return _group.active() && (_cfg.shard_mode == RBFMAP_SHARD_EXCHANGE || isConservative()); }
   bool duplicateMode() const { return _group.active() && !exchangeMode(); }
 
@@ -289,13 +291,13 @@ double PumMapping::estimateClusterRadius(const double *dXyz, int64_t nXyz, const
   return radii[middle];
 }
 
-// SURVEY.md 8(e), include/rbfmap.h: slabs along the lattice axis with the most layers, cut so that the largest number of
-// clusters a rank processes is minimal. Every rank computes the same cuts from the same (complete) centre list.
-void PumMapping::shardClusters(const double bbMin[3], const double bbMax[3], const int latticeCount[3], bool haveLattice)
+// SURVEY.md 8(e), include/rbfmap.h: slabs along the lattice axis with the most layers. The cuts are chosen BEFORE the
+// clustering, from the histogram of the in-vertices along that axis (clusters follow the vertex density), so that every
+// rank can restrict binning and clustering to its own region of the lattice; every rank computes the same cuts.
+void PumMapping::chooseSlab(const double bbMin[3], const double bbMax[3], const int latticeCount[3], bool haveLattice)
 {
   const int    world = _group.world, rank = _group.rank;
   const double inf   = std::numeric_limits<double>::infinity();
-  const bool   exch  = exchangeMode();
   int          axis  = 0;
   for (int d = 1; d < _cfg.dimensions; ++d)
     if (latticeCount[d] > latticeCount[axis])
@@ -310,9 +312,9 @@ void PumMapping::shardClusters(const double bbMin[3], const double bbMax[3], con
   } else {
     constexpr int kBins    = 4096;
     const double  binWidth = edge / kBins;
-    const auto    hist     = pumCentreHistogram(_centers.p, _nClusters, axis, bbMin[axis], binWidth, kBins, _stream);
+    const auto    hist     = pumVertexHistogram(_inXyz.p, _nIn, axis, bbMin[axis], binWidth, kBins, _stream);
     // duplicate mode: a rank also processes the clusters within one radius of its slab
-    const int        haloBins = exch ? 0 : static_cast<int>(std::ceil(_radius / binWidth)) + 1;
+    const int        haloBins = exchangeMode() ? 0 : static_cast<int>(std::ceil(_radius / binWidth)) + 1;
     std::vector<int> cuts(world + 1);
     pumPartitionSlabs(hist.data(), kBins, world, haloBins, cuts.data());
     if (rank > 0)
@@ -329,15 +331,37 @@ void PumMapping::shardClusters(const double bbMin[3], const double bbMax[3], con
   stats.shard_axis = axis;
   stats.shard_lo   = lo;
   stats.shard_hi   = hi;
-  // centres this rank processes: its own (exchange mode), or every centre whose sphere reaches into the slab (duplicate
-  // mode; |v - c| < r implies |v_a - c_a| < r, the margin covers the rounding of the comparison)
-  const double margin = exch ? 0.0 : _radius * (1.0 + 1e-12) + 1e-300;
-  double       selLo = lo - margin, selHi = hi + margin;
-  if (lo == inf) // empty slab
+}
+
+// After the (region-restricted) clustering: keeps the centres this rank processes - its own (exchange mode), or every centre
+// whose sphere reaches into the slab (duplicate mode; |v - c| < r implies |v_a - c_a| < r, the margin covers the rounding
+// of the comparison) - and counts the clusters of the whole mapping (every centre is owned by exactly one slab).
+void PumMapping::selectClusters()
+{
+  const double inf    = std::numeric_limits<double>::infinity();
+  const double margin = exchangeMode() ? 0.0 : _radius * (1.0 + 1e-12) + 1e-300;
+  double       selLo = _slab.lo - margin, selHi = _slab.hi + margin;
+  if (_slab.lo == inf) // empty slab
     selLo = selHi = inf;
-  DevBuf<double> local;
-  _nClusters = pumSelectSlab(_centers.p, _nClustersGlobal, axis, selLo, selHi, local, _globalIdx, _stream);
-  _centers   = std::move(local);
+  const int64_t  nRegion = _nClusters;
+  DevBuf<double> local, owned;
+  DevBuf<int>    ownedIdx;
+  const int64_t  nOwned = (margin > 0.0 && _group.connected()) ? pumSelectSlab(_centers.p, nRegion, _slab.axis, _slab.lo, _slab.hi, owned, ownedIdx, _stream) : -1;
+  _nClusters            = pumSelectSlab(_centers.p, nRegion, _slab.axis, selLo, selHi, local, _globalIdx, _stream);
+  _centers              = std::move(local);
+  // clusters of the whole mapping = sum of the owned ones; unknown (-1) without communicator
+  _nClustersGlobal = -1;
+  if (_group.connected()) {
+    DevBuf<int> cnt;
+    cnt.alloc(1);
+    const int mine = static_cast<int>(nOwned >= 0 ? nOwned : _nClusters);
+    RBF_CUDA(cudaMemcpyAsync(cnt.p, &mine, sizeof(int), cudaMemcpyHostToDevice, _stream));
+    _group.allReduceSum(cnt.p, 1, _stream);
+    int total = 0;
+    RBF_CUDA(cudaMemcpyAsync(&total, cnt.p, sizeof(int), cudaMemcpyDeviceToHost, _stream));
+    RBF_CUDA(cudaStreamSynchronize(_stream));
+    _nClustersGlobal = total;
+  }
 }
 
 void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const double *dOutputXyz, int64_t nOutput, cudaMemcpyKind kind)
@@ -440,7 +464,7 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
 
   BinGrid inGrid, outGrid;
   int     latticeCount[3] = {1, 1, 1};
-  bool    haveLattice     = false;
+  bool    haveLattice = false, replicatedDone = false;
   if (static_cast<uint64_t>(_nIn) < static_cast<uint64_t>(_cfg.vertices_per_cluster) * 2) {
     // single-cluster fallback :352-359
     double cRadius = 0.0;
@@ -519,18 +543,54 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
       axes.start[d]   = d < dim ? start[d] : 0.0;
       axes.invDist[d] = (d < dim && distances[d] > 0) ? 1.0 / distances[d] : 0.0;
     }
+    for (int d = 0; d < 3; ++d)
+      latticeCount[d] = static_cast<int>(nLocal[d]);
+    haveLattice = true;
+    // ---- up to here every rank of a sharded mapping repeats the same work (bounds, radius estimate) ----
+    stats.ms_replicated = replicated.stop();
+    replicatedDone      = true;
+    // Sharded mapping: this rank only clusters its own region. A final centre p that it needs lies within one radius of
+    // the slab [lo, hi); p is the in-vertex nearest to a lattice point l with |p - l| < r, so l_a lies within 2 r; the
+    // duplicate rule of l looks at its index neighbours, one lattice spacing s further; and the emptiness test and
+    // the projection of those need the vertices within another radius. Hence: lattice layers within 2 r + s, vertices
+    // within 3 r + s of the slab (plus a rounding margin). Inside that region every decision is made from complete
+    // information and is identical to the one of the unsharded mapping.
+    int    regionAxis = -1;
+    double regionLo = 0.0, regionHi = 0.0;
+    if (_group.active()) {
+      chooseSlab(bbMin, bbMax, latticeCount, true);
+      const int    ax = _slab.axis;
+      const double sp = distances[ax], eps = 1e-9 * _radius;
+      const double layerLo = _slab.lo - (2.0 * _radius + sp + eps), layerHi = _slab.hi + (2.0 * _radius + sp + eps);
+      regionAxis = ax;
+      regionLo   = _slab.lo - (3.0 * _radius + sp + 2.0 * eps);
+      regionHi   = _slab.hi + (3.0 * _radius + sp + 2.0 * eps);
+      int first = static_cast<int>(nLocal[ax]), last = -1;
+      for (int i = 0; i < static_cast<int>(nLocal[ax]); ++i)
+        if (axis[ax][i] >= layerLo && axis[ax][i] <= layerHi) {
+          first = std::min(first, i);
+          last  = std::max(last, i);
+        }
+      axes.rangeAxis = ax;
+      axes.rangeLo   = first;
+      axes.rangeHi   = last; // first > last: an empty slab
+      if (!(_slab.lo < _slab.hi))
+        regionLo = regionHi = std::numeric_limits<double>::quiet_NaN(); // nothing is binned
+      trace.phase("slab");
+    }
     // the lattice itself is never materialised: one tag per centre, one "still empty" bit per mesh that has to
     // populate the cluster (tagEmptyLattice clears them); coordinates only for the centres that survive
     cl.initLattice(axes, jit ? 1 : 3, _stream);
     trace.phase("lattice");
-    inGrid.build(_inXyz.p, _nIn, bbMin, bbMax, 0.5 * _radius, _stream); // half-radius cells, 5x5x5 neighbourhoods (forCandidatesWarp<2>)
+    // half-radius cells, 5x5x5 neighbourhoods (forCandidatesWarp<2>)
+    inGrid.build(_inXyz.p, _nIn, bbMin, bbMax, 0.5 * _radius, _stream, regionAxis, regionLo, regionHi);
     waitForOutMesh();
     if (_nOut > 0)
       computeBounds(_outXyz.p, _nOut, obMin, obMax, _stream);
     else
       for (int d = 0; d < 3; ++d)
         obMin[d] = bbMin[d], obMax[d] = bbMax[d];
-    outGrid.build(_outXyz.p, _nOut, obMin, obMax, 0.5 * _radius, _stream);
+    outGrid.build(_outXyz.p, _nOut, obMin, obMax, 0.5 * _radius, _stream, regionAxis, regionLo, regionHi);
     trace.phase("bin meshes");
 
     // :468-471
@@ -560,18 +620,19 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
     }
     _nClusters = cl.compact(_centers, _stream);
     trace.phase("compact");
-    if (_nClusters == 0)
+    if (_nClusters == 0 && !_group.active())
       throw MapError(RBFMAP_ERR_EMPTY, "Too many vertices have been filtered out."); // :502
-    for (int d = 0; d < 3; ++d)
-      latticeCount[d] = static_cast<int>(nLocal[d]);
-    haveLattice = true;
   }
   _nClustersGlobal = _nClusters;
-  // ---- everything up to here is repeated by every rank of a sharded mapping (identical, deterministic results) ----
-  stats.ms_replicated = replicated.stop();
+  if (!replicatedDone)
+    stats.ms_replicated = replicated.stop();
   if (_group.active()) {
-    shardClusters(bbMin, bbMax, latticeCount, haveLattice);
-    trace.phase("shard");
+    if (!haveLattice)
+      chooseSlab(bbMin, bbMax, latticeCount, false); // single-cluster fallback: rank 0 takes it
+    selectClusters();
+    trace.phase("select clusters");
+    if (_nClustersGlobal == 0)
+      throw MapError(RBFMAP_ERR_EMPTY, "Too many vertices have been filtered out."); // :502, decided by all ranks together
   }
   const PumSlab *outSlab = duplicateMode() ? &_slab : nullptr;
 

@@ -24,7 +24,17 @@ struct LatticeAxes {
   const double *a[3];
   int           n[3];
   double        start[3], invDist[3];
+  // sharded mapping: only the layers rangeLo <= index[rangeAxis] <= rangeHi of the lattice are processed by this rank
+  // (rangeAxis < 0: all); the centres outside count as empty
+  int rangeAxis = -1, rangeLo = 0, rangeHi = -1;
 };
+__host__ __device__ inline bool latticeLayerInRange(const LatticeAxes &L, int x, int y, int z)
+{
+  if (L.rangeAxis < 0)
+    return true;
+  const int i = L.rangeAxis == 0 ? x : (L.rangeAxis == 1 ? y : z);
+  return i >= L.rangeLo && i <= L.rangeHi;
+}
 
 struct PumClustering {
   int64_t        total  = 0; // lattice size
@@ -83,9 +93,9 @@ void    pumBuildMembership(const double *dCenters, int64_t nClusters, const BinG
                            PumScratch &scratch, double *wsum, int *wcount, const double *inXyz, const double *outXyz, DevBuf<double> &inRec,
                            DevBuf<double4> &outRec, cudaStream_t s, const PumSlab *outSlab = nullptr,
                            const std::function<void()> &weightsComplete = {}, bool fullMatrices = false);
-// sharded mapping: histogram of the centre coordinates along `axis`, selection of the centres inside [lo, hi) (order
-// preserved; globalIdx = index in the complete list), and the host-side choice of the cut positions
-std::vector<long long> pumCentreHistogram(const double *dCenters, int64_t n, int axis, double lo, double binWidth, int nBins, cudaStream_t s);
+// sharded mapping: histogram of the vertex coordinates along `axis`, selection of the centres inside [lo, hi) (order
+// preserved; globalIdx = index in the list handed in), and the host-side choice of the cut positions
+std::vector<long long> pumVertexHistogram(const double *dXyz, int64_t n, int axis, double lo, double binWidth, int nBins, cudaStream_t s);
 int64_t pumSelectSlab(const double *dCenters, int64_t n, int axis, double lo, double hi, DevBuf<double> &out, DevBuf<int> &globalIdx, cudaStream_t s);
 void    pumPartitionSlabs(const long long *hist, int nBins, int world, int haloBins, int *cuts /* world + 1 */);
 bool    pumBuildPointMembership(const double *dCenters, int64_t nClusters, const BinGrid &points, double radius, PumScratch &scratch, DevBuf<int> &nPts,

@@ -110,6 +110,8 @@ __global__ void __launch_bounds__(kBlockThreads) latticeEmptyKernel(LatticeAxes 
   const int    z = static_cast<int>(id % L.n[2]);
   const int    y = static_cast<int>((id / L.n[2]) % L.n[1]);
   const int    x = static_cast<int>(id / (static_cast<int64_t>(L.n[2]) * L.n[1]));
+  if (!latticeLayerInRange(L, x, y, z))
+    return; // another rank's part of the lattice
   const double cx = L.a[0][x], cy = L.a[1][y], cz = L.a[2][z];
   if (anyVertexInside(g, cx, cy, cz, r2Bound, lane) && lane == 0)
     atomicAnd(&tag[id], ~bit);
@@ -154,6 +156,8 @@ __global__ void __launch_bounds__(256) markLatticeKernel(const double *__restric
     for (int y = y0; y <= y1; ++y) {
       const double cy = L.a[1][y];
       for (int z = z0; z <= z1; ++z) {
+        if (!latticeLayerInRange(L, x, y, z))
+          continue;
         const int64_t id = (static_cast<int64_t>(x) * L.n[1] + y) * L.n[2] + z; // impl/CreateClustering.hpp:36-45
         // most centres have long been cleared by another vertex (a stale read only costs a redundant test)
         if ((tag[id] & bit) && sqDist3(cx, cy, L.a[2][z], vx, vy, vz) <= r2Bound)
@@ -221,6 +225,17 @@ __global__ void fillIntKernel(int *__restrict__ p, int64_t n, int v)
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i < n)
     p[i] = v;
+}
+// tag0 for the lattice layers this rank processes, "empty" (all bits) for the others
+__global__ void initLatticeTagKernel(int *__restrict__ tag, int64_t total, LatticeAxes L, int tag0)
+{
+  const int64_t id = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (id >= total)
+    return;
+  const int z = static_cast<int>(id % L.n[2]);
+  const int y = static_cast<int>((id / L.n[2]) % L.n[1]);
+  const int x = static_cast<int>(id / (static_cast<int64_t>(L.n[2]) * L.n[1]));
+  tag[id]     = latticeLayerInRange(L, x, y, z) ? tag0 : 7;
 }
 
 __global__ void liveListKernel(int64_t total, const int *__restrict__ tag, const int *__restrict__ pos, LatticeAxes L, int *__restrict__ liveIds,
@@ -584,13 +599,20 @@ __global__ void unassignedKernel(const int *__restrict__ wcount, int64_t nOut, i
 }
 
 // ---- sharded mapping: slab decomposition of the (global) centre list ----
-__global__ void centreHistogramKernel(const double *__restrict__ centers, int64_t n, int axis, double lo, double invBin, int nBins, int *__restrict__ hist)
+__global__ void vertexHistogramKernel(const double *__restrict__ xyz, int64_t n, int axis, double lo, double invBin, int nBins, int *__restrict__ hist)
 {
-  const int64_t c = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  if (c >= n)
-    return;
-  const double t = floor((centers[3 * c + axis] - lo) * invBin);
-  atomicAdd(&hist[static_cast<int>(fmin(fmax(t, 0.0), static_cast<double>(nBins - 1)))], 1);
+  __shared__ int local[4096];
+  for (int b = threadIdx.x; b < nBins; b += blockDim.x)
+    local[b] = 0;
+  __syncthreads();
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const double t = floor((xyz[3 * i + axis] - lo) * invBin);
+    atomicAdd(&local[static_cast<int>(fmin(fmax(t, 0.0), static_cast<double>(nBins - 1)))], 1);
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < nBins; b += blockDim.x)
+    if (local[b])
+      atomicAdd(&hist[b], local[b]);
 }
 
 __global__ void slabFlagKernel(const double *__restrict__ centers, int64_t n, int axis, double lo, double hi, int *__restrict__ keep)
@@ -688,7 +710,10 @@ void PumClustering::initLattice(const LatticeAxes &ax, int tag0, cudaStream_t s)
   total = static_cast<int64_t>(ax.n[0]) * ax.n[1] * ax.n[2];
   nLive = 0;
   tag.alloc(total);
-  fillIntKernel<<<divUp(total, 256), 256, 0, s>>>(tag.p, total, tag0);
+  if (ax.rangeAxis >= 0)
+    initLatticeTagKernel<<<divUp(total, 256), 256, 0, s>>>(tag.p, total, ax, tag0);
+  else
+    fillIntKernel<<<divUp(total, 256), 256, 0, s>>>(tag.p, total, tag0);
   RBF_LAUNCHED();
 }
 
@@ -699,7 +724,10 @@ void PumClustering::tagEmptyLattice(const BinGrid &mesh, int bit, cudaStream_t s
   // dense lattice (volume meshes: a centre per ~vertices-per-cluster / 5 vertices): one warp per centre, which finds a
   // vertex in its first batch of candidates; sparse lattice (surface meshes in 3-D: 97 % of the lattice is empty): from
   // the vertex side, work proportional to the mesh. Both decide every centre with the same distance test.
-  if (total * 8 <= mesh.n)
+  int64_t active = total; // lattice centres this rank processes
+  if (axes.rangeAxis >= 0)
+    active = total / std::max(1, axes.n[axes.rangeAxis]) * std::max(0, axes.rangeHi - axes.rangeLo + 1);
+  if (active * 8 <= mesh.n)
     latticeEmptyKernel<<<warpGrid(total), kBlockThreads, 0, s>>>(axes, total, mesh.view(), strictRadiusBound(radius), tag.p, bit);
   else
     markLatticeKernel<<<divUp(mesh.n, 256), 256, 0, s>>>(mesh.xyz.p, mesh.n, axes, radius, strictRadiusBound(radius), tag.p, bit);
@@ -1131,13 +1159,16 @@ void pumBlendGather(const double *stage, const PumVertexIndex &ix, int dims, dou
   RBF_CUDA(cudaGetLastError());
 }
 
-std::vector<long long> pumCentreHistogram(const double *dCenters, int64_t n, int axis, double lo, double binWidth, int nBins, cudaStream_t s)
+std::vector<long long> pumVertexHistogram(const double *dXyz, int64_t n, int axis, double lo, double binWidth, int nBins, cudaStream_t s)
 {
+  if (nBins > 4096)
+    throw MapError(RBFMAP_ERR_INVALID, "too many histogram bins");
   DevBuf<int> hist;
   hist.alloc(nBins);
   RBF_CUDA(cudaMemsetAsync(hist.p, 0, nBins * sizeof(int), s));
   if (n > 0) {
-    centreHistogramKernel<<<divUp(n, 256), 256, 0, s>>>(dCenters, n, axis, lo, binWidth > 0 ? 1.0 / binWidth : 0.0, nBins, hist.p);
+    const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, static_cast<int64_t>(smCount()) * 8)));
+    vertexHistogramKernel<<<grid, 256, 0, s>>>(dXyz, n, axis, lo, binWidth > 0 ? 1.0 / binWidth : 0.0, nBins, hist.p);
     RBF_LAUNCHED();
   }
   std::vector<int> h(nBins);

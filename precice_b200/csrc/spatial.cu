@@ -133,9 +133,17 @@ __global__ void collectWithinKernel(const double *__restrict__ xyz, int64_t n, P
 }
 
 // ------------------------------------------------------------------ binning
-__global__ void binCountKernel(const double *__restrict__ xyz, int64_t n, BinGridView g, int *__restrict__ cellOf, int *__restrict__ counts)
+__global__ void binCountKernel(const double *__restrict__ xyz, int64_t n, BinGridView g, int *__restrict__ cellOf, int *__restrict__ counts, int regionAxis,
+                               double regionLo, double regionHi)
 {
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    if (regionAxis >= 0) { // sharded mapping: points outside this rank's region are not binned
+      const double t = xyz[3 * i + regionAxis];
+      if (!(t >= regionLo && t <= regionHi)) {
+        cellOf[i] = -1;
+        continue;
+      }
+    }
     int cx = cellCoordUnclamped(xyz[3 * i], g.ox, g.ihx, g.nx);
     int cy = cellCoordUnclamped(xyz[3 * i + 1], g.oy, g.ihy, g.ny);
     int cz = cellCoordUnclamped(xyz[3 * i + 2], g.oz, g.ihz, g.nz);
@@ -152,6 +160,8 @@ __global__ void binScatterKernel(int64_t n, const int *__restrict__ cellOf, cons
 {
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int c               = cellOf[i];
+    if (c < 0)
+      continue;
     const int slot            = atomicAdd(&cursor[c], 1);
     ids[cellStart[c] + slot]  = static_cast<int>(i);
   }
@@ -307,7 +317,8 @@ void kthNeighbourDistance(const double *dXyz, int64_t n, const int *probeIds, in
     throw MapError(RBFMAP_ERR_INVALID, "cluster radius estimation did not converge");
 }
 
-void BinGrid::build(const double *dXyz, int64_t nPts, const double bbMin[3], const double bbMax[3], double minCell, cudaStream_t s)
+void BinGrid::build(const double *dXyz, int64_t nPts, const double bbMin[3], const double bbMax[3], double minCell, cudaStream_t s, int regionAxis,
+                    double regionLo, double regionHi)
 {
   n = nPts;
   // cell edge slightly above the query radius so that the 3x3x3 neighbourhood is conservative under rounding
@@ -341,18 +352,26 @@ void BinGrid::build(const double *dXyz, int64_t nPts, const double bbMin[3], con
   RBF_CUDA(cudaMemsetAsync(counts.p, 0, nCells * sizeof(int), s));
   const BinGridView g = view();
   if (nPts > 0) {
-    binCountKernel<<<gridFor(nPts), kBlock, 0, s>>>(dXyz, nPts, g, cellOf.p, counts.p);
+    binCountKernel<<<gridFor(nPts), kBlock, 0, s>>>(dXyz, nPts, g, cellOf.p, counts.p, regionAxis, regionLo, regionHi);
     RBF_LAUNCHED();
   }
   exclusiveScan(counts.p, cellStart.p, nCells, s);
+  if (regionAxis >= 0 && nPts > 0) { // number of points inside the region
+    int binned = 0;
+    RBF_CUDA(cudaMemcpyAsync(&binned, cellStart.p + nCells, sizeof(int), cudaMemcpyDeviceToHost, s));
+    RBF_CUDA(cudaStreamSynchronize(s));
+    n = binned;
+  }
   if (nPts > 0) {
     RBF_CUDA(cudaMemsetAsync(counts.p, 0, nCells * sizeof(int), s));
     binScatterKernel<<<gridFor(nPts), kBlock, 0, s>>>(nPts, cellOf.p, cellStart.p, counts.p, ids.p);
     RBF_LAUNCHED();
     binSortCellsKernel<<<gridFor(nCells), kBlock, 0, s>>>(nCells, cellStart.p, ids.p);
     RBF_LAUNCHED();
-    binGatherKernel<<<gridFor(nPts), kBlock, 0, s>>>(dXyz, nPts, ids.p, xyz.p);
-    RBF_LAUNCHED();
+    if (n > 0) {
+      binGatherKernel<<<gridFor(n), kBlock, 0, s>>>(dXyz, n, ids.p, xyz.p);
+      RBF_LAUNCHED();
+    }
   }
   RBF_CUDA(cudaGetLastError()); // temporaries are released stream-ordered
 }

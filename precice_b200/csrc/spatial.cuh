@@ -27,8 +27,11 @@ struct BinGrid {
   DevBuf<int>    cellStart, ids;
   DevBuf<double> xyz;
 
-  // bins `n` points (device AoS) with cell edge >= minCell; bounds are the mesh bounds
-  void        build(const double *dXyz, int64_t n, const double bbMin[3], const double bbMax[3], double minCell, cudaStream_t s);
+  // bins `n` points (device AoS) with cell edge >= minCell; bounds are the mesh bounds.
+  // regionAxis >= 0 (sharded mappings): only the points with regionLo <= x[regionAxis] <= regionHi are binned - the cell
+  // geometry is that of the whole mesh, `n` becomes the number of binned points and the vertex IDs stay global.
+  void        build(const double *dXyz, int64_t n, const double bbMin[3], const double bbMax[3], double minCell, cudaStream_t s, int regionAxis = -1,
+                    double regionLo = 0.0, double regionHi = 0.0);
   BinGridView view() const
   {
     return BinGridView{origin[0], origin[1], origin[2], 1.0 / h[0], 1.0 / h[1], 1.0 / h[2], dims[0], dims[1], dims[2], cellStart.p, xyz.p, ids.p};

@@ -73,7 +73,7 @@ def test_pum_sharded_duplicate_virtual_ranks(pb, world, dim, dims, project):
         m.computeMapping(inp, out)
         part = m.map(vals, dims)
         st = m.stats()
-        assert st["n_clusters_global"] == st0["n_clusters"]
+        assert st["n_clusters_global"] == -1  # unknown without communicator: every rank only clusters its own region
         ax, lo, hi = st["shard_axis"], st["shard_lo"], st["shard_hi"]
         assert 0 <= ax < dim
         own = (out[:, ax] >= lo) & (out[:, ax] < hi)
