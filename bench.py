@@ -308,6 +308,7 @@ def time_steps(ctx, mapping, compute_args, vals, res, steps, warmup, sampler=Non
     acc = {"ev": 0.0, "asm": 0.0, "map": 0.0, "rep": 0.0, "coll": 0.0, "launches": 0}
     if sampler:
         sampler.poll_reasons()
+        ctx.barrier()  # the NVML query above delays the ranks by different amounts
     for _ in range(steps):
         st = step()
         acc["ev"] += st["ms_compute_kernels"] + st["ms_map_kernels"]
@@ -317,7 +318,12 @@ def time_steps(ctx, mapping, compute_args, vals, res, steps, warmup, sampler=Non
         acc["coll"] += st["ms_collectives"]
         acc["launches"] += st["kernel_launches"]
         if sampler:
+            # NVML queries take 1 - 3 ms and delay the rank that issues them; in a sharded step the other ranks would
+            # then wait for it inside the next computeMapping (collectives) and that wait would be booked as device time of
+            # the step. The ranks therefore line up again after the query; the wall-clock figure contains all of it.
             sampler.poll_clock()
+            if ctx.world > 1:
+                ctx.dist.barrier()
         if os.environ.get("BENCH_VERBOSE"):
             print(f"[bench] rank {ctx.rank} step: compute {st['ms_compute_kernels']:.2f} ms (replicated {st['ms_replicated']:.2f}, factor "
                   f"{st['ms_assembly_factor']:.2f}) map {st['ms_map_kernels']:.2f} ms", file=sys.stderr, flush=True)
@@ -330,10 +336,15 @@ def time_steps(ctx, mapping, compute_args, vals, res, steps, warmup, sampler=Non
 
 def time_host_steps(ctx, mapping, h_in, h_out, h_vals, h_res, steps, warmup):
     def step():
+        t0 = time.perf_counter()
         if mapping.hasComputedMapping():
             mapping.clear()
         mapping.computeMapping(h_in, h_out)
+        t1 = time.perf_counter()
         mapping.map(h_vals, 1, out=h_res)
+        if os.environ.get("BENCH_VERBOSE"):
+            print(f"[bench] rank {ctx.rank} host step: clear + computeMapping {1e3 * (t1 - t0):.2f} ms, map {1e3 * (time.perf_counter() - t1):.2f} ms",
+                  file=sys.stderr, flush=True)
 
     for _ in range(warmup):
         step()
@@ -581,6 +592,8 @@ def main():
     os.dup2(2, 1)
     ctx = Ctx(args)
     rank, world, dev = ctx.rank, ctx.world, ctx.dev
+    if os.environ.get("BENCH_TRACE_RANK") is not None:  # development: phase trace (adds synchronisations) of one rank only
+        os.environ["RBFMAP_TRACE"] = "1" if rank == int(os.environ["BENCH_TRACE_RANK"]) else "0"
 
     n = args.n
     # every rank holds the complete (replicated) meshes of the ONE mapping
