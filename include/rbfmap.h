@@ -188,6 +188,13 @@ int rbfmap_map(rbfmap_handle *h, const double *in, int dims, double *out);
 int rbfmap_map_consistent(rbfmap_handle *h, const double *in, int dims, double *out);   /* Mapping.hpp:337 */
 int rbfmap_map_conservative(rbfmap_handle *h, const double *in, int dims, double *out); /* Mapping.hpp:324 */
 
+/* Several samples in one call: DataContext::mapData (precice/impl/DataContext.cpp:110-171) maps every time stample of a
+ * data, and every data of a mesh, with a separate Mapping::map(); handing them over together lets the device treat them as
+ * the components of one field (one gather, one factor load and one basis-function evaluation per cluster for up to three
+ * components). Sample k has dims[k] components, in[k] = n_input * dims[k] and out[k] = n_output * dims[k] doubles; the
+ * results equal those of `count` separate rbfmap_map() calls. Host pointers. */
+int rbfmap_map_batch(rbfmap_handle *h, int count, const double *const *in, const int *dims, double *const *out);
+
 /* Mapping::map(Sample, VectorXd&, VectorXd &lastSolution) (Mapping.cpp:150-156): the variant for mappings with
  * Mapping::requiresInitialGuess() (InitialGuessRequirement::Required, PetRadialBasisFctMapping.hpp:176) - the caller
  * (precice/impl/DataContext.cpp:159-161) owns one `guess` vector per data and hands it to every map() of that data: the

@@ -393,6 +393,24 @@ __global__ void scaleKernel(double *__restrict__ out, long long n, int dims, con
 } // namespace rbfmap
 using namespace rbfmap::scaled;
 
+namespace rbfmap {
+namespace scaled {
+// combined[v * D + off + c] <-> sample[v * dims + c]
+__global__ void interleaveKernel(const double *__restrict__ sample, long long n, int dims, int D, int off, double *__restrict__ combined)
+{
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i < n * dims)
+    combined[(i / dims) * D + off + (i % dims)] = sample[i];
+}
+__global__ void deinterleaveKernel(const double *__restrict__ combined, long long n, int dims, int D, int off, double *__restrict__ sample)
+{
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i < n * dims)
+    sample[i] = combined[(i / dims) * D + off + (i % dims)];
+}
+} // namespace scaled
+} // namespace rbfmap
+
 static bool isScaledConsistent(const DeviceMapping *m)
 {
   const int c = m->config().constraint;
@@ -694,6 +712,54 @@ static int mapHostImpl(rbfmap_handle *h, int mode, const double *in, int dims, d
 int rbfmap_map(rbfmap_handle *h, const double *in, int dims, double *out) { return mapHostImpl(h, 0, in, dims, out); }
 int rbfmap_map_consistent(rbfmap_handle *h, const double *in, int dims, double *out) { return mapHostImpl(h, 1, in, dims, out); }
 int rbfmap_map_conservative(rbfmap_handle *h, const double *in, int dims, double *out) { return mapHostImpl(h, 2, in, dims, out); }
+
+int rbfmap_map_batch(rbfmap_handle *h, int count, const double *const *in, const int *dims, double *const *out)
+{
+  if (!h)
+    return RBFMAP_ERR_INVALID;
+  return guarded(h, [&] {
+    DeviceMapping *m = h->impl.get();
+    if (!m->hasComputedMapping())
+      throw MapError(RBFMAP_ERR_STATE, "The mapping has not been computed; call computeMapping() first.");
+    if (count < 0 || (count > 0 && (!in || !dims || !out)))
+      throw MapError(RBFMAP_ERR_INVALID, "invalid batch");
+    int D = 0;
+    for (int k = 0; k < count; ++k) {
+      if (dims[k] < 1 || !in[k] || !out[k])
+        throw MapError(RBFMAP_ERR_INVALID, "invalid sample in the batch");
+      D += dims[k];
+    }
+    if (count == 0)
+      return;
+    cudaStream_t     s = m->stream();
+    AllocStreamScope allocScope(s);
+    const int64_t    nIn = m->nInput(), nOut = m->nOutput();
+    int              maxDims = 0;
+    for (int k = 0; k < count; ++k)
+      maxDims = std::max(maxDims, dims[k]);
+    DevBuf<double> dAllIn, dAllOut, dStage;
+    dAllIn.alloc(std::max<int64_t>(nIn * D, 1));
+    dAllOut.alloc(std::max<int64_t>(nOut * D, 1));
+    dStage.alloc(std::max<int64_t>(m->group().padded(std::max(nIn, nOut) * maxDims), 1));
+    // all samples side by side as the components of one field: the per-cluster kernels gather, factor-load and evaluate the
+    // basis function once per group of three components instead of once per sample
+    for (int k = 0, off = 0; k < count; off += dims[k], ++k) {
+      m->uploadReplicated(dStage.p, in[k], nIn * dims[k], s);
+      if (nIn > 0)
+        interleaveKernel<<<divUp(nIn * dims[k], 256), 256, 0, s>>>(dStage.p, nIn, dims[k], D, off, dAllIn.p);
+    }
+    RBF_CUDA(cudaGetLastError());
+    mapDeviceImpl(h, 0, dAllIn.p, D, dAllOut.p);
+    for (int k = 0, off = 0; k < count; off += dims[k], ++k) {
+      if (nOut > 0) {
+        deinterleaveKernel<<<divUp(nOut * dims[k], 256), 256, 0, s>>>(dAllOut.p, nOut, dims[k], D, off, dStage.p);
+        RBF_CUDA(cudaMemcpyAsync(out[k], dStage.p, static_cast<size_t>(nOut) * dims[k] * sizeof(double), cudaMemcpyDeviceToHost, s));
+      }
+    }
+    RBF_CUDA(cudaGetLastError());
+    RBF_CUDA(cudaStreamSynchronize(s));
+  });
+}
 
 int64_t rbfmap_initial_guess_size(const rbfmap_handle *h) { return h ? h->impl->initialGuessSize() : 0; }
 

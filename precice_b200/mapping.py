@@ -119,6 +119,20 @@ class _Mapping:
         """Mapping::map(Sample, VectorXd&): dispatch on the constraint (Mapping.cpp:158-173)."""
         return self._map(self._L.rbfmap_map, values, dims, out)
 
+    def mapBatch(self, samples, dims):
+        """Maps several samples (time stamples / data of one mesh, DataContext.cpp:110-171) in one call; returns one array per
+        sample, equal to [self.map(s, d) for s, d in zip(samples, dims)]."""
+        ins = [np.ascontiguousarray(np.asarray(v, dtype=np.float64).reshape(-1)) for v in samples]
+        for v, d in zip(ins, dims):
+            assert v.size == self._n_input * d
+        outs = [np.zeros(self._n_output * d) for d in dims]
+        k = len(ins)
+        pin = (C.c_void_p * k)(*[v.ctypes.data for v in ins])
+        pout = (C.c_void_p * k)(*[v.ctypes.data for v in outs])
+        pd = (C.c_int * k)(*[int(d) for d in dims])
+        self._check(self._L.rbfmap_map_batch(self._h, k, pin, pd, pout))
+        return outs
+
     def initialGuessSize(self) -> int:
         """Per-dimension length of the caller-owned initial guess (0: the mapping needs none, Mapping::requiresInitialGuess)."""
         return int(self._L.rbfmap_initial_guess_size(self._h))

@@ -289,3 +289,22 @@ def test_deterministic_blend_sharded(pb):
         m.computeMapping(inp, out)
         again += m.map(vals, 1)
     assert np.array_equal(again, total)  # ... but the sharded mapping itself is bit-reproducible
+
+
+# ---------------------------------------------------------------------------------------------- batched samples
+@pytest.mark.parametrize("constraint", ["consistent", "conservative"])
+def test_map_batch_equals_separate_maps(pb, constraint):
+    """rbfmap_map_batch: the stamples / data of DataContext::mapData (DataContext.cpp:110-171) in one call."""
+    inp, out, f = _case(3, 5000, 4500, 1)
+    samples = [f, np.stack([f, 2 * f + 1, -f], 1).reshape(-1), np.cos(5 * f), np.stack([f * f, 1 - f], 1).reshape(-1)]
+    dims = [1, 3, 1, 2]
+    makers = [lambda: pb.PartitionOfUnityMapping(constraint, 3, "compact-polynomial-c6", 0.2, "separate", 50, 0.15, True),
+              lambda: pb.RadialBasisFctMapping(constraint, 3, "compact-polynomial-c2", 0.3, polynomial="separate")]
+    for make in makers:
+        m = make()
+        m.computeMapping(inp, out)
+        separate = [m.map(s, d) for s, d in zip(samples, dims)]
+        batched = m.mapBatch(samples, dims)
+        for a, b in zip(batched, separate):
+            assert a.shape == b.shape and refcases.rel_l2(a, b) <= 1e-13
+        assert m.mapBatch([], []) == []
