@@ -87,6 +87,114 @@ __global__ void __launch_bounds__(256) sparseApplyKernel(RbfParams rbf, double s
   }
 }
 
+// ---- assembled system matrix (compactly supported functions): CSR over the cell-ordered vertices ----
+// The matrix-free operator above spends its time on candidates outside the support (5x5x5 cells hold 3.7x the volume of the
+// support sphere) and, because the hits are scattered over the lanes, pays the basis-function evaluation for every batch
+// of 32 candidates. The system matrix C is applied once per CG iteration, hundreds of times per map: its non-zeros are
+// therefore evaluated once in computeMapping and every iteration becomes a sparse matrix-vector product that streams
+// 12 bytes per non-zero from HBM (what the reference's PETSc path does with its assembled SBAIJ matrix,
+// PetRadialBasisFctMapping.hpp:842-1000; 1.6 GB at 500k vertices with ~260 neighbours).
+template <int H>
+__global__ void __launch_bounds__(256) countNeighboursKernel(double support2, BinGridView rows, long long rowBegin, long long nRows, BinGridView cols,
+                                                            int *__restrict__ count)
+{
+  const long long r    = rowBegin + ((blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5);
+  const int       lane = threadIdx.x & 31;
+  if (r >= nRows)
+    return;
+  const double px = rows.xyz[3 * r], py = rows.xyz[3 * r + 1], pz = rows.xyz[3 * r + 2];
+  int          n  = 0;
+  forNeighbourhoodWarp<H>(cols, px, py, pz, lane, [&](int pos, bool valid) {
+    if (valid && sqDistD<true>(px, py, pz, cols.xyz[3 * pos], cols.xyz[3 * pos + 1], cols.xyz[3 * pos + 2]) <= support2)
+      ++n;
+    return false;
+  });
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    n += __shfl_xor_sync(0xffffffffu, n, o);
+  if (lane == 0)
+    count[r - rowBegin] = n;
+}
+
+template <int KIND, int H>
+__global__ void __launch_bounds__(256) fillMatrixKernel(RbfParams rbf, double support2, BinGridView rows, long long rowBegin, long long nRows, BinGridView cols,
+                                                       const long long *__restrict__ rowOff, int *__restrict__ colIdx, double *__restrict__ val)
+{
+  const long long r    = rowBegin + ((blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5);
+  const int       lane = threadIdx.x & 31;
+  if (r >= nRows)
+    return;
+  const double px = rows.xyz[3 * r], py = rows.xyz[3 * r + 1], pz = rows.xyz[3 * r + 2];
+  long long    at = rowOff[r - rowBegin];
+  forNeighbourhoodWarp<H>(cols, px, py, pz, lane, [&](int pos, bool valid) {
+    double d2  = 0.0;
+    bool   hit = false;
+    if (valid) {
+      d2  = sqDistD<true>(px, py, pz, cols.xyz[3 * pos], cols.xyz[3 * pos + 1], cols.xyz[3 * pos + 2]);
+      hit = d2 <= support2;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (hit) {
+      const long long k = at + __popc(m & ((1u << lane) - 1u));
+      colIdx[k]         = pos;
+      val[k]            = evalBasisK<KIND>(distSqrt(d2), rbf); // the value sparseApplyKernel computes on the fly
+    }
+    at += __popc(m);
+    return false;
+  });
+}
+
+// y[c][r] = sum_k val[k] x[c][col[k]] over the row's non-zeros; one warp per row; optional fused dot product as above
+template <int NC>
+__global__ void __launch_bounds__(256) spmvKernel(const long long *__restrict__ rowOff, const int *__restrict__ colIdx, const double *__restrict__ val,
+                                                 long long rowBegin, long long nRows, const double *__restrict__ x, long long ldx, double *__restrict__ y,
+                                                 long long ldy, const double *__restrict__ dotWith, long long ldd, double *__restrict__ dotOut)
+{
+  __shared__ double dots[NC][8];
+  const long long r    = rowBegin + ((blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5);
+  const int       lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const bool      live = r < nRows;
+  double          acc[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+    acc[c] = 0.0;
+  if (live) {
+    const long long beg = rowOff[r - rowBegin], end = rowOff[r - rowBegin + 1];
+    for (long long k = beg + lane; k < end; k += 32) {
+      const double v = val[k];
+      const int    j = colIdx[k];
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+        acc[c] = fma(v, x[c * ldx + j], acc[c]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+      acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      if (live)
+        y[c * ldy + r] = acc[c];
+      if (dotWith)
+        dots[c][w] = live ? acc[c] * dotWith[c * ldd + r] : 0.0;
+    }
+  }
+  if (dotWith) {
+    __syncthreads();
+    if (threadIdx.x < NC) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        s += dots[threadIdx.x][k];
+      atomicAdd(&dotOut[threadIdx.x], s);
+    }
+  }
+}
+
 __global__ void gatherPlanarKernel(const double *__restrict__ in /*interleaved*/, int dims, int c0, int nc, const int *__restrict__ ids, long long n,
                                    double *__restrict__ out, long long ld)
 {
@@ -442,6 +550,8 @@ public:
   {
     if (world > 1 && !uniqueId)
       throw MapError(RBFMAP_ERR_INVALID, "rbf-global-iterative needs an NCCL id to shard (all-gather / all-reduce per iteration).");
+    if (_computed)
+      throw MapError(RBFMAP_ERR_STATE, "Please clear the mapping before joining a group."); // the row slices depend on the group
     _group.init(uniqueId, rank, world);
     // the kept initial guess has the leading dimension of the previous world size
     _guess.release();
@@ -476,6 +586,11 @@ public:
     _guessDims = 0;
     _oneInterpolant.release();
     _rescale = false;
+    _rowOff.release();
+    _colIdx.release();
+    _val.release();
+    _nnz       = 0;
+    _assembled = false;
     _computed  = false;
     stats      = rbfmap_stats{};
   }
@@ -505,6 +620,13 @@ private:
   DevBuf<double> _oneInterpolant;
   bool           _rescale = false;
   void           setupRescaling();
+  // assembled system matrix of this rank's row slice (CSR over cell-ordered positions), see spmvKernel
+  DevBuf<int64_t> _rowOff;
+  DevBuf<int>     _colIdx;
+  DevBuf<double>  _val;
+  int64_t         _nnz       = 0;
+  bool            _assembled = false;
+  void            assembleSystem();
 };
 
 void GlobalIterativeMapping::apply(const BinGrid &rows, int64_t rb, int64_t re, const BinGrid &cols, const double *x, int64_t ldx, double *y, int64_t ldy,
@@ -519,6 +641,18 @@ void GlobalIterativeMapping::apply(const BinGrid &rows, int64_t rb, int64_t re, 
   }
   const int    grid = divUp((re - rb) * 32, 256);
   const double s2   = _support * _support * (1.0 + 1e-12);
+  if (_assembled && &rows == &_inGrid && &cols == &_inGrid) { // the system matrix C of this rank's rows
+    const long long *off = reinterpret_cast<const long long *>(_rowOff.p);
+    if (nc == 1)
+      spmvKernel<1><<<grid, 256, 0, _stream>>>(off, _colIdx.p, _val.p, rb, re, x, ldx, y, ldy, dotWith, ldd, dotOut);
+    else if (nc == 2)
+      spmvKernel<2><<<grid, 256, 0, _stream>>>(off, _colIdx.p, _val.p, rb, re, x, ldx, y, ldy, dotWith, ldd, dotOut);
+    else
+      spmvKernel<3><<<grid, 256, 0, _stream>>>(off, _colIdx.p, _val.p, rb, re, x, ldx, y, ldy, dotWith, ldd, dotOut);
+    RBF_LAUNCHED();
+    RBF_CUDA(cudaGetLastError());
+    return;
+  }
   RBF_DISPATCH_HOT_BASIS(_rbf.kind, {
     if (nc == 1)
       sparseApplyKernel<KIND, 1, 2><<<grid, 256, 0, _stream>>>(_rbf, s2, rows.view(), rb, re, cols.view(), x, ldx, y, ldy, dotWith, ldd, dotOut);
@@ -627,6 +761,48 @@ void GlobalIterativeMapping::setupPolynomial()
       _poly.G[4 * r + s] = (r < p && s < p) ? inv[r][s] : 0.0;
 }
 
+void GlobalIterativeMapping::assembleSystem()
+{
+  _assembled = false;
+  if (!_sparse || _nIn == 0)
+    return;
+  int64_t rb, re, slice;
+  partitionRows(_nIn, _group.world, _group.rank, rb, re, slice);
+  const int64_t m = re - rb;
+  if (m <= 0) {
+    _assembled = true; // no rows on this rank
+    _rowOff.alloc(1);
+    RBF_CUDA(cudaMemsetAsync(_rowOff.p, 0, sizeof(int64_t), _stream));
+    return;
+  }
+  const double s2   = _support * _support * (1.0 + 1e-12);
+  const int    grid = divUp(m * 32, 256);
+  DevBuf<int>  count;
+  count.alloc(m);
+  countNeighboursKernel<2><<<grid, 256, 0, _stream>>>(s2, _inGrid.view(), rb, re, _inGrid.view(), count.p);
+  RBF_LAUNCHED();
+  _rowOff.alloc(m + 1);
+  exclusiveScan(count.p, _rowOff.p, m, _stream);
+  int64_t nnz = 0;
+  RBF_CUDA(cudaMemcpyAsync(&nnz, _rowOff.p + m, sizeof(int64_t), cudaMemcpyDeviceToHost, _stream));
+  RBF_CUDA(cudaStreamSynchronize(_stream));
+  // 12 bytes per non-zero; keep the matrix-free operator when the matrix would not fit comfortably
+  size_t freeB = 0, totalB = 0;
+  RBF_CUDA(cudaMemGetInfo(&freeB, &totalB));
+  if (static_cast<double>(nnz) * 12.0 > 0.5 * static_cast<double>(freeB)) {
+    _rowOff.release();
+    return;
+  }
+  _nnz = nnz;
+  _colIdx.alloc(std::max<int64_t>(nnz, 1));
+  _val.alloc(std::max<int64_t>(nnz, 1));
+  RBF_DISPATCH_HOT_BASIS(_rbf.kind, (fillMatrixKernel<KIND, 2><<<grid, 256, 0, _stream>>>(_rbf, s2, _inGrid.view(), rb, re, _inGrid.view(),
+                                                                                        reinterpret_cast<const long long *>(_rowOff.p), _colIdx.p, _val.p)));
+  RBF_LAUNCHED();
+  RBF_CUDA(cudaGetLastError());
+  _assembled = true;
+}
+
 // PetRadialBasisFctMapping.hpp:470-490: rescaling coefficients = C^-1 1 with the system-matrix solver, interpolant of
 // g(x) = 1 at the output sites, entries below 1e-6 set to exactly 0. Only for consistent mappings with a separated
 // polynomial; a solve that does not converge deactivates the rescaling (the reference warns and does the same).
@@ -709,6 +885,7 @@ void GlobalIterativeMapping::computeMapping(const double *dInputXyz, int64_t nIn
   _inGrid.build(inXyz.p, _nIn, iMin, iMax, cell, _stream);
   _outGrid.build(outXyz.p, _nOut, oMin, oMax, cell, _stream);
   setupPolynomial();
+  assembleSystem();
   _computed = true; // the operator is complete; the rescaling coefficients are obtained with it
   try {
     setupRescaling();
@@ -716,7 +893,8 @@ void GlobalIterativeMapping::computeMapping(const double *dInputXyz, int64_t nIn
     _computed = false;
     throw;
   }
-  stats.device_bytes       = static_cast<int64_t>(_inGrid.bytes() + _outGrid.bytes() + _oneInterpolant.bytes());
+  stats.device_bytes       = static_cast<int64_t>(_inGrid.bytes() + _outGrid.bytes() + _oneInterpolant.bytes() + _rowOff.bytes() + _colIdx.bytes() + _val.bytes());
+  stats.sum_mn             = _nnz; // non-zeros of this rank's rows of the assembled system matrix (0: matrix-free)
   stats.ms_compute_kernels = whole.stop();
   stats.kernel_launches    = g_launches;
   _computed                = true;
