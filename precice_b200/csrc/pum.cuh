@@ -2,6 +2,7 @@
 // kernels (pum_cluster.cu), the per-cluster algebra kernels (pum_solve.cu) and the host driver (pum.cu).
 #pragma once
 
+#include <algorithm>
 #include <functional>
 #include <vector>
 
@@ -179,12 +180,43 @@ struct __align__(16) PumEntry {
   long long inOff, outOff, matOff, pad2;
 };
 
+// Inside a bucket the clusters are sorted by their size n (size classes 0..128 and "more than 128"): the map kernels are
+// launched per group of sizes, with exactly the shared memory those sizes need (the packed factor is 8 n(n+1)/2 bytes, so
+// a launch sized for the largest cluster of a bucket of eight sizes would keep fewer clusters resident per SM).
+constexpr int kNumSizeClasses = 130;
+__host__ __device__ inline int pumSizeClassOf(int n) { return n > 128 ? 129 : (n < 0 ? 0 : n); }
 struct PumBuckets {
-  DevBuf<int>      order;             // cluster indices sorted by bucket
+  DevBuf<int>      order;             // cluster indices sorted by size class (hence by bucket)
   DevBuf<PumEntry> entries;           // the same order, with sizes and offsets
   int64_t     start[kNumBuckets + 1]; // offsets into `order`
   int         maxN[kNumBuckets];      // largest cluster of each bucket
+  int64_t     sizeStart[kNumSizeClasses + 1]; // offsets into `order` per size class
 };
+// calls fn(firstEntry, count, maxN) for the size groups of bucket b (groups of `width` consecutive sizes)
+template <typename F>
+inline void pumForSizeGroups(const PumBuckets &bk, int b, int width, F &&fn)
+{
+  int lo, hi; // sizes of the bucket
+  if (b < 8) {
+    lo = b == 0 ? 0 : 8 * b + 1;
+    hi = 8 * (b + 1);
+  } else if (b < 12) {
+    lo = 16 * (b - 4) + 1;
+    hi = 16 * (b - 3);
+  } else {
+    lo = hi = 129;
+  }
+  for (int n0 = lo; n0 <= hi; n0 += width) {
+    const int     n1    = std::min(hi, n0 + width - 1);
+    const int64_t count = bk.sizeStart[n1 + 1] - bk.sizeStart[n0];
+    if (count <= 0)
+      continue;
+    int maxN = n1;
+    while (maxN > n0 && bk.sizeStart[maxN + 1] == bk.sizeStart[maxN])
+      --maxN; // largest size class of the group that is populated
+    fn(bk.sizeStart[n0], count, b == 12 ? bk.maxN[12] : maxN);
+  }
+}
 
 // device-side classification + statistics (fills stats.sum_* and stats.max_n)
 void pumClassify(const PumMembership &m, int64_t nClusters, PumBuckets &b, rbfmap_stats &stats, cudaStream_t s);

@@ -639,10 +639,22 @@ __global__ void slabCompactKernel(int64_t n, const int *__restrict__ keep, const
 
 // ---- size buckets + statistics ----------------------------------------------------------------
 // acc: [0..12] bucket counts, [13] sum n, [14] sum m, [15] sum n^2, [16] sum n^3, [17] sum m n, [18] max n, [19..31] max n per bucket
-__global__ void classifyKernel(const int *__restrict__ nIn, const int *__restrict__ nOut, int64_t nClusters, unsigned long long *__restrict__ acc)
+// sizeHist: clusters per size class (pumSizeClassOf)
+__global__ void classifyKernel(const int *__restrict__ nIn, const int *__restrict__ nOut, int64_t nClusters, unsigned long long *__restrict__ acc,
+                               int *__restrict__ sizeHist)
 {
+  __shared__ int localHist[kNumSizeClasses];
+  for (int k = threadIdx.x; k < kNumSizeClasses; k += blockDim.x)
+    localHist[k] = 0;
+  __syncthreads();
   const int64_t c    = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   const int     lane = threadIdx.x & 31;
+  if (c < nClusters)
+    atomicAdd(&localHist[pumSizeClassOf(nIn[c])], 1);
+  __syncthreads();
+  for (int k = threadIdx.x; k < kNumSizeClasses; k += blockDim.x)
+    if (localHist[k])
+      atomicAdd(&sizeHist[k], localHist[k]);
   unsigned long long n = 0, m = 0;
   int                b = -1;
   if (c < nClusters) {
@@ -687,7 +699,7 @@ __global__ void bucketScatterKernel(const int *__restrict__ nIn, const int *__re
 {
   const int64_t c    = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   const int     lane = threadIdx.x & 31;
-  const int     b    = c < nClusters ? pumBucketOf(nIn[c]) : -1;
+  const int     b    = c < nClusters ? pumSizeClassOf(nIn[c]) : -1; // size class: the entries end up sorted by size
   const unsigned peers = __match_any_sync(0xffffffffu, b);
   if (b >= 0) {
     const int leader = __ffs(peers) - 1;
@@ -1253,25 +1265,35 @@ void pumClassify(const PumMembership &m, int64_t nClusters, PumBuckets &b, rbfma
 {
   DevBuf<unsigned long long> acc;
   DevBuf<long long>          dStart;
-  DevBuf<int>                cursor;
+  DevBuf<int>                cursor, sizeHist;
   acc.alloc(32);
-  dStart.alloc(kNumBuckets + 1);
-  cursor.alloc(kNumBuckets);
+  dStart.alloc(kNumSizeClasses + 1);
+  cursor.alloc(kNumSizeClasses);
+  sizeHist.alloc(kNumSizeClasses);
   RBF_CUDA(cudaMemsetAsync(acc.p, 0, 32 * sizeof(unsigned long long), s));
-  RBF_CUDA(cudaMemsetAsync(cursor.p, 0, kNumBuckets * sizeof(int), s));
-  classifyKernel<<<divUp(nClusters, 256), 256, 0, s>>>(m.nIn.p, m.nOut.p, nClusters, acc.p);
+  RBF_CUDA(cudaMemsetAsync(cursor.p, 0, kNumSizeClasses * sizeof(int), s));
+  RBF_CUDA(cudaMemsetAsync(sizeHist.p, 0, kNumSizeClasses * sizeof(int), s));
+  classifyKernel<<<divUp(nClusters, 256), 256, 0, s>>>(m.nIn.p, m.nOut.p, nClusters, acc.p, sizeHist.p);
   RBF_LAUNCHED();
   unsigned long long h[32];
+  int                hs[kNumSizeClasses];
   RBF_CUDA(cudaMemcpyAsync(h, acc.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+  RBF_CUDA(cudaMemcpyAsync(hs, sizeHist.p, sizeof(hs), cudaMemcpyDeviceToHost, s));
   RBF_CUDA(cudaStreamSynchronize(s));
-  long long start[kNumBuckets + 1];
+  long long start[kNumSizeClasses + 1]; // per size class; the buckets are unions of consecutive size classes
   start[0] = 0;
-  for (int k = 0; k < kNumBuckets; ++k) {
-    start[k + 1] = start[k] + static_cast<long long>(h[k]);
-    b.start[k]   = start[k];
-    b.maxN[k]    = static_cast<int>(h[19 + k]);
+  for (int k = 0; k < kNumSizeClasses; ++k) {
+    start[k + 1]   = start[k] + hs[k];
+    b.sizeStart[k] = start[k];
   }
-  b.start[kNumBuckets] = start[kNumBuckets];
+  b.sizeStart[kNumSizeClasses] = start[kNumSizeClasses];
+  int64_t run = 0;
+  for (int k = 0; k < kNumBuckets; ++k) {
+    b.start[k] = run;
+    run += static_cast<int64_t>(h[k]);
+    b.maxN[k] = static_cast<int>(h[19 + k]);
+  }
+  b.start[kNumBuckets] = run;
   stats.sum_n  = static_cast<int64_t>(h[13]);
   stats.sum_m  = static_cast<int64_t>(h[14]);
   stats.sum_n2 = static_cast<int64_t>(h[15]);

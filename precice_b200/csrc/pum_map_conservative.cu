@@ -298,15 +298,18 @@ void dispatchConservative(const PumSolveArgs &a, const PumBuckets &bk, const dou
     const int64_t count = bk.start[b + 1] - bk.start[b];
     if (count <= 0)
       continue;
-    const int *list = bk.order.p + bk.start[b];
     for (int c0 = 0; c0 < dims;) {
       const int nc = std::min(3, dims - c0);
-      if (nc == 1)
-        bucketConservative<KIND, 1>(a, b, list, count, bk.maxN[b], in, dims, c0, out, s);
-      else if (nc == 2)
-        bucketConservative<KIND, 2>(a, b, list, count, bk.maxN[b], in, dims, c0, out, s);
-      else
-        bucketConservative<KIND, 3>(a, b, list, count, bk.maxN[b], in, dims, c0, out, s);
+      // one launch per group of cluster sizes (see pumForSizeGroups)
+      pumForSizeGroups(bk, b, b < 8 ? 2 : 4, [&](int64_t first, int64_t cnt, int maxN) {
+        const int *list = bk.order.p + first;
+        if (nc == 1)
+          bucketConservative<KIND, 1>(a, b, list, cnt, maxN, in, dims, c0, out, s);
+        else if (nc == 2)
+          bucketConservative<KIND, 2>(a, b, list, cnt, maxN, in, dims, c0, out, s);
+        else
+          bucketConservative<KIND, 3>(a, b, list, cnt, maxN, in, dims, c0, out, s);
+      });
       c0 += nc;
     }
   }

@@ -8,6 +8,7 @@
 #include "pum_map.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 
 namespace rbfmap {
 #ifdef RBF_PHASE_TIMING
@@ -338,6 +339,13 @@ void bucketConsistent(const PumSolveArgs &a, int bucket, const PumEntry *list, i
     launchConsistent<KIND, NC, 256, false>(a, list, count, maxN, in, dims, c0, out, s);
 }
 
+// sizes per launch group of the warp-per-cluster buckets (RBFMAP_MAP_SIZE_GROUP overrides, for experiments)
+static const int kMapSizeGroup = [] {
+  const char *e = std::getenv("RBFMAP_MAP_SIZE_GROUP");
+  const int   v = e ? std::atoi(e) : 4;
+  return v >= 1 && v <= 8 ? v : 4;
+}();
+
 template <int KIND>
 void dispatchConsistent(const PumSolveArgs &a, const PumBuckets &bk, const double *in, int dims, double *out, cudaStream_t s)
 {
@@ -345,15 +353,18 @@ void dispatchConsistent(const PumSolveArgs &a, const PumBuckets &bk, const doubl
     const int64_t count = bk.start[b + 1] - bk.start[b];
     if (count <= 0)
       continue;
-    const PumEntry *list = bk.entries.p + bk.start[b];
     for (int c0 = 0; c0 < dims;) { // components are processed in groups of up to 3 per launch
       const int nc = std::min(3, dims - c0);
-      if (nc == 1)
-        bucketConsistent<KIND, 1>(a, b, list, count, bk.maxN[b], in, dims, c0, out, s);
-      else if (nc == 2)
-        bucketConsistent<KIND, 2>(a, b, list, count, bk.maxN[b], in, dims, c0, out, s);
-      else
-        bucketConsistent<KIND, 3>(a, b, list, count, bk.maxN[b], in, dims, c0, out, s);
+      // one launch per group of cluster sizes, with the shared memory (and hence the residency) of exactly those sizes
+      pumForSizeGroups(bk, b, b < 8 ? kMapSizeGroup : 4, [&](int64_t first, int64_t cnt, int maxN) {
+        const PumEntry *list = bk.entries.p + first;
+        if (nc == 1)
+          bucketConsistent<KIND, 1>(a, b, list, cnt, maxN, in, dims, c0, out, s);
+        else if (nc == 2)
+          bucketConsistent<KIND, 2>(a, b, list, cnt, maxN, in, dims, c0, out, s);
+        else
+          bucketConsistent<KIND, 3>(a, b, list, cnt, maxN, in, dims, c0, out, s);
+      });
       c0 += nc;
     }
   }
