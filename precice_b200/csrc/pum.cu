@@ -669,7 +669,7 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
 
   // partition-of-unity weight sums (PartitionOfUnityMapping.hpp:263-276, 290-341)
   {
-    const int64_t bad = pumFirstUnassigned(_wcount.p, _nOut, _stream, _outXyz.p, outSlab, _group.active() ? &_group : nullptr);
+    const int64_t bad = pumFirstUnassigned(_wsum.p, _wcount.p, _nOut, _stream, _outXyz.p, outSlab, _group.active() ? &_group : nullptr);
     if (bad >= 0) {
       double v[3];
       RBF_CUDA(cudaMemcpy(v, _outXyz.p + 3 * bad, sizeof(v), cudaMemcpyDeviceToHost));
@@ -883,7 +883,7 @@ void PumMapping::jitMapConsistentAt(JitCache &c, const double *hCoords, int64_t 
     RBF_CUDA(cudaMemsetAsync(wcount.p, 0, nPts * sizeof(int), _stream));
     clustered = pumBuildPointMembership(_centers.p, _nClusters, ptGrid, _radius, _scratch, nP, ptOff, ptIds, wsum.p, wcount.p, _stream);
     if (clustered) {
-      const int64_t bad = pumFirstUnassigned(wcount.p, nPts, _stream);
+      const int64_t bad = pumFirstUnassigned(wsum.p, wcount.p, nPts, _stream);
       if (bad >= 0)
         throwUnassigned(dX.p, bad, false);
       pumJitEvaluateClustered(solveArgs(), _nClusters, static_cast<int>(stats.max_n), dX.p, nP.p, reinterpret_cast<const long long *>(ptOff.p), ptIds.p, wsum.p,

@@ -441,8 +441,14 @@ __device__ __forceinline__ int gatherToShared(const BinGridView &g, double cx, d
       stagePos[at] = pos; // position in the binned arrays: neighbouring hits share cache lines there
     }
     if (WEIGHTS && d2 <= rW2Bound) {
-      atomicAdd(wsum + id, pumWeight(__dsqrt_rn(d2), rinv));
-      atomicAdd(wcount + id, 1);
+      // wcount only counts the coverings with weight exactly zero (a vertex within an ulp of the cluster radius): it is
+      // what tells "covered, all weights zero -> equal weights" (PartitionOfUnityMapping.hpp:329-333) from "not covered"
+      // (:314-318); one atomic per covering instead of two
+      const double wgt = pumWeight(__dsqrt_rn(d2), rinv);
+      if (wgt > 0.0)
+        atomicAdd(wsum + id, wgt);
+      else
+        atomicAdd(wcount + id, 1);
     }
     base += __popc(m);
     return false;
@@ -561,7 +567,7 @@ __global__ void memberPackKernel(int64_t nClusters, const int *__restrict__ nIn,
     dO[i]         = id;
     const double *p = gout.xyz + 3 * static_cast<long long>(pos);
     const double  x = p[0], y = p[1], z = p[2];
-    ro[i]           = make_double4(x, y, z, normalizedWeight(x, y, z, cx, cy, cz, rinv, wsum[id], wcount[id]));
+    ro[i]           = make_double4(x, y, z, normalizedWeight(x, y, z, cx, cy, cz, rinv, wsum[id], wcount + id));
   }
 }
 
@@ -584,11 +590,12 @@ __global__ void memberFillKernel(const double *__restrict__ centers, int64_t nCl
 }
 
 // ---- out-vertices that no cluster covers (PartitionOfUnityMapping.hpp:312-320) ----
-__global__ void unassignedKernel(const int *__restrict__ wcount, int64_t nOut, int *__restrict__ firstUnassigned, const double *__restrict__ outXyz,
+__global__ void unassignedKernel(const double *__restrict__ wsum, const int *__restrict__ wcount, int64_t nOut, int *__restrict__ firstUnassigned,
+                                 const double *__restrict__ outXyz,
                                  PumSlab slab, bool useSlab)
 {
   const int64_t v = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  if (v < nOut && wcount[v] == 0) {
+  if (v < nOut && !(wsum[v] > 0.0) && wcount[v] == 0) { // no covering cluster at all
     if (useSlab) { // sharded mapping: only the vertices this rank owns have complete counts
       const double t = outXyz[3 * v + slab.axis];
       if (!(t >= slab.lo && t < slab.hi))
@@ -993,7 +1000,7 @@ __global__ void outRecordKernel(PumSolveArgs a, int64_t nClusters, double4 *__re
     const long long gid = a.outIds[off + o];
     const double   *p   = a.outXyz + 3 * gid;
     const double    x = p[0], y = p[1], z = p[2];
-    rec[off + o]        = make_double4(x, y, z, normalizedWeight(x, y, z, cx, cy, cz, rinv, a.wsum[gid], a.wcount[gid]));
+    rec[off + o]        = make_double4(x, y, z, normalizedWeight(x, y, z, cx, cy, cz, rinv, a.wsum[gid], a.wcount + gid));
   }
 }
 
@@ -1027,13 +1034,14 @@ void pumBuildInRecords(const PumSolveArgs &a, int64_t sumIn, double *rec, cudaSt
   RBF_CUDA(cudaGetLastError());
 }
 
-int64_t pumFirstUnassigned(const int *wcount, int64_t nOut, cudaStream_t s, const double *outXyz, const PumSlab *slab, const ShardGroup *group)
+int64_t pumFirstUnassigned(const double *wsum, const int *wcount, int64_t nOut, cudaStream_t s, const double *outXyz, const PumSlab *slab,
+                           const ShardGroup *group)
 {
   DevBuf<int> first;
   first.alloc(1);
   RBF_CUDA(cudaMemsetAsync(first.p, 0x7f, sizeof(int), s));
   if (nOut > 0) {
-    unassignedKernel<<<divUp(nOut, 256), 256, 0, s>>>(wcount, nOut, first.p, outXyz, slab ? *slab : PumSlab{}, slab != nullptr);
+    unassignedKernel<<<divUp(nOut, 256), 256, 0, s>>>(wsum, wcount, nOut, first.p, outXyz, slab ? *slab : PumSlab{}, slab != nullptr);
     RBF_LAUNCHED();
   }
   if (group) // every rank reports the same (lowest) unassigned vertex, so that all ranks raise the same error

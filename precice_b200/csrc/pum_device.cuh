@@ -300,10 +300,13 @@ __device__ __forceinline__ void blockReduceSum(double (&v)[NV], double *red, int
 
 // normalized partition-of-unity weight of out-vertex (x,y,z) in the cluster centred at (cx,cy,cz)
 // (PartitionOfUnityMapping.hpp:321-336)
-__device__ __forceinline__ double normalizedWeight(double x, double y, double z, double cx, double cy, double cz, double rinv, double wsum, int wcount)
+// `zeroCount` points to the number of covering clusters whose weight is exactly zero; it is only read when the weight sum
+// is not positive - then every covering cluster has weight zero and the count is the number of covering clusters
+__device__ __forceinline__ double normalizedWeight(double x, double y, double z, double cx, double cy, double cz, double rinv, double wsum,
+                                                   const int *__restrict__ zeroCount)
 {
   if (wsum <= 0.0)
-    return __ddiv_rn(1.0, static_cast<double>(wcount));
+    return __ddiv_rn(1.0, static_cast<double>(*zeroCount));
   const double w = pumWeight(__dsqrt_rn(sqDist3(cx, cy, cz, x, y, z)), rinv);
   return __ddiv_rn(w, wsum);
 }

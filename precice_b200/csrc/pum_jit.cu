@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(32, 16) pumEvaluateClusteredKernel(PumSolveArg
           for (int k = 0; k < 4; ++k)
             acc[cc] += q[k] * beta[k][cc];
       }
-      const double w = normalizedWeight(x, y, z, cx, cy, cz, rinv, wsum[gid], wcount[gid]);
+      const double w = normalizedWeight(x, y, z, cx, cy, cz, rinv, wsum[gid], wcount + gid);
 #pragma unroll
       for (int cc = 0; cc < NC; ++cc)
         atomicAdd(&out[gid * dims + c0 + cc], acc[cc] * w);
