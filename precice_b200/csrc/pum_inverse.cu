@@ -44,11 +44,13 @@ __global__ void __launch_bounds__(kInvThreads) pumInverseKernel(PumSolveArgs arg
     sx[i] = p[0], sy[i] = p[1], sz[i] = p[2];
   }
   __syncthreads();
+  // thread (tx, ty) owns the elements (tx + 16 a, ty + 8 b): consecutive threads touch consecutive rows of a column, and
+  // the loops need no integer division (the flat e % n, e / n version spent most of its time on them)
+  const int tx = tid & 15, ty = tid >> 4;
   // ---- buildMatrixCLU (RadialBasisFctSolver.hpp:191-192), both triangles ----
-  for (int e = tid; e < n * n; e += kInvThreads) {
-    const int i = e % n, j = e / n;
-    a[e]        = pairBasis<KIND_RUNTIME, DIM3>(sx[j], sy[j], sz[j], sx[i], sy[i], sz[i], rbf, 0.0);
-  }
+  for (int j = ty; j < n; j += kInvThreads / 16)
+    for (int i = tx; i < n; i += 16)
+      a[j * n + i] = pairBasis<KIND_RUNTIME, DIM3>(sx[j], sy[j], sz[j], sx[i], sy[i], sz[i], rbf, 0.0);
   __syncthreads();
   // ---- in-place Gauss-Jordan inversion with partial pivoting ----
   for (int k = 0; k < n; ++k) {
@@ -108,16 +110,25 @@ __global__ void __launch_bounds__(kInvThreads) pumInverseKernel(PumSolveArgs arg
     __syncthreads();
     const double d = 1.0 / colk[k];
     // row k <- row k / pivot with a(k, k) <- 1 / pivot; row i <- row i - a(i, k) row k with a(i, k) <- -a(i, k) / pivot
-    for (int e = tid; e < n * n; e += kInvThreads) {
-      const int i = e % n, j = e / n;
-      double    v;
-      if (i == k)
-        v = (j == k) ? d : rowk[j] * d;
-      else if (j == k)
-        v = -colk[i] * d;
-      else
-        v = fma(-colk[i], rowk[j] * d, a[e]);
-      a[e] = v;
+    // rank-one update of all elements with branch-free inner loops (the thread's rows of the pivot column stay in
+    // registers); the pivot row and the pivot column are overwritten with their final values afterwards
+    double ci[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      ci[q] = (tx + 16 * q < n) ? colk[tx + 16 * q] : 0.0;
+    for (int j = ty; j < n; j += kInvThreads / 16) {
+      const double rj  = rowk[j] * d;
+      double      *col = a + j * n + tx;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (tx + 16 * q < n)
+          col[16 * q] = fma(-ci[q], rj, col[16 * q]);
+    }
+    __syncthreads();
+    for (int j = tid; j < n; j += kInvThreads) {
+      a[j * n + k] = (j == k) ? d : rowk[j] * d; // row k <- row k / pivot, a(k, k) <- 1 / pivot
+      if (j != k)
+        a[k * n + j] = -colk[j] * d;             // column k <- -column k / pivot
     }
     __syncthreads();
   }
