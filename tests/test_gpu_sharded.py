@@ -219,3 +219,33 @@ def test_global_tag_mesh_rounds(pb):
     assert mt.tagMeshFirstRound(remote, local).all()
     z = np.zeros(20000, np.uint8)
     assert mt.tagMeshSecondRound(remote, np.ones(20000, np.uint8), z).sum() == 0
+
+
+@pytest.mark.parametrize("long_axis", [1, 2])
+def test_pum_sharded_slab_axis_follows_the_lattice(pb, long_axis):
+    """The slabs are cut along the lattice axis with the most layers: meshes elongated along y / z are cut along y / z (the
+    lattice index is x-major, so only axis 0 gives contiguous index ranges - the other axes exercise the general path)."""
+    n, vpc = 8000, 30
+    inp, out = _meshes(n)
+    inp[:, long_axis] *= 3.0
+    out[:, long_axis] *= 3.0
+    vals = _field(inp, 1)
+    support = 2.0 * (3.0 * 3.0 * vpc / (4.0 * np.pi * n)) ** (1.0 / 3.0)
+    args = ("consistent", 3, "compact-polynomial-c6", support, "separate", vpc, 0.15, True)
+    single = pb.PartitionOfUnityMapping(*args)
+    single.computeMapping(inp, out)
+    ref = single.map(vals, 1)
+    _, centers0, *_ = single.clusters()
+    total, seen, owners = np.zeros_like(ref), set(), np.zeros(n, dtype=int)
+    for r in range(4):
+        m = pb.PartitionOfUnityMapping(*args)
+        m.distributedInit(None, r, 4)
+        m.computeMapping(inp, out)
+        st = m.stats()
+        assert st["shard_axis"] == long_axis
+        owners += (out[:, long_axis] >= st["shard_lo"]) & (out[:, long_axis] < st["shard_hi"])
+        total += m.map(vals, 1)
+        if st["n_clusters"]:
+            seen.update(map(tuple, m.clusters()[1]))
+    assert np.all(owners == 1) and seen == set(map(tuple, centers0))
+    assert refcases.rel_l2(total, ref) <= 1e-13
