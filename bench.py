@@ -683,6 +683,20 @@ def main():
             except pb.MappingError as e:
                 map_only[mode] = {"error": f"{e.status}: {e}"}
         secondary["map_only"] = map_only
+        # several samples in one call (rbfmap_map_batch: the stamples / data of DataContext::mapData as components of one
+        # field): three scalar samples as ONE 3-component map against three separate maps, device-resident
+        if not mapping.hasComputedMapping():
+            mapping.computeMapping(in_xyz, out_xyz)
+        v3 = vector_field_torch(in_xyz)
+        t1, t3 = [], []
+        for _ in range(3):
+            mapping.map(vals, 1, out=res_dev)
+            t1.append(mapping.stats()["ms_map_kernels"])
+            mapping.map(v3, 3)
+            t3.append(mapping.stats()["ms_map_kernels"])
+        (ms1, ms3) = ctx.max_over_ranks([min(t1), min(t3)])
+        secondary["batched_samples"] = {"ms_three_separate_scalar_maps": 3 * ms1, "ms_one_batched_map_of_three": ms3,
+                                        "note": "rbfmap_map_batch interleaves the samples on the device and maps them as one field"}
         if world > 1:
             other = "exchange" if args.shard_mode == "duplicate" else "duplicate"
             mo = ctx.pum("consistent", n, other)
