@@ -85,6 +85,17 @@ struct ShardGroup {
     if (connected() && count > 0)
       RBF_NCCL(ncclApi().AllReduce(v, v, static_cast<size_t>(count), ncclInt32, ncclMin, comm, s));
   }
+  // several collectives in one launch
+  void groupStart() const
+  {
+    if (connected())
+      RBF_NCCL(ncclApi().GroupStart());
+  }
+  void groupEnd() const
+  {
+    if (connected())
+      RBF_NCCL(ncclApi().GroupEnd());
+  }
   // every rank holds its slice [rank * slice, (rank + 1) * slice) of v (padded(count) elements); afterwards all of v
   void allGatherInPlace(double *v, int64_t slice, cudaStream_t s) const
   {

@@ -198,6 +198,7 @@ private:
   double          _radius    = 0.0;
   int64_t         _nClusters = 0; // clusters this rank processes (all of them unless the mapping is sharded)
   int64_t         _nClustersGlobal = 0;
+  int64_t         _ownedClusters   = 0; // sharded mapping: clusters whose centre lies in this rank's slab
   PumSlab         _slab{};        // sharded mapping: what this rank owns
   DevBuf<int>     _globalIdx;     // sharded mapping: index of each local cluster in the complete list
   DevBuf<double>  _centers;
@@ -349,19 +350,10 @@ void PumMapping::selectClusters()
   const int64_t  nOwned = (margin > 0.0 && _group.connected()) ? pumSelectSlab(_centers.p, nRegion, _slab.axis, _slab.lo, _slab.hi, owned, ownedIdx, _stream) : -1;
   _nClusters            = pumSelectSlab(_centers.p, nRegion, _slab.axis, selLo, selHi, local, _globalIdx, _stream);
   _centers              = std::move(local);
-  // clusters of the whole mapping = sum of the owned ones; unknown (-1) without communicator
+  // clusters of the whole mapping = sum of the owned ones over the ranks: agreed on at the end of computeMapping together
+  // with the error flags (one collective); unknown (-1) without communicator
+  _ownedClusters   = nOwned >= 0 ? nOwned : _nClusters;
   _nClustersGlobal = -1;
-  if (_group.connected()) {
-    DevBuf<int> cnt;
-    cnt.alloc(1);
-    const int mine = static_cast<int>(nOwned >= 0 ? nOwned : _nClusters);
-    RBF_CUDA(cudaMemcpyAsync(cnt.p, &mine, sizeof(int), cudaMemcpyHostToDevice, _stream));
-    _group.allReduceSum(cnt.p, 1, _stream);
-    int total = 0;
-    RBF_CUDA(cudaMemcpyAsync(&total, cnt.p, sizeof(int), cudaMemcpyDeviceToHost, _stream));
-    RBF_CUDA(cudaStreamSynchronize(_stream));
-    _nClustersGlobal = total;
-  }
 }
 
 void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const double *dOutputXyz, int64_t nOutput, cudaMemcpyKind kind)
@@ -631,8 +623,15 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
       chooseSlab(bbMin, bbMax, latticeCount, false); // single-cluster fallback: rank 0 takes it
     selectClusters();
     trace.phase("select clusters");
-    if (_nClustersGlobal == 0)
-      throw MapError(RBFMAP_ERR_EMPTY, "Too many vertices have been filtered out."); // :502, decided by all ranks together
+  }
+  // Sharded mapping: the three things the ranks have to agree on - lowest unassigned output vertex, lowest cluster with a
+  // singular matrix, number of clusters - travel in ONE pair of grouped all-reduces after the factorisation, so that
+  // every rank raises the same error (a rank that stopped early would leave the others waiting in the next collective).
+  DevBuf<int> agree; // [0] first unassigned vertex (min), [1] failing cluster (min), [2] -(largest cluster) (min), [3] owned clusters (sum)
+  if (_group.active()) {
+    agree.alloc(4);
+    const int init[4] = {0x7f7f7f7f, INT_MAX, 0, static_cast<int>(_ownedClusters)};
+    RBF_CUDA(cudaMemcpyAsync(agree.p, init, sizeof(init), cudaMemcpyHostToDevice, _stream)); // pageable source: staged before the call returns
   }
   const PumSlab *outSlab = duplicateMode() ? &_slab : nullptr;
 
@@ -668,9 +667,7 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
   trace.phase("membership");
 
   // partition-of-unity weight sums (PartitionOfUnityMapping.hpp:263-276, 290-341)
-  {
-    const int64_t bad = pumFirstUnassigned(_wsum.p, _wcount.p, _nOut, _stream, _outXyz.p, outSlab, _group.active() ? &_group : nullptr);
-    if (bad >= 0) {
+  auto throwUnassignedVertex = [&](int64_t bad) {
       double v[3];
       RBF_CUDA(cudaMemcpy(v, _outXyz.p + 3 * bad, sizeof(v), cudaMemcpyDeviceToHost));
       std::ostringstream os;
@@ -684,7 +681,13 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
             "\"vertices-per-cluster\" (default is 50), the \"relative-overlap\" (default is 0.15), or disable the option \"project-to-input\". "
             "These options are only valid for the <mapping:rbf-pum-direct/> tag.";
       throw MapError(RBFMAP_ERR_UNASSIGNED, os.str());
-    }
+  };
+  if (_group.active()) {
+    pumMarkFirstUnassigned(_wsum.p, _wcount.p, _nOut, _stream, _outXyz.p, outSlab, agree.p);
+  } else {
+    const int64_t bad = pumFirstUnassigned(_wsum.p, _wcount.p, _nOut, _stream, _outXyz.p);
+    if (bad >= 0)
+      throwUnassignedVertex(bad);
   }
 
   // deterministic mode: the weight sums (accumulated with atomics above) are recomputed per vertex in cluster order and
@@ -714,37 +717,75 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
   stats.n_clusters_global = _nClustersGlobal;
   stats.cluster_radius    = _radius;
   trace.phase("classify");
-  if (stats.max_n > kPumMaxClusterVertices)
-    throw MapError(RBFMAP_ERR_UNSUPPORTED, "rbf-pum-direct: a cluster with " + std::to_string(stats.max_n) + " vertices exceeds the supported cluster size of " +
-                                               std::to_string(kPumMaxClusterVertices) + " vertices; reduce \"vertices-per-cluster\".");
+  // cluster-size limits of the factor / inverse kernels; on a sharded mapping the largest cluster of ALL ranks decides
+  const auto checkClusterSize = [&](int64_t maxN) {
+    if (_inverse && maxN > kPumMaxInverseVertices)
+      throw MapError(RBFMAP_ERR_UNSUPPORTED, "rbf-pum-direct with a basis function that is not strictly positive definite supports clusters of up to " +
+                                                 std::to_string(kPumMaxInverseVertices) + " vertices (found " + std::to_string(maxN) +
+                                                 "); reduce \"vertices-per-cluster\".");
+    if (maxN > kPumMaxClusterVertices)
+      throw MapError(RBFMAP_ERR_UNSUPPORTED, "rbf-pum-direct: a cluster with " + std::to_string(maxN) + " vertices exceeds the supported cluster size of " +
+                                                 std::to_string(kPumMaxClusterVertices) + " vertices; reduce \"vertices-per-cluster\".");
+  };
+  const bool tooLarge = stats.max_n > (_inverse ? kPumMaxInverseVertices : kPumMaxClusterVertices);
+  if (!_group.active())
+    checkClusterSize(stats.max_n);
   // separated polynomial + assembly/factorisation of all local systems
   _poly.alloc(std::max<int64_t>(_nClusters, 1));
-  if (_mat.n < static_cast<size_t>(std::max<int64_t>(_mem.sumTri, 1))) {
+  if (!tooLarge && _mat.n < static_cast<size_t>(std::max<int64_t>(_mem.sumTri, 1))) {
     RBF_CUDA(cudaStreamSynchronize(_stream));
     _mat.reserve(static_cast<size_t>(_mem.sumTri) + static_cast<size_t>(_mem.sumTri) / 16 + 2);
   }
   const PumSolveArgs args = solveArgs();
   trace.phase("alloc factors");
-  if (_nClusters > 0)
+  if (_nClusters > 0 && !tooLarge)
     pumPolySetup(args, _nClusters, _cfg.polynomial, _stream);
   trace.phase("polySetup");
-  DevBuf<int> fail;
-  fail.alloc(1);
-  const int noFail = INT_MAX;
-  RBF_CUDA(cudaMemcpyAsync(fail.p, &noFail, sizeof(int), cudaMemcpyHostToDevice, _stream));
+  DevBuf<int> failBuf;
+  int        *failP = nullptr; // lowest failing cluster index or INT_MAX
+  if (_group.active()) {
+    failP = agree.p + 1;
+    const int negMax = -static_cast<int>(stats.max_n);
+    RBF_CUDA(cudaMemcpyAsync(agree.p + 2, &negMax, sizeof(int), cudaMemcpyHostToDevice, _stream));
+  } else {
+    failBuf.alloc(1);
+    const int noFail = INT_MAX;
+    RBF_CUDA(cudaMemcpyAsync(failBuf.p, &noFail, sizeof(int), cudaMemcpyHostToDevice, _stream));
+    failP = failBuf.p;
+  }
   EventTimer tf(_stream);
   tf.start();
-  if (_inverse)
-    pumInverse(args, _buckets, fail.p, _stream);
+  if (tooLarge)
+    ; // sharded mapping: this rank joins the agreement below and raises the size error with the others
+  else if (_inverse)
+    pumInverse(args, _buckets, failP, _stream);
   else
-    pumFactor(args, _buckets, fail.p, _stream);
+    pumFactor(args, _buckets, failP, _stream);
   stats.ms_assembly_factor = tf.stop();
   trace.phase("assembly + factorisation");
-  if (_group.active()) { // every rank raises the error of the failing rank (the next collective would wait for it forever)
-    _group.allReduceMin(fail.p, 1, _stream);
-  }
   int failed = INT_MAX;
-  RBF_CUDA(cudaMemcpy(&failed, fail.p, sizeof(int), cudaMemcpyDeviceToHost));
+  if (_group.active()) {
+    _group.groupStart();
+    _group.allReduceMin(agree.p, 3, _stream);
+    _group.allReduceSum(agree.p + 3, 1, _stream);
+    _group.groupEnd();
+    int h[4];
+    RBF_CUDA(cudaMemcpyAsync(h, agree.p, sizeof(h), cudaMemcpyDeviceToHost, _stream));
+    RBF_CUDA(cudaStreamSynchronize(_stream));
+    checkClusterSize(-h[2]);
+    failed = h[1];
+    if (_group.connected()) {
+      _nClustersGlobal        = h[3];
+      stats.n_clusters_global = _nClustersGlobal;
+      if (_nClustersGlobal == 0)
+        throw MapError(RBFMAP_ERR_EMPTY, "Too many vertices have been filtered out."); // CreateClustering.hpp:502, decided by all ranks together
+    }
+    // the reference builds the cluster solvers (singular matrix) before it assigns the weights (unassigned vertex)
+    if (failed == INT_MAX && h[0] != 0x7f7f7f7f)
+      throwUnassignedVertex(h[0]);
+  } else {
+    RBF_CUDA(cudaMemcpy(&failed, failBuf.p, sizeof(int), cudaMemcpyDeviceToHost));
+  }
   if (failed != INT_MAX) {
     // RadialBasisFctSolver.hpp:360-365
     const char *inName = cons ? "output" : "input", *outName = cons ? "input" : "output";

@@ -102,6 +102,8 @@ void    pumPartitionSlabs(const long long *hist, int nBins, int world, int haloB
 bool    pumBuildPointMembership(const double *dCenters, int64_t nClusters, const BinGrid &points, double radius, PumScratch &scratch, DevBuf<int> &nPts,
                                 DevBuf<int64_t> &off, DevBuf<int> &ids, double *wsum, int *wcount, cudaStream_t s);
 // -1: every out-vertex (of the slab, if given) lies in a cluster; with a group the lowest index over all ranks
+// device-only variant: atomicMin of the lowest unassigned vertex into *dFirst (0x7f7f7f7f = none); no synchronisation
+void pumMarkFirstUnassigned(const double *wsum, const int *wcount, int64_t nOut, cudaStream_t s, const double *outXyz, const PumSlab *slab, int *dFirst);
 // wsum / wcount: partition-of-unity weight sum of every out-vertex and the number of its covering clusters with weight zero
 int64_t pumFirstUnassigned(const double *wsum, const int *wcount, int64_t nOut, cudaStream_t s, const double *outXyz = nullptr,
                            const PumSlab *slab = nullptr, const ShardGroup *group = nullptr);

@@ -1034,6 +1034,14 @@ void pumBuildInRecords(const PumSolveArgs &a, int64_t sumIn, double *rec, cudaSt
   RBF_CUDA(cudaGetLastError());
 }
 
+void pumMarkFirstUnassigned(const double *wsum, const int *wcount, int64_t nOut, cudaStream_t s, const double *outXyz, const PumSlab *slab, int *dFirst)
+{
+  if (nOut > 0) {
+    unassignedKernel<<<divUp(nOut, 256), 256, 0, s>>>(wsum, wcount, nOut, dFirst, outXyz, slab ? *slab : PumSlab{}, slab != nullptr);
+    RBF_LAUNCHED();
+  }
+}
+
 int64_t pumFirstUnassigned(const double *wsum, const int *wcount, int64_t nOut, cudaStream_t s, const double *outXyz, const PumSlab *slab,
                            const ShardGroup *group)
 {

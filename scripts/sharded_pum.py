@@ -117,6 +117,25 @@ for constraint in ("consistent", "conservative"):
                 del m
         del single
 
+# Errors are agreed on by all ranks (one grouped all-reduce at the end of computeMapping): a stray vertex that only one
+# rank owns, or a singular cluster that only one rank factorises, raises the SAME error on every rank - none is left
+# waiting in a collective - and the singular matrix wins over the unassigned vertex like in the reference's order.
+stray = np.concatenate([out, [[0.5, 0.5, 3.0]]])
+dup = inp.copy()
+dup[1] = dup[0]  # two identical in-vertices: one cluster matrix is singular
+for mode in ("duplicate", "exchange"):
+    for label, ci, co, want in (("unassigned", inp, stray, "UNASSIGNED"), ("singular", dup, out, "SINGULAR"), ("both", dup, stray, "SINGULAR")):
+        m = make("consistent", mode)
+        got = "none"
+        try:
+            m.computeMapping(ci, co)
+        except pb.MappingError as e:
+            got = e.status
+        print(f"[rank {rank}] error agreement {mode:9s} {label:10s}: {got}", flush=True)
+        if got != want:
+            failures.append(f"error agreement {mode}/{label}: rank {rank} got {got}, expected {want}")
+        del m
+
 if a.time:
     ti, to = torch.from_numpy(inp).to(dev), torch.from_numpy(out).to(dev)
     tv = torch.from_numpy(values("consistent", 1)).to(dev)

@@ -230,6 +230,12 @@ def test_pum_not_positive_definite_limits(pb):
     with pytest.raises(pb.MappingError) as e:
         m.computeMapping(inp, out)
     assert e.value.status == "UNSUPPORTED" and "128 vertices" in str(e.value)
+    for r in range(2):  # a rank of a sharded mapping reaches the ranks' agreement first and raises the same error there
+        m = pb.PartitionOfUnityMapping("consistent", 3, "thin-plate-splines", 0.0, "separate", 300, 0.15, True)
+        m.distributedInit(None, r, 2)
+        with pytest.raises(pb.MappingError) as e:
+            m.computeMapping(inp, out)
+        assert e.value.status == "UNSUPPORTED" and "128 vertices" in str(e.value)
     # duplicated vertices make the cluster matrices singular: the reference's message (RadialBasisFctSolver.hpp:360-365)
     dup = np.concatenate([inp, inp[:40]])
     m = pb.PartitionOfUnityMapping("consistent", 3, "volume-splines", 0.0, "separate", 40, 0.15, True)
