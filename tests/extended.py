@@ -19,6 +19,10 @@ def basis_ld(kind, param, r):
         return {"c0": q ** 2, "c2": q ** 4 * (4 * p + 1), "c4": q ** 6 * (35 * p ** 2 + 18 * p + 3),
                 "c6": q ** 8 * (32 * p ** 3 + 25 * p ** 2 + 8 * p + 1),
                 "c8": q ** 10 * (1287 * p ** 4 + 1350 * p ** 3 + 630 * p ** 2 + 150 * p + 15)}[kind[-2:]]
+    if kind == "compact-tps-c2":  # impl/BasisFunctions.hpp:328-335
+        p = np.minimum(r / LD(param), LD(1))
+        v = 1 - 30 * p ** 2 - 10 * p ** 3 + 45 * p ** 4 - 6 * p ** 5 - p ** 3 * 60 * np.log(np.maximum(p, LD(1e-14)))
+        return np.where(p >= 1, LD(0), v)
     if kind == "gaussian":  # shape parameter; cut off at sqrt(-ln 1e-9) / s (impl/BasisFunctions.hpp:229-272)
         s = LD(param)
         cut = np.sqrt(-np.log(LD(1e-9))) / s

@@ -37,6 +37,9 @@ PUM_CASES = [  # id, dim, basis, param (None: 2 x cluster radius; gaussian: supp
     ("thin-plate-splines", 3, "thin-plate-splines", 0.0, "separate", 40, 2000, 1e-7),  # test_pum_with_functions_that_are_not_positive_definite
     ("volume-splines", 3, "volume-splines", 0.0, "off", 40, 2000, 1e-7),
     ("headline", 3, "compact-polynomial-c6", "2r", "separate", 50, 4000, 1e-10),      # cfg4 configuration: no wide tolerance needed
+    # sensitivity of the headline configuration to the support radius (cond(C_c) grows like (R/h)^7.5 for C6)
+    ("headline-3r", 3, "compact-polynomial-c6", "3r", "separate", 50, 4000, 1e-10),
+    ("headline-5r", 3, "compact-polynomial-c6", "5r", "separate", 50, 4000, 1e-9),
 ]
 
 
@@ -55,7 +58,7 @@ def test_pum_tolerances_against_extended_precision(pb, case, constraint):
         probe = oracle.PumMapping(constraint, dim, "compact-polynomial-c0", 1.0, polynomial, vpc, 0.15, True)
         probe.compute_mapping(a, b)
         r = probe.cluster_radius
-        param = {"2r": 2.0 * r, "1.5r": 1.5 * r, "gauss": 4.55228 / (2.0 * r)}[param]
+        param = {"2r": 2.0 * r, "3r": 3.0 * r, "5r": 5.0 * r, "1.5r": 1.5 * r, "gauss": 4.55228 / (2.0 * r)}[param]
     args = (constraint, dim, basis, param, polynomial, vpc, 0.15, True)
     o = oracle.PumMapping(*args)
     o.compute_mapping(a, b)
@@ -80,8 +83,6 @@ def test_global_tolerances_against_extended_precision(pb, basis, param, polynomi
     """test_global_direct_vs_oracle (1e-6 for the functions without compact polynomial form) and the thin-plate-spline
     cases (1e-7), on a 600 -> 520 vertex version of the same meshes (the long-double elimination is O(n^3) in numpy)."""
     import oracle
-    if basis == "compact-tps-c2":
-        pytest.skip("the extended-precision model has no compact thin-plate spline")
     inp, out = refcases.halton(600, (2, 3, 5)), refcases.halton(520, (7, 11, 13))
     a, b = (inp, out) if constraint == "consistent" else (out, inp)
     vals = refcases.field(a)
