@@ -12,6 +12,7 @@ ap.add_argument("--vertices", dest="n", type=int, default=1_000_000)
 ap.add_argument("--steps", type=int, default=1)
 ap.add_argument("--constraint", default="consistent")
 ap.add_argument("--dims", type=int, default=1)
+ap.add_argument("--virtual-rank", default=None, help="R/W: this GPU plays rank R of a mapping sharded over W ranks (group without communicator)")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 inp = bench.halton_torch(a.n, (2, 3, 5), 1, dev)
@@ -20,6 +21,9 @@ vals = bench.field_torch(inp if a.constraint == "consistent" else out).contiguou
 if a.dims > 1:
     vals = torch.stack([vals * (k + 1) for k in range(a.dims)], dim=1).contiguous().reshape(-1)
 m = pb.PartitionOfUnityMapping(a.constraint, 3, bench.BASIS, bench.support_radius(a.n), "separate", bench.VPC, bench.OVERLAP, True)
+if a.virtual_rank:
+    r_, w_ = (int(x) for x in a.virtual_rank.split("/"))
+    m.distributedInit(None, r_, w_)
 for s in range(a.steps):
     if m.hasComputedMapping():
         m.clear()
