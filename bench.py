@@ -199,6 +199,35 @@ def workload_config(n, world, shard_mode, n_sample_note=None):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(index):
+    """Pins this process to the CPUs of the NUMA node its GPU hangs off (what `numactl --cpunodebind` does in a production
+    launcher), BEFORE any host buffer is allocated: pinned staging memory is then first-touched on the socket whose PCIe
+    root the GPU sits on, and eight ranks do not all stream through one socket's memory controllers. Returns a note for
+    the JSON line. BENCH_NUMA=0 switches it off; silently skipped where sysfs has no topology (containers)."""
+    if os.environ.get("BENCH_NUMA", "1") == "0":
+        return "off"
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.lower().split(":", 1)
+        dev = f"/sys/bus/pci/devices/{dom[-4:]}:{rest}"
+        node = int(open(dev + "/numa_node").read())
+        cpus = set()
+        for part in open(dev + "/local_cpulist").read().strip().split(","):
+            if part:
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if node < 0 or not cpus:
+            return "no topology"
+        os.sched_setaffinity(0, cpus)
+        return f"node {node} ({len(cpus)} cpus)"
+    except Exception as e:  # no NVML / sysfs: leave the affinity alone
+        return f"unavailable ({type(e).__name__})"
+
+
 class Ctx:
     """Per-process state: device, process group, helpers."""
 
@@ -209,6 +238,7 @@ class Ctx:
         self.rank = int(os.environ.get("RANK", "0"))
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.numa = bind_to_gpu_numa_node(self.local_rank)
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
         if self.world > 1:
@@ -334,14 +364,21 @@ def time_steps(ctx, mapping, compute_args, vals, res, steps, warmup, sampler=Non
     return acc, mapping.stats()
 
 
-def time_host_steps(ctx, mapping, h_in, h_out, h_vals, h_res, steps, warmup):
+def time_host_steps(ctx, mapping, h_in, h_out, h_vals, h_res, steps, warmup, sliced=False):
+    """`sliced`: every rank reads back its 1/world slice of the complete result (rbfmap_map_sliced), the mirror of the
+    upload in which every rank sends 1/world of the inputs; returns (ms, slice begin, slice end)."""
+    span = [0, h_res.numel()]
+
     def step():
         t0 = time.perf_counter()
         if mapping.hasComputedMapping():
             mapping.clear()
         mapping.computeMapping(h_in, h_out)
         t1 = time.perf_counter()
-        mapping.map(h_vals, 1, out=h_res)
+        if sliced:
+            _, span[0], span[1] = mapping.mapSliced(h_vals, 1, out=h_res)
+        else:
+            mapping.map(h_vals, 1, out=h_res)
         if os.environ.get("BENCH_VERBOSE"):
             print(f"[bench] rank {ctx.rank} host step: clear + computeMapping {1e3 * (t1 - t0):.2f} ms, map {1e3 * (time.perf_counter() - t1):.2f} ms",
                   file=sys.stderr, flush=True)
@@ -353,7 +390,7 @@ def time_host_steps(ctx, mapping, h_in, h_out, h_vals, h_res, steps, warmup):
     for _ in range(steps):
         step()
     ctx.barrier()
-    return (time.perf_counter() - t0) * 1e3
+    return (time.perf_counter() - t0) * 1e3, span[0], span[1]
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -628,12 +665,17 @@ def main():
     checksum = None
     if "e2e" in legs:
         h_in, h_out, h_vals = in_xyz.cpu().pin_memory(), out_xyz.cpu().pin_memory(), vals.cpu().pin_memory()
-        h_res = torch.empty(n, dtype=torch.float64).pin_memory()
-        e2e_ms = time_host_steps(ctx, mapping, h_in, h_out, h_vals, h_res, args.steps, min(args.warmup, 3))
-        checksum = float(h_res.sum())
+        h_res = torch.zeros(n, dtype=torch.float64).pin_memory()
+        e2e_ms, lo, hi = time_host_steps(ctx, mapping, h_in, h_out, h_vals, h_res, args.steps, min(args.warmup, 3), sliced=world > 1)
+        # the slices of the ranks tile the complete field: each is checked against the device-resident result
+        want = complete_result(ctx, mapping, res_timed)[lo:hi]
+        got = h_res[lo:hi].to(dev)
+        if hi > lo and float((got - want).norm() / want.norm().clamp_min(1e-300)) > 1e-12:
+            raise SystemExit(f"bench.py: rank {rank}: the end-to-end result differs from the device-resident one")
+        checksum = float(ctx.sum_over_ranks(got.sum().reshape(1)).item()) if world > 1 else float(h_res.sum())
         if world == 1:  # pageable host memory (what a caller without pinned staging buffers hands over): driver-staged copies
             p_in, p_out, p_vals, p_res = h_in.clone(), h_out.clone(), h_vals.clone(), torch.empty(n, dtype=torch.float64)
-            e2e_pageable_ms = time_host_steps(ctx, mapping, p_in, p_out, p_vals, p_res, max(2, args.steps // 2), 1) / max(2, args.steps // 2)
+            e2e_pageable_ms = time_host_steps(ctx, mapping, p_in, p_out, p_vals, p_res, max(2, args.steps // 2), 1)[0] / max(2, args.steps // 2)
             del p_in, p_out, p_vals, p_res
 
     # ---------------- max over ranks ----------------
@@ -783,10 +825,11 @@ def main():
                 "hbm_peak_gbs": peaks.get("hbm_gbs")}
         if e2e_ms is not None:
             line["e2e"] = {"value": n / (e2e_max / steps * 1e-3), "unit": "vertices/s",
-                           "h2d_bytes_per_step": 8 * (3 * n + 3 * n + n), "d2h_bytes_per_step": 8 * n * world,
-                           "ms_per_step": e2e_max / steps, "host_memory": "pinned (rbfmap_host_alloc / cudaHostAlloc)",
+                           "h2d_bytes_per_step": 8 * (3 * n + 3 * n + n), "d2h_bytes_per_step": 8 * n,
+                           "ms_per_step": e2e_max / steps, "host_memory": "pinned (rbfmap_host_alloc / cudaHostAlloc)", "numa": ctx.numa,
                            "note": "sharded: every rank uploads 1/world of the meshes and values over PCIe (all-gather over NVLink) and "
-                                   "reads back the complete result array" if world > 1 else "one GPU: complete upload and read-back"}
+                                   "reads back 1/world of the complete result (rbfmap_map_sliced: reduce-scatter over NVLink); bytes are "
+                                   "totals over the ranks" if world > 1 else "one GPU: complete upload and read-back"}
             line["checksum"] = checksum
             if e2e_pageable_ms is not None:
                 line["e2e_pageable"] = {"value": n / (e2e_pageable_ms * 1e-3), "unit": "vertices/s", "ms_per_step": e2e_pageable_ms,

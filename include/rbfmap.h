@@ -188,6 +188,13 @@ int rbfmap_map(rbfmap_handle *h, const double *in, int dims, double *out);
 int rbfmap_map_consistent(rbfmap_handle *h, const double *in, int dims, double *out);   /* Mapping.hpp:337 */
 int rbfmap_map_conservative(rbfmap_handle *h, const double *in, int dims, double *out); /* Mapping.hpp:324 */
 
+/* rbfmap_map for a sharded mapping (rbfmap_distributed_init) whose ranks each want THEIR part of the result - the mirror of
+ * the upload, where every rank sends 1/world of the values over PCIe: the partial results are reduce-scattered over NVLink
+ * (nothing to exchange where every rank already holds the complete result) and only the values of the output vertices
+ * [*begin, *end) = rbfmap_partition_rows(n_output, world, rank) are copied to `out[*begin * dims .. *end * dims)`; the rest
+ * of `out` (a full-size array, like `in`) is not touched. On a single device the slice is the whole result. Host pointers. */
+int rbfmap_map_sliced(rbfmap_handle *h, const double *in, int dims, double *out, int64_t *begin, int64_t *end);
+
 /* Several samples in one call: DataContext::mapData (precice/impl/DataContext.cpp:110-171) maps every time stample of a
  * data, and every data of a mesh, with a separate Mapping::map(); handing them over together lets the device treat them as
  * the components of one field (one gather, one factor load and one basis-function evaluation per cluster for up to three

@@ -35,7 +35,7 @@ EXPORTS = [
     "rbfmap_pum_get_clusters", "rbfmap_pum_get_cluster_ids", "rbfmap_eval_basis", "rbfmap_device_count",
     "rbfmap_device_info", "rbfmap_measure_fp64_peak", "rbfmap_debug_dist_sqrt", "rbfmap_debug_pair_basis", "rbfmap_nccl_unique_id", "rbfmap_distributed_init",
     "rbfmap_partition_rows", "rbfmap_partition_slabs", "rbfmap_struct_sizes", "rbfmap_tag_mesh_first_round", "rbfmap_tag_mesh_second_round",
-    "rbfmap_estimate_cluster_radius", "rbfmap_set_connectivity", "rbfmap_map_batch", "rbfmap_initial_guess_size", "rbfmap_map_with_initial_guess", "rbfmap_host_alloc", "rbfmap_host_free", "rbfmap_compute_mapping_just_in_time", "rbfmap_cache_create", "rbfmap_cache_reset", "rbfmap_cache_destroy",
+    "rbfmap_estimate_cluster_radius", "rbfmap_set_connectivity", "rbfmap_map_batch", "rbfmap_map_sliced", "rbfmap_initial_guess_size", "rbfmap_map_with_initial_guess", "rbfmap_host_alloc", "rbfmap_host_free", "rbfmap_compute_mapping_just_in_time", "rbfmap_cache_create", "rbfmap_cache_reset", "rbfmap_cache_destroy",
     "rbfmap_cache_update", "rbfmap_map_consistent_at", "rbfmap_map_conservative_at", "rbfmap_complete_just_in_time_mapping",
 ]
 
@@ -127,6 +127,7 @@ def lib():
         L.rbfmap_tag_mesh_second_round.argtypes = [vp, vp, C.c_int64, vp, vp]
         L.rbfmap_estimate_cluster_radius.argtypes = [vp, vp, C.c_int64, dp, dp, dp]
         L.rbfmap_set_connectivity.argtypes = [vp, C.c_int, vp, C.c_int64, C.c_int]
+        L.rbfmap_map_sliced.argtypes = [vp, vp, C.c_int, vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.rbfmap_map_batch.argtypes = [vp, C.c_int, C.POINTER(vp), ip, C.POINTER(vp)]
         L.rbfmap_initial_guess_size.argtypes = [vp]
         L.rbfmap_initial_guess_size.restype = C.c_int64

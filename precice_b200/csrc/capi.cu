@@ -709,6 +709,45 @@ static int mapHostImpl(rbfmap_handle *h, int mode, const double *in, int dims, d
   });
 }
 
+int rbfmap_map_sliced(rbfmap_handle *h, const double *in, int dims, double *out, int64_t *begin, int64_t *end)
+{
+  if (!h || !begin || !end)
+    return RBFMAP_ERR_INVALID;
+  return guarded(h, [&] {
+    DeviceMapping *m = h->impl.get();
+    if (!m->hasComputedMapping())
+      throw MapError(RBFMAP_ERR_STATE, "The mapping has not been computed; call computeMapping() first.");
+    if (dims < 1)
+      throw MapError(RBFMAP_ERR_INVALID, "data dimension has to be positive");
+    const ShardGroup &g = m->group();
+    if (g.active() && !g.connected() && m->mapResultIsPartial())
+      throw MapError(RBFMAP_ERR_UNSUPPORTED, "a group without communicator cannot complete the result slices; use rbfmap_map.");
+    cudaStream_t     s = m->stream();
+    AllocStreamScope allocScope(s);
+    const int64_t    nIn = m->nInput() * dims, nOutV = m->nOutput();
+    const int64_t    sliceV = g.connected() ? g.sliceOf(nOutV) : nOutV; // output vertices per rank
+    const int64_t    b = std::min(nOutV, sliceV * (g.connected() ? g.rank : 0)), e = std::min(nOutV, b + sliceV);
+    const int64_t    nOut = nOutV * dims, nOutPad = (g.connected() ? sliceV * g.world : nOutV) * dims;
+    const int64_t    nInPad = std::max<int64_t>(g.padded(nIn), 1);
+    if (h->dIn.n < static_cast<size_t>(nInPad))
+      h->dIn.alloc(nInPad);
+    if (h->dOut.n < static_cast<size_t>(std::max<int64_t>(nOutPad, 1)))
+      h->dOut.alloc(std::max<int64_t>(nOutPad, 1));
+    m->uploadReplicated(h->dIn.p, in, nIn, s);
+    mapDeviceImpl(h, 0, h->dIn.p, dims, h->dOut.p);
+    if (g.connected() && m->mapResultIsPartial()) { // every rank contributes its owned vertices; the slices are summed over NVLink
+      if (nOutPad > nOut)
+        RBF_CUDA(cudaMemsetAsync(h->dOut.p + nOut, 0, static_cast<size_t>(nOutPad - nOut) * sizeof(double), s));
+      g.reduceScatterSumInPlace(h->dOut.p, sliceV * dims, s);
+    }
+    if (e > b)
+      RBF_CUDA(cudaMemcpyAsync(out + b * dims, h->dOut.p + b * dims, static_cast<size_t>(e - b) * dims * sizeof(double), cudaMemcpyDeviceToHost, s));
+    RBF_CUDA(cudaStreamSynchronize(s));
+    *begin = b;
+    *end   = e;
+  });
+}
+
 int rbfmap_map(rbfmap_handle *h, const double *in, int dims, double *out) { return mapHostImpl(h, 0, in, dims, out); }
 int rbfmap_map_consistent(rbfmap_handle *h, const double *in, int dims, double *out) { return mapHostImpl(h, 1, in, dims, out); }
 int rbfmap_map_conservative(rbfmap_handle *h, const double *in, int dims, double *out) { return mapHostImpl(h, 2, in, dims, out); }

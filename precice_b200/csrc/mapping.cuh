@@ -52,6 +52,9 @@ public:
   // 1/world slice over PCIe and the slices are all-gathered over NVLink. `dDst` must hold group().padded(count) doubles.
   // Enqueued on `s`; the host buffer may be reused after `s` has been synchronised.
   void uploadReplicated(double *dDst, const double *hSrc, int64_t count, cudaStream_t s) const;
+  // true if map() leaves on this rank only a part of the result and the complete result is the sum over the ranks of the
+  // group (rbf-pum-direct, duplicate shard mode); false if every rank holds the complete result
+  virtual bool mapResultIsPartial() const { return false; }
 
   // ---- re-partitioning hooks (Mapping::tagMeshFirstRound / tagMeshSecondRound, Mapping.hpp:179-182), host pointers ----
   // Marks (tags[i] = 1) the vertices of the REMOTE mesh - Mapping::input() for consistent, Mapping::output() for

@@ -30,6 +30,7 @@ const NcclApi &ncclApi()
     api.CommDestroy    = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
     api.AllReduce      = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
     api.AllGather      = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
+    api.ReduceScatter  = reinterpret_cast<decltype(api.ReduceScatter)>(sym("ncclReduceScatter"));
     api.GroupStart     = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
     api.GroupEnd       = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
     api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));

@@ -17,6 +17,7 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t)                                                                               = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t)        = nullptr;
   ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t)                     = nullptr;
+  ncclResult_t (*ReduceScatter)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t)    = nullptr;
   ncclResult_t (*GroupStart)()                                                                                          = nullptr;
   ncclResult_t (*GroupEnd)()                                                                                            = nullptr;
   const char *(*GetErrorString)(ncclResult_t)                                                                           = nullptr;
@@ -95,6 +96,13 @@ struct ShardGroup {
   {
     if (connected())
       RBF_NCCL(ncclApi().GroupEnd());
+  }
+  // v holds world * slice elements on every rank; afterwards the slice [rank * slice, (rank + 1) * slice) of v is the sum
+  // over the ranks (in place), the other slices are unspecified
+  void reduceScatterSumInPlace(double *v, int64_t slice, cudaStream_t s) const
+  {
+    if (connected() && slice > 0)
+      RBF_NCCL(ncclApi().ReduceScatter(v, v + rank * slice, static_cast<size_t>(slice), ncclDouble, ncclSum, comm, s));
   }
   // every rank holds its slice [rank * slice, (rank + 1) * slice) of v (padded(count) elements); afterwards all of v
   void allGatherInPlace(double *v, int64_t slice, cudaStream_t s) const

@@ -192,6 +192,7 @@ private:
   void selectClusters();
   bool exchangeMode() const { return _group.active() && (_cfg.shard_mode == RBFMAP_SHARD_EXCHANGE || isConservative()); }
   bool duplicateMode() const { return _group.active() && !exchangeMode(); }
+  bool mapResultIsPartial() const override { return duplicateMode(); }
 
   DevBuf<double>  _inXyz, _outXyz; // solver-side inMesh / outMesh
   int64_t         _nIn = 0, _nOut = 0;

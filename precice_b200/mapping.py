@@ -119,6 +119,25 @@ class _Mapping:
         """Mapping::map(Sample, VectorXd&): dispatch on the constraint (Mapping.cpp:158-173)."""
         return self._map(self._L.rbfmap_map, values, dims, out)
 
+    def mapSliced(self, values, dims=1, out=None):
+        """rbfmap_map_sliced: map() on a sharded mapping, every rank reads back only its slice of the output vertices.
+        Returns (out, begin, end): `out` is a full-size host array of which [begin * dims, end * dims) has been written."""
+        b, e = C.c_int64(0), C.c_int64(0)
+        if _is_torch(values):
+            import torch
+            v = values.contiguous()
+            assert not v.is_cuda and v.numel() == self._n_input * dims
+            if out is None:
+                out = torch.zeros(self._n_output * dims, dtype=torch.float64)
+            self._check(self._L.rbfmap_map_sliced(self._h, v.data_ptr(), dims, out.data_ptr(), C.byref(b), C.byref(e)))
+            return out, b.value, e.value
+        v = np.ascontiguousarray(np.asarray(values, dtype=np.float64).reshape(-1))
+        assert v.size == self._n_input * dims, (v.size, self._n_input, dims)
+        if out is None:
+            out = np.zeros(self._n_output * dims)
+        self._check(self._L.rbfmap_map_sliced(self._h, v.ctypes.data, dims, out.ctypes.data, C.byref(b), C.byref(e)))
+        return out, b.value, e.value
+
     def mapBatch(self, samples, dims):
         """Maps several samples (time stamples / data of one mesh, DataContext.cpp:110-171) in one call; returns one array per
         sample, equal to [self.map(s, d) for s, d in zip(samples, dims)]."""

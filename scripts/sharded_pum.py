@@ -83,6 +83,18 @@ for constraint in ("consistent", "conservative"):
                 if where == "host":
                     m.computeMapping(inp, out)
                     res = m.map(vals, dims)
+                    # rbfmap_map_sliced: every rank reads back its slice of the complete result; the slices tile the result
+                    part, b, e = m.mapSliced(vals, dims, out=np.full(ref.size, np.nan))
+                    untouched = np.ones(ref.size, bool)
+                    untouched[b * dims:e * dims] = False
+                    if not np.all(np.isnan(part[untouched])):
+                        failures.append(f"{constraint}/{mode}/dims={dims}: mapSliced wrote outside its slice")
+                    pieces = [None] * world
+                    dist.all_gather_object(pieces, (b, e, part[b * dims:e * dims]))
+                    tiled = np.concatenate([p[2] for p in sorted(pieces, key=lambda p: p[0])])
+                    es = rel_l2(tiled, ref) if tiled.size == ref.size else float("inf")
+                    if es > TOL:
+                        failures.append(f"{constraint}/{mode}/dims={dims}: mapSliced differs from the single-device result by {es:.2e}")
                 else:
                     ti, to = torch.from_numpy(inp).to(dev), torch.from_numpy(out).to(dev)
                     tv = torch.from_numpy(np.ascontiguousarray(vals)).to(dev)

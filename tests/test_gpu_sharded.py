@@ -145,6 +145,25 @@ def test_group_without_communicator_is_limited_to_duplicate_consistent(pb):
         m.distributedInit(None, 0, 2)
 
 
+def test_map_sliced_on_one_device_and_without_communicator(pb):
+    """rbfmap_map_sliced: on a single device the slice is the whole result; a group without communicator cannot complete
+    the slices of a duplicate-mode mapping."""
+    n, vpc = 3000, 30
+    inp, out = _meshes(n)
+    vals = _field(inp, 3)
+    args = ("consistent", 3, "compact-polynomial-c6", _support(n, vpc, 3), "separate", vpc, 0.15, True)
+    m = pb.PartitionOfUnityMapping(*args)
+    m.computeMapping(inp, out)
+    res, b, e = m.mapSliced(vals, 3)
+    assert (b, e) == (0, out.shape[0]) and refcases.rel_l2(res, m.map(vals, 3)) <= 1e-14  # the blend uses atomics
+    v = pb.PartitionOfUnityMapping(*args)
+    v.distributedInit(None, 1, 2)
+    v.computeMapping(inp, out)
+    with pytest.raises(pb.MappingError) as err:
+        v.mapSliced(vals, 3)
+    assert err.value.status == "UNSUPPORTED"
+
+
 def _torchrun(nproc, *script_args, timeout=600):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr", "127.0.0.1",
            "--master-port", "29541", os.path.join(ROOT, "scripts", "sharded_pum.py"), *script_args]
