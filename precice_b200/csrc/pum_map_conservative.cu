@@ -10,10 +10,18 @@
 namespace rbfmap {
 namespace {
 
+#ifndef RBF_CONS_BATCH
+#define RBF_CONS_BATCH 4
+#endif
+#ifndef RBF_CONS_MINBLOCKS
+#define RBF_CONS_MINBLOCKS 12
+#endif
+constexpr int kConsMinBlocks = RBF_CONS_MINBLOCKS; // resident clusters per SM the 64-thread kernels are compiled for
+
 // STORED: execution-mode minimal-compute, A is read from args.eval (pum_eval.cu; lanes = in-vertices: entry (i, j) at
 // evalOff[c] + i * ld + j) instead of being re-evaluated
 template <int KIND, int NC, int NT, bool STAGE_M, bool DIM3, bool STORED = false>
-__global__ void __launch_bounds__(NT) pumMapConservativeKernel(PumSolveArgs args, const int *__restrict__ list, const double *__restrict__ in, int dims, int c0,
+__global__ void __launch_bounds__(NT, NT == 64 ? kConsMinBlocks : 1) pumMapConservativeKernel(PumSolveArgs args, const int *__restrict__ list, const double *__restrict__ in, int dims, int c0,
                                                                double *__restrict__ out)
 {
   constexpr int LDV = TileLd<NC>::value;
@@ -129,9 +137,32 @@ __global__ void __launch_bounds__(NT) pumMapConservativeKernel(PumSolveArgs args
             for (int cc = 0; cc < NC; ++cc)
               acc[cc] = fma(a, op[3 + cc], acc[cc]);
           }
-        } else
-#pragma unroll 2
-        for (int oo = 0; oo < chunk; ++oo, op += LDV) {
+        } else {
+          // four out-vertices side by side (pairBasisBatch: the dependent FP64 chain of one evaluation uses a fraction of the pipe)
+          constexpr int kBatch = RBF_CONS_BATCH;
+          int           oo     = 0;
+          for (; oo + kBatch <= chunk; oo += kBatch, op += kBatch * LDV) {
+            double bx[kBatch], by[kBatch], bz[kBatch], cf[kBatch][NC], phi[kBatch];
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+              const double2 xy = *reinterpret_cast<const double2 *>(op + u * LDV);
+              const double2 zu = *reinterpret_cast<const double2 *>(op + u * LDV + 2);
+              bx[u] = xy.x, by[u] = xy.y, bz[u] = zu.x, cf[u][0] = zu.y;
+              if (NC > 1) {
+                const double2 u12 = *reinterpret_cast<const double2 *>(op + u * LDV + 4);
+                cf[u][1]          = u12.x;
+                if (NC > 2)
+                  cf[u][2] = u12.y;
+              }
+            }
+            pairBasisBatch<KIND, DIM3, kBatch>(xj, yj, zj, bx, by, bz, rbf, invR2, phi);
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u)
+#pragma unroll
+              for (int cc = 0; cc < NC; ++cc)
+                acc[cc] = fma(phi[u], cf[u][cc], acc[cc]);
+          }
+        for (; oo < chunk; ++oo, op += LDV) {
           const double2 xy  = *reinterpret_cast<const double2 *>(op);
           const double2 zu  = *reinterpret_cast<const double2 *>(op + 2);
           const double  phi = pairBasis<KIND, DIM3>(xy.x, xy.y, zu.x, xj, yj, zj, rbf, invR2);
@@ -142,6 +173,7 @@ __global__ void __launch_bounds__(NT) pumMapConservativeKernel(PumSolveArgs args
             if (NC > 2)
               acc[2] = fma(phi, u12.y, acc[2]);
           }
+        }
         }
 #pragma unroll
         for (int cc = 0; cc < NC; ++cc)
