@@ -14,7 +14,7 @@ namespace {
 #define RBF_CONS_BATCH 4
 #endif
 #ifndef RBF_CONS_MINBLOCKS
-#define RBF_CONS_MINBLOCKS 12
+#define RBF_CONS_MINBLOCKS 14
 #endif
 constexpr int kConsMinBlocks = RBF_CONS_MINBLOCKS; // resident clusters per SM the 64-thread kernels are compiled for
 
