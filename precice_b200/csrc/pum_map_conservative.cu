@@ -21,26 +21,27 @@ constexpr int kConsMinBlocks = RBF_CONS_MINBLOCKS; // resident clusters per SM t
 // STORED: execution-mode minimal-compute, A is read from args.eval (pum_eval.cu; lanes = in-vertices: entry (i, j) at
 // evalOff[c] + i * ld + j) instead of being re-evaluated
 template <int KIND, int NC, int NT, bool STAGE_M, bool DIM3, bool STORED = false>
-__global__ void __launch_bounds__(NT, NT == 64 ? kConsMinBlocks : 1) pumMapConservativeKernel(PumSolveArgs args, const int *__restrict__ list, const double *__restrict__ in, int dims, int c0,
+__global__ void __launch_bounds__(NT, NT == 64 ? kConsMinBlocks : 1) pumMapConservativeKernel(PumSolveArgs args, const PumEntry *__restrict__ list, const double *__restrict__ in, int dims, int c0,
                                                                double *__restrict__ out)
 {
   constexpr int LDV = TileLd<NC>::value;
   extern __shared__ __align__(16) double dyn[];
   __shared__ __align__(8) unsigned long long mbar;
 
-  const int c   = list[blockIdx.x];
-  const int n   = args.nIn[c];
-  const int m   = args.nOut[c];
+  const PumEntry en = list[blockIdx.x]; // sizes and offsets in one record: no list -> sizes / offsets -> data chain
+  const int c   = en.c;
+  const int n   = en.n;
+  const int m   = en.m;
   const int tid = threadIdx.x;
   // completeJustInTimeMapping (PartitionOfUnityMapping.hpp:411-422): Au and epsilon come from the cache
   // (SphericalVertexCluster::evaluateConservativeCache :242-253, RadialBasisFctSolver::evaluateConservativeCache :562-573)
   const bool fromCache = args.cacheAu != nullptr;
   if (m == 0 && !fromCache)
     return;
-  const long long inOffC = args.inOff[c];
+  const long long inOffC = en.inOff;
   const int      *ids  = args.inIds + inOffC;
-  const int      *oids = args.outIds + args.outOff[c];
-  const double   *mg   = args.mat + args.matOff[c];
+  const int      *oids = args.outIds + en.outOff;
+  const double   *mg   = args.mat + en.matOff;
   const RbfParams rbf  = args.rbf;
   const double    cx = args.centers[3 * c], cy = args.centers[3 * c + 1], cz = args.centers[3 * c + 2];
   const double    rinv = 1.0 / args.radius;
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(NT, NT == 64 ? kConsMinBlocks : 1) pumMapConse
     const int o = o0 + tid;
     if (o < m) {
       const long long gid = oids[o];
-      const double4   rec = args.outRec[args.outOff[c] + o]; // x, y, z, normalised weight
+      const double4   rec = args.outRec[en.outOff + o]; // x, y, z, normalised weight
       const double    x = rec.x, y = rec.y, z = rec.z;
       ot[tid * LDV]     = x;
       ot[tid * LDV + 1] = y;
@@ -293,7 +294,7 @@ __global__ void __launch_bounds__(NT, NT == 64 ? kConsMinBlocks : 1) pumMapConse
 }
 
 template <int KIND, int NC, int NT, bool STAGE_M>
-void launchConservative(const PumSolveArgs &a, const int *list, int64_t count, int maxN, const double *in, int dims, int c0, double *out, cudaStream_t s)
+void launchConservative(const PumSolveArgs &a, const PumEntry *list, int64_t count, int maxN, const double *in, int dims, int c0, double *out, cudaStream_t s)
 {
   const size_t tri = STAGE_M ? static_cast<size_t>(pumMatSize(maxN, a.inverse)) : 0;
   const size_t sm  = (tri + static_cast<size_t>(TileLd<NC>::value) * (maxN + NT) + 16 * (NT / 32)) * sizeof(double);
@@ -313,7 +314,7 @@ void launchConservative(const PumSolveArgs &a, const int *list, int64_t count, i
 }
 
 template <int KIND, int NC>
-void bucketConservative(const PumSolveArgs &a, int bucket, const int *list, int64_t count, int maxN, const double *in, int dims, int c0, double *out, cudaStream_t s)
+void bucketConservative(const PumSolveArgs &a, int bucket, const PumEntry *list, int64_t count, int maxN, const double *in, int dims, int c0, double *out, cudaStream_t s)
 {
   if (bucket < 8)
     launchConservative<KIND, NC, 64, true>(a, list, count, maxN, in, dims, c0, out, s);
@@ -334,7 +335,7 @@ void dispatchConservative(const PumSolveArgs &a, const PumBuckets &bk, const dou
       const int nc = std::min(3, dims - c0);
       // one launch per group of cluster sizes (see pumForSizeGroups)
       pumForSizeGroups(bk, b, b < 8 ? 2 : 4, [&](int64_t first, int64_t cnt, int maxN) {
-        const int *list = bk.order.p + first;
+        const PumEntry *list = bk.entries.p + first;
         if (nc == 1)
           bucketConservative<KIND, 1>(a, b, list, cnt, maxN, in, dims, c0, out, s);
         else if (nc == 2)
