@@ -142,6 +142,7 @@ public:
     // PartitionOfUnityMapping.hpp:593-600
     _inXyz.release();
     _outXyz.release();
+    _inPtr = _outPtr = nullptr;
     _centers.release();
     _mem = PumMembership();
     _poly.release();
@@ -194,7 +195,11 @@ private:
   bool duplicateMode() const { return _group.active() && !exchangeMode(); }
   bool mapResultIsPartial() const override { return duplicateMode(); }
 
-  DevBuf<double>  _inXyz, _outXyz; // solver-side inMesh / outMesh
+  DevBuf<double>  _inXyz, _outXyz; // solver-side inMesh / outMesh (owned copies: host-pointer and just-in-time mappings)
+  // what computeMapping reads: the owned copies, or - device-pointer entry - the caller's buffers themselves (the call is
+  // synchronous and nothing refers to the meshes afterwards: the map kernels read the cluster-ordered records), which
+  // saves a 480 MB device-to-device copy per computeMapping at 10M; null outside computeMapping in that case
+  const double *_inPtr = nullptr, *_outPtr = nullptr;
   int64_t         _nIn = 0, _nOut = 0;
   double          _radius    = 0.0;
   int64_t         _nClusters = 0; // clusters this rank processes (all of them unless the mapping is sharded)
@@ -233,8 +238,8 @@ PumSolveArgs PumMapping::solveArgs() const
   a.rbf     = _rbf;
   a.dim     = _cfg.dimensions;
   a.radius  = _radius;
-  a.inXyz   = _inXyz.p;
-  a.outXyz  = _outXyz.p;
+  a.inXyz   = _inPtr;
+  a.outXyz  = _outPtr;
   a.centers = _centers.p;
   a.nIn     = _mem.nIn.p;
   a.nOut    = _mem.nOut.p;
@@ -275,7 +280,8 @@ double PumMapping::estimateClusterRadius(const double *dXyz, int64_t nXyz, const
   }
   const int        nProbes = static_cast<int>(probes.size() / 3);
   std::vector<int> samples(nProbes);
-  nearestVertices(dXyz, nXyz, probes.data(), nProbes, samples.data(), _stream);
+  std::vector<double> sampleXyz(3 * static_cast<size_t>(nProbes));
+  nearestVertices(dXyz, nXyz, probes.data(), nProbes, samples.data(), _stream, sampleXyz.data());
 
   // starting radius for the k-nearest search from the mean density of the bounding box
   double vol  = 1.0;
@@ -287,7 +293,7 @@ double PumMapping::estimateClusterRadius(const double *dXyz, int64_t nXyz, const
     }
   const double guess = live > 0 ? 0.8 * std::pow(vol * static_cast<double>(_cfg.vertices_per_cluster) / static_cast<double>(nXyz), 1.0 / live) : 1.0;
   std::vector<double> radii(nProbes);
-  kthNeighbourDistance(dXyz, nXyz, samples.data(), nProbes, static_cast<int>(_cfg.vertices_per_cluster), guess, radii.data(), _stream);
+  kthNeighbourDistance(dXyz, nXyz, samples.data(), nProbes, static_cast<int>(_cfg.vertices_per_cluster), guess, radii.data(), _stream, sampleXyz.data());
   const size_t middle = radii.size() / 2;
   std::nth_element(radii.begin(), radii.begin() + middle, radii.end());
   return radii[middle];
@@ -314,7 +320,7 @@ void PumMapping::chooseSlab(const double bbMin[3], const double bbMax[3], const 
   } else {
     constexpr int kBins    = 4096;
     const double  binWidth = edge / kBins;
-    const auto    hist     = pumVertexHistogram(_inXyz.p, _nIn, axis, bbMin[axis], binWidth, kBins, _stream);
+    const auto    hist     = pumVertexHistogram(_inPtr, _nIn, axis, bbMin[axis], binWidth, kBins, _stream);
     // duplicate mode: a rank also processes the clusters within one radius of its slab
     const int        haloBins = exchangeMode() ? 0 : static_cast<int>(std::ceil(_radius / binWidth)) + 1;
     std::vector<int> cuts(world + 1);
@@ -378,11 +384,30 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
     throw MapError(RBFMAP_ERR_UNSUPPORTED, "mesh too large for 32-bit vertex IDs");
   EventTimer replicated(_stream);
   replicated.start();
-  // sharded mapping: every rank uploads 1/world of each mesh over PCIe, the slices are all-gathered over NVLink
-  _inXyz.alloc(std::max<int64_t>(_group.padded(3 * _nIn), 1));
-  _outXyz.alloc(std::max<int64_t>(_group.padded(3 * _nOut), 1));
+  const bool borrow = kind == cudaMemcpyDeviceToDevice && !_jit; // device-resident caller: read its buffers in place
+  struct Unborrow {
+    PumMapping *m;
+    bool        on;
+    ~Unborrow()
+    {
+      if (on)
+        m->_inPtr = m->_outPtr = nullptr;
+    }
+  } unborrow{this, borrow};
+  if (borrow) {
+    _inXyz.release();
+    _outXyz.release();
+    _inPtr  = srcIn;
+    _outPtr = srcOut;
+  } else {
+    // sharded mapping: every rank uploads 1/world of each mesh over PCIe, the slices are all-gathered over NVLink
+    _inXyz.alloc(std::max<int64_t>(_group.padded(3 * _nIn), 1));
+    _outXyz.alloc(std::max<int64_t>(_group.padded(3 * _nOut), 1));
+    _inPtr  = _inXyz.p;
+    _outPtr = _outXyz.p;
+  }
   trace.phase("alloc meshes");
-  if (_nIn > 0) {
+  if (_nIn > 0 && !borrow) {
     if (kind == cudaMemcpyDeviceToDevice)
       deviceCopy(_inXyz.p, srcIn, 3 * _nIn, _stream);
     else
@@ -399,7 +424,7 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
         cudaStreamSynchronize(s);
     }
   } outCopy;
-  if (_nOut > 0) {
+  if (_nOut > 0 && !borrow) {
     if (kind == cudaMemcpyHostToDevice) {
       if (!_copyStream) {
         RBF_CUDA(cudaStreamCreateWithFlags(&_copyStream, cudaStreamNonBlocking));
@@ -451,7 +476,7 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
   const int dim = _cfg.dimensions;
   double    bbMin[3], bbMax[3], obMin[3], obMax[3];
   trace.phase("alloc + copy");
-  computeBounds(_inXyz.p, _nIn, bbMin, bbMax, _stream); // :334 (bounds of the inMesh)
+  computeBounds(_inPtr, _nIn, bbMin, bbMax, _stream); // :334 (bounds of the inMesh)
   trace.phase("bounds");
   auto edge = [&](int d) { return std::abs(bbMax[d] - bbMin[d]); };
 
@@ -473,16 +498,16 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
     RBF_CUDA(cudaMemcpyAsync(_centers.p, c, sizeof(c), cudaMemcpyHostToDevice, _stream));
     RBF_CUDA(cudaStreamSynchronize(_stream));
     _nClusters = 1;
-    inGrid.build(_inXyz.p, _nIn, bbMin, bbMax, 0.5 * _radius, _stream); // half-radius cells, 5x5x5 neighbourhoods (forCandidatesWarp<2>)
+    inGrid.build(_inPtr, _nIn, bbMin, bbMax, 0.5 * _radius, _stream); // half-radius cells, 5x5x5 neighbourhoods (forCandidatesWarp<2>)
     waitForOutMesh();
     if (_nOut > 0)
-      computeBounds(_outXyz.p, _nOut, obMin, obMax, _stream);
+      computeBounds(_outPtr, _nOut, obMin, obMax, _stream);
     else
       for (int d = 0; d < 3; ++d)
         obMin[d] = bbMin[d], obMax[d] = bbMax[d];
-    outGrid.build(_outXyz.p, _nOut, obMin, obMax, 0.5 * _radius, _stream);
+    outGrid.build(_outPtr, _nOut, obMin, obMax, 0.5 * _radius, _stream);
   } else {
-    _radius = estimateClusterRadius(_inXyz.p, _nIn, bbMin, bbMax);
+    _radius = estimateClusterRadius(_inPtr, _nIn, bbMin, bbMax);
     trace.phase("estimateClusterRadius");
     if (!(_radius > 0.0))
       throw MapError(RBFMAP_ERR_SINGULAR, "rbf-pum-direct: the estimated cluster radius is zero (duplicated vertices?).");
@@ -576,14 +601,14 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
     cl.initLattice(axes, jit ? 1 : 3, _stream);
     trace.phase("lattice");
     // half-radius cells, 5x5x5 neighbourhoods (forCandidatesWarp<2>)
-    inGrid.build(_inXyz.p, _nIn, bbMin, bbMax, 0.5 * _radius, _stream, regionAxis, regionLo, regionHi);
+    inGrid.build(_inPtr, _nIn, bbMin, bbMax, 0.5 * _radius, _stream, regionAxis, regionLo, regionHi);
     waitForOutMesh();
     if (_nOut > 0)
-      computeBounds(_outXyz.p, _nOut, obMin, obMax, _stream);
+      computeBounds(_outPtr, _nOut, obMin, obMax, _stream);
     else
       for (int d = 0; d < 3; ++d)
         obMin[d] = bbMin[d], obMax[d] = bbMax[d];
-    outGrid.build(_outXyz.p, _nOut, obMin, obMax, 0.5 * _radius, _stream, regionAxis, regionLo, regionHi);
+    outGrid.build(_outPtr, _nOut, obMin, obMax, 0.5 * _radius, _stream, regionAxis, regionLo, regionHi);
     trace.phase("bin meshes");
 
     // :468-471
@@ -658,7 +683,7 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
     _group.allReduceSum(_wcount.p, _nOut, _stream);
   };
   if (_nClusters > 0) {
-    pumBuildMembership(_centers.p, _nClusters, inGrid, outGrid, _radius, _mem, _scratch, _wsum.p, _wcount.p, _inXyz.p, _outXyz.p, _inRec, _outRec, _stream,
+    pumBuildMembership(_centers.p, _nClusters, inGrid, outGrid, _radius, _mem, _scratch, _wsum.p, _wcount.p, _inPtr, _outPtr, _inRec, _outRec, _stream,
                        outSlab, exchangeMode() ? std::function<void()>(weightsComplete) : std::function<void()>(), _inverse);
   } else { // a rank of a sharded mapping without clusters still takes part in the collectives
     _mem = PumMembership();
@@ -670,7 +695,7 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
   // partition-of-unity weight sums (PartitionOfUnityMapping.hpp:263-276, 290-341)
   auto throwUnassignedVertex = [&](int64_t bad) {
       double v[3];
-      RBF_CUDA(cudaMemcpy(v, _outXyz.p + 3 * bad, sizeof(v), cudaMemcpyDeviceToHost));
+      RBF_CUDA(cudaMemcpy(v, _outPtr + 3 * bad, sizeof(v), cudaMemcpyDeviceToHost));
       std::ostringstream os;
       os.precision(17);
       os << "Output vertex " << v[0] << " " << v[1];
@@ -684,9 +709,9 @@ void PumMapping::computeImpl(const double *dInputXyz, int64_t nInput, const doub
       throw MapError(RBFMAP_ERR_UNASSIGNED, os.str());
   };
   if (_group.active()) {
-    pumMarkFirstUnassigned(_wsum.p, _wcount.p, _nOut, _stream, _outXyz.p, outSlab, agree.p);
+    pumMarkFirstUnassigned(_wsum.p, _wcount.p, _nOut, _stream, _outPtr, outSlab, agree.p);
   } else {
-    const int64_t bad = pumFirstUnassigned(_wsum.p, _wcount.p, _nOut, _stream, _outXyz.p);
+    const int64_t bad = pumFirstUnassigned(_wsum.p, _wcount.p, _nOut, _stream, _outPtr);
     if (bad >= 0)
       throwUnassignedVertex(bad);
   }

@@ -245,7 +245,16 @@ void computeBounds(const double *dXyz, int64_t n, double bbMin[3], double bbMax[
   }
 }
 
-void nearestVertices(const double *dXyz, int64_t n, const double *probes, int nProbes, int *nearestIds, cudaStream_t s)
+namespace {
+__global__ void probeCoordsKernel(const double *__restrict__ xyz, const int *__restrict__ ids, int nProbes, double *__restrict__ out)
+{
+  const int t = threadIdx.x;
+  if (t < 3 * nProbes)
+    out[t] = xyz[3 * static_cast<long long>(ids[t / 3]) + t % 3];
+}
+} // namespace
+
+void nearestVertices(const double *dXyz, int64_t n, const double *probes, int nProbes, int *nearestIds, cudaStream_t s, double *nearestXyz)
 {
   const Probes               pr = makeProbes(probes, nProbes);
   DevBuf<unsigned long long> best;
@@ -259,19 +268,31 @@ void nearestVertices(const double *dXyz, int64_t n, const double *probes, int nP
   probeArgMinKernel<<<gridFor(n, 4), kBlock, 0, s>>>(dXyz, n, pr, best.p, ids.p);
   RBF_LAUNCHED();
   RBF_CUDA(cudaMemcpyAsync(nearestIds, ids.p, nProbes * sizeof(int), cudaMemcpyDeviceToHost, s));
+  DevBuf<double> coords;
+  if (nearestXyz && n > 0) { // the coordinates of the found vertices travel with their IDs (one synchronisation)
+    coords.alloc(3 * kMaxProbes);
+    probeCoordsKernel<<<1, 32, 0, s>>>(dXyz, ids.p, nProbes, coords.p);
+    RBF_LAUNCHED();
+    RBF_CUDA(cudaMemcpyAsync(nearestXyz, coords.p, 3 * nProbes * sizeof(double), cudaMemcpyDeviceToHost, s));
+  }
   RBF_CUDA(cudaStreamSynchronize(s));
 }
 
-void kthNeighbourDistance(const double *dXyz, int64_t n, const int *probeIds, int nProbes, int k, double guess, double *result, cudaStream_t s)
+void kthNeighbourDistance(const double *dXyz, int64_t n, const int *probeIds, int nProbes, int k, double guess, double *result, cudaStream_t s,
+                          const double *probeXyz)
 {
   k = static_cast<int>(std::min<int64_t>(k, n));
   if (k < 1)
     throw MapError(RBFMAP_ERR_INVALID, "vertices-per-cluster has to be greater zero.");
   // coordinates of the probe vertices
   std::vector<double> pts(3 * static_cast<size_t>(nProbes));
-  for (int p = 0; p < nProbes; ++p)
-    RBF_CUDA(cudaMemcpyAsync(&pts[3 * p], dXyz + 3 * static_cast<int64_t>(probeIds[p]), 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
-  RBF_CUDA(cudaStreamSynchronize(s));
+  if (probeXyz) {
+    std::copy(probeXyz, probeXyz + 3 * nProbes, pts.begin());
+  } else {
+    for (int p = 0; p < nProbes; ++p)
+      RBF_CUDA(cudaMemcpyAsync(&pts[3 * p], dXyz + 3 * static_cast<int64_t>(probeIds[p]), 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    RBF_CUDA(cudaStreamSynchronize(s));
+  }
   Probes pr = makeProbes(pts.data(), nProbes);
 
   const int      cap = std::max(4096, 8 * k);
@@ -279,7 +300,10 @@ void kthNeighbourDistance(const double *dXyz, int64_t n, const int *probeIds, in
   DevBuf<int>    counts;
   cand.alloc(static_cast<size_t>(kMaxProbes) * cap);
   counts.alloc(kMaxProbes);
-  std::vector<double> host(static_cast<size_t>(cap));
+  // the head of every probe's candidate list comes back with the counts (one synchronisation per round); the starting
+  // radius holds ~2 k vertices, longer lists are fetched separately
+  const int           head = std::min(cap, std::max(512, 4 * k));
+  std::vector<double> host(static_cast<size_t>(kMaxProbes) * head), longList;
   std::vector<char>   done(nProbes, 0);
   // every probe searches with its own radius: grow while fewer than k vertices are inside, shrink (bisect) when the
   // candidate buffer overflows
@@ -294,6 +318,7 @@ void kthNeighbourDistance(const double *dXyz, int64_t n, const int *probeIds, in
     RBF_LAUNCHED();
     int cnt[kMaxProbes];
     RBF_CUDA(cudaMemcpyAsync(cnt, counts.p, sizeof(cnt), cudaMemcpyDeviceToHost, s));
+    RBF_CUDA(cudaMemcpy2DAsync(host.data(), head * sizeof(double), cand.p, cap * sizeof(double), head * sizeof(double), nProbes, cudaMemcpyDeviceToHost, s));
     RBF_CUDA(cudaStreamSynchronize(s));
     for (int p = 0; p < nProbes; ++p) {
       if (done[p])
@@ -305,9 +330,14 @@ void kthNeighbourDistance(const double *dXyz, int64_t n, const int *probeIds, in
         lo[p]     = radius[p];
         radius[p] = std::isfinite(hi[p]) ? 0.5 * (lo[p] + hi[p]) : 2.0 * radius[p];
       } else {
-        RBF_CUDA(cudaMemcpy(host.data(), cand.p + static_cast<size_t>(p) * cap, cnt[p] * sizeof(double), cudaMemcpyDeviceToHost));
-        std::nth_element(host.begin(), host.begin() + (k - 1), host.begin() + cnt[p]);
-        result[p] = std::sqrt(host[k - 1]);
+        double *list = host.data() + static_cast<size_t>(p) * head;
+        if (cnt[p] > head) {
+          longList.resize(cnt[p]);
+          RBF_CUDA(cudaMemcpy(longList.data(), cand.p + static_cast<size_t>(p) * cap, cnt[p] * sizeof(double), cudaMemcpyDeviceToHost));
+          list = longList.data();
+        }
+        std::nth_element(list, list + (k - 1), list + cnt[p]);
+        result[p] = std::sqrt(list[k - 1]);
         done[p]   = 1;
         ++nDone;
       }

@@ -46,12 +46,13 @@ void computeBounds(const double *dXyz, int64_t n, double bbMin[3], double bbMax[
 
 // nearest vertex to each of nProbes host points: vertex ID with the smallest squared distance, ties -> lowest ID
 // (query/Index.cpp:171-182; tie-break is implementation-defined in the reference)
-void nearestVertices(const double *dXyz, int64_t n, const double *probes, int nProbes, int *nearestIds, cudaStream_t s);
+void nearestVertices(const double *dXyz, int64_t n, const double *probes, int nProbes, int *nearestIds, cudaStream_t s, double *nearestXyz = nullptr);
 
 // distance to the k-th nearest vertex (k >= 1, counting the query vertex itself) for each of nProbes
 // vertices of the mesh, i.e. max over Index::getClosestVertices (query/Index.cpp:184-195) as consumed by
 // impl/CreateClustering.hpp:259-268. `guess` is a starting search radius.
-void kthNeighbourDistance(const double *dXyz, int64_t n, const int *probeIds, int nProbes, int k, double guess, double *result, cudaStream_t s);
+void kthNeighbourDistance(const double *dXyz, int64_t n, const int *probeIds, int nProbes, int k, double guess, double *result, cudaStream_t s,
+                          const double *probeXyz = nullptr);
 
 #ifdef __CUDACC__
 __device__ __forceinline__ int cellCoordUnclamped(double p, double o, double ih, int n)
