@@ -120,6 +120,24 @@ inline BasisFunction Multiquadrics(double shape) { return {RBFMAP_MULTIQUADRICS,
 inline BasisFunction InverseMultiquadrics(double shape) { return {RBFMAP_INVERSE_MULTIQUADRICS, 0.0, shape}; }
 inline BasisFunction Gaussian(double shape, double supportRadius = 0.0) { return {RBFMAP_GAUSSIAN, supportRadius, shape}; }
 
+class Mapping;
+
+/// impl::MappingDataCache (mapping/impl/MappingDataCache.hpp:23-71): the per-data state of a just-in-time mapping, created by
+/// Mapping::initializeMappingDataCache and owned by the caller (precice/impl/ReadDataContext.cpp, WriteDataContext.cpp)
+class MappingDataCache {
+public:
+  explicit MappingDataCache(int dataDim) : _dataDim(dataDim) {}
+  MappingDataCache(const MappingDataCache &)            = delete;
+  MappingDataCache &operator=(const MappingDataCache &) = delete;
+  ~MappingDataCache() { rbfmap_cache_destroy(_c); }
+  int getDataDimensions() const { return _dataDim; }
+
+private:
+  friend class Mapping;
+  int           _dataDim;
+  rbfmap_cache *_c = nullptr;
+};
+
 /// The interface of precice::mapping::Mapping (mapping/Mapping.hpp) for the three RBF mappings, on one B200
 class Mapping {
 public:
@@ -207,6 +225,41 @@ public:
       return;
     check(rbfmap_tag_mesh_second_round(_h, remote.rawCoords(), static_cast<int64_t>(remote.nVertices()), remote.owners().data(), remote.tags().data()));
   }
+
+  // ---- just-in-time mapping (mapping/Mapping.hpp:215-289; rbf-pum-direct only, PartitionOfUnityMapping.hpp:382-476) ----
+  /// computeMapping() when the other mesh is a just-in-time mesh (mesh::MeshConfiguration::getJustInTimeMappingMesh): only
+  /// input() (consistent / read) resp. output() (conservative / write) has to be set
+  void computeMappingJustInTime()
+  {
+    const mesh::PtrMesh &m = hasConstraint(CONSERVATIVE) ? _output : _input;
+    if (!m)
+      throw Error(RBFMAP_ERR_STATE, "setMeshes() has to be called before the mapping is used.");
+    check(rbfmap_compute_mapping_just_in_time(_h, m->rawCoords(), static_cast<int64_t>(m->nVertices())));
+  }
+  /// Mapping::initializeMappingDataCache (PartitionOfUnityMapping.hpp:424-434); also resets an initialised cache
+  void initializeMappingDataCache(MappingDataCache &cache)
+  {
+    if (cache._c)
+      check(rbfmap_cache_reset(_h, cache._c));
+    else
+      check(rbfmap_cache_create(_h, cache._dataDim, &cache._c));
+  }
+  /// Mapping::updateMappingDataCache (PartitionOfUnityMapping.hpp:436-448): values of input(), dataDim per vertex
+  void updateMappingDataCache(MappingDataCache &cache, const std::vector<double> &in) { check(rbfmap_cache_update(_h, cache._c, in.data())); }
+  /// Mapping::mapConsistentAt (PartitionOfUnityMapping.hpp:450-476): coordinates = nPoints x 3 (z = 0 in 2-D),
+  /// values = nPoints x dataDim
+  void mapConsistentAt(const std::vector<std::array<double, 3>> &coordinates, MappingDataCache &cache, std::vector<double> &values)
+  {
+    values.assign(coordinates.size() * cache._dataDim, 0.0);
+    check(rbfmap_map_consistent_at(_h, cache._c, coordinates.empty() ? nullptr : coordinates.front().data(), static_cast<int64_t>(coordinates.size()), values.data()));
+  }
+  /// Mapping::mapConservativeAt (PartitionOfUnityMapping.hpp:382-409): accumulates `source` (nPoints x dataDim) into the cache
+  void mapConservativeAt(const std::vector<std::array<double, 3>> &coordinates, const std::vector<double> &source, MappingDataCache &cache)
+  {
+    check(rbfmap_map_conservative_at(_h, cache._c, coordinates.empty() ? nullptr : coordinates.front().data(), static_cast<int64_t>(coordinates.size()), source.data()));
+  }
+  /// Mapping::completeJustInTimeMapping (PartitionOfUnityMapping.hpp:411-422): adds the mapped data to `result` (dataDim x output vertices)
+  void completeJustInTimeMapping(MappingDataCache &cache, std::vector<double> &result) { check(rbfmap_complete_just_in_time_mapping(_h, cache._c, result.data())); }
 
   rbfmap_stats stats() const
   {

@@ -6,6 +6,7 @@
 //   PartitionOfUnityMappingTest.cpp:380-476  perform2DTestConservativeMapping (golden :475)
 //   PartitionOfUnityMappingTest.cpp:1102-1197 perform3DTestConsistentMappingVector (golden :1191)
 //   RadialBasisFctHelper.hpp:50-140          global mappings reproduce linear functions
+//   PartitionOfUnityMappingTest.cpp:772-937, 1311-1495 just-in-time read / write mapping (goldens :1423-1424)
 // Tolerance: relative 1e-9 like the reference (src/testing/main.cpp:84-87).
 // Build + run: tests/test_cxx_host.py (g++ -std=c++17 -Iinclude ... -lrbfmap). Prints "CXX MAPPING OK".
 #include <rbfmap_mapping.hpp>
@@ -256,6 +257,50 @@ static void scaledConsistentSurface()
   CHECK_CLOSE(integral(*inMesh, in.values), integral(*outMesh, out));
 }
 
+// PartitionOfUnityMappingTest.cpp:772-937 (read) and :1311-1495 (write): just-in-time mapping
+static void justInTime()
+{
+  const time::Sample values{1, {1, 2, 2, 1, 3, 6, 6, 3, 3, 4, 4, 3, 9, 12, 12, 9, 5, 6, 6, 5, 15, 18, 18, 15}};
+  {
+    mapping::PartitionOfUnityMapping mapping(Mapping::CONSISTENT, 3, mapping::CompactPolynomialC0(3.0), Polynomial::SEPARATE, 5, 0.265, false);
+    mapping.setMeshes(cubes3D(), nullptr); // the output mesh is a just-in-time mesh
+    mapping.computeMappingJustInTime();
+    CHECK(mapping.hasComputedMapping());
+    mapping::MappingDataCache cache(1);
+    mapping.initializeMappingDataCache(cache);
+    mapping.updateMappingDataCache(cache, values.values);
+    std::vector<double> out;
+    mapping.mapConsistentAt({{0.0, 0.0, 0.0}}, cache, out);
+    CHECK_CLOSE(out[0], 1.0);
+    mapping.mapConsistentAt({{3.5, 0.5, 0.5}, {2.5, 0.5, 1.0}}, cache, out);
+    CHECK_CLOSE(out[0], 9.0);
+    CHECK_CLOSE(out[1], 10.5);
+    std::vector<double> doubled = values.values;
+    for (double &v : doubled)
+      v *= 2.0;
+    mapping.updateMappingDataCache(cache, doubled);
+    mapping.mapConsistentAt({{0.0, 0.5, 0.5}, {0.0, 1.0, 1.0}, {1.0, 0.0, 0.0}}, cache, out);
+    CHECK_CLOSE(out[0], 4.0);
+    CHECK_CLOSE(out[1], 6.0);
+    CHECK_CLOSE(out[2], 4.0);
+  }
+  {
+    mapping::PartitionOfUnityMapping mapping(Mapping::CONSERVATIVE, 3, mapping::CompactPolynomialC2(3.0), Polynomial::SEPARATE, 5, 0.265, false);
+    auto outMesh = cubes3D();
+    mapping.setMeshes(nullptr, outMesh); // the input mesh is a just-in-time mesh
+    mapping.computeMappingJustInTime();
+    mapping::MappingDataCache cache(1);
+    mapping.initializeMappingDataCache(cache);
+    std::vector<double> result(outMesh->nVertices(), 0.0);
+    mapping.mapConservativeAt({{5.0, 0.0, 1.0}}, {4.3}, cache);
+    mapping.mapConservativeAt({{3.5, 0.5, 0.5}, {4.5, 1.0, 1.0}, {0.1, 0.0, 1.0}}, {4.3, 17.3, 5.8}, cache);
+    mapping.completeJustInTimeMapping(cache, result);
+    CHECK_CLOSE(std::accumulate(result.begin(), result.end(), 0.0), 4.3 + 4.3 + 17.3 + 5.8);
+    CHECK(close(result[6], 0.063700286667, 1e-7));  // :1423
+    CHECK(close(result[23], 9.2744883594, 1e-7));   // :1424
+  }
+}
+
 int main()
 {
   if (rbfmap_device_count() < 1) {
@@ -269,6 +314,7 @@ int main()
     errors();
     globalLinearReproduction();
     scaledConsistentSurface();
+    justInTime();
   } catch (const Error &e) {
     std::printf("FAILED: unexpected rbfmap::Error %d: %s\n", e.status, e.what());
     return 1;
