@@ -217,7 +217,9 @@ int     rbfmap_map_with_initial_guess(rbfmap_handle *h, const double *in, int di
  * device-resident callers and by bench.py's kernel-only figure. The work is enqueued on the
  * library's stream and the call returns after it completed. The library's stream is not
  * ordered behind the caller's streams: the device buffers must be completely written (the
- * producing stream synchronised or joined by an event the caller waited for) before the call. */
+ * producing stream synchronised or joined by an event the caller waited for) before the call.
+ * rbfmap_compute_mapping_device reads the meshes in place (no copy is kept: the mapping owns only what it derived from
+ * them, so the buffers may be freed or overwritten as soon as the call has returned). */
 int rbfmap_compute_mapping_device(rbfmap_handle *h, const double *d_input_xyz, int64_t n_input, const double *d_output_xyz, int64_t n_output);
 int rbfmap_map_device(rbfmap_handle *h, const double *d_in, int dims, double *d_out);
 
