@@ -1,6 +1,9 @@
 // nccl_dyn.cuh — NCCL entry points resolved at run time (dlopen), so that librbfmap.so has no link-time dependency and
-// shares the NCCL copy the host application (e.g. PyTorch) already loaded. Used only by the sharded matrix-free CG of
-// rbf-global-iterative: all-gather of the direction vector slices and all-reduce of the dot products over NVLink.
+// shares the NCCL copy the host application (e.g. PyTorch) already loaded. Used by the mappings that shard ONE mapping
+// over the GPUs of a node (rbfmap_distributed_init): rbf-pum-direct (all-gather of the uploaded mesh / value slices,
+// all-reduce of weight sums and partial blends in exchange mode, the grouped agreement on errors and cluster count,
+// reduce-scatter of the result for rbfmap_map_sliced) and the CG of rbf-global-iterative (all-gather of the direction
+// vector slices, all-reduce of the dot products), all over NVLink.
 #pragma once
 
 #include <nccl.h>
