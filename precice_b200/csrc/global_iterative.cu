@@ -217,8 +217,9 @@ __global__ void scatterInterleavedKernel(const double *__restrict__ in, long lon
 }
 
 // r = b - Ax (Ax given), p = r, rr = r.r
+// (b and r may be the same array: the residual replaces the right-hand side in place, so neither is `restrict`)
 template <int NC>
-__global__ void cgInitKernel(const double *__restrict__ b, const double *__restrict__ Ax, double *__restrict__ r, double *__restrict__ p, long long n, long long ld,
+__global__ void cgInitKernel(const double *b, const double *__restrict__ Ax, double *r, double *__restrict__ p, long long n, long long ld,
                              CgScalars *sc)
 {
   double acc[NC], accB[NC];

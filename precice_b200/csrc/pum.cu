@@ -134,7 +134,6 @@ public:
     tagInsideBox(dFilter.p, nFilter, lo, hi, 2 * _radius, hTags); // :527-532
   }
   void tagMeshSecondRound(const double *, int64_t, const unsigned char *, unsigned char *) override {} // :535-539
-  double clusterRadius() const { return _radius; }
   void mapConsistent(const double *dIn, int dims, double *dOut) override { map(false, dIn, dims, dOut); }
   void mapConservative(const double *dIn, int dims, double *dOut) override { map(true, dIn, dims, dOut); }
   void clear() override

@@ -59,7 +59,6 @@ __global__ void __launch_bounds__(32, NB <= 4 ? 20 : NB == 5 ? 16 : NB == 6 ? 14
   const int       n    = en.n;
   const int       lane = threadIdx.x;
   const int       g = lane >> 2, q = lane & 3;
-  const int      *ids   = args.inIds + en.inOff;
   const RbfParams rbf   = args.rbf;
   const double    invR2 = rbf.p1 * rbf.p1;
 

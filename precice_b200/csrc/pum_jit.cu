@@ -324,7 +324,6 @@ __global__ void __launch_bounds__(32, 16) pumEvaluateClusteredKernel(PumSolveArg
   const int       n    = args.nIn[c];
   const int       tid  = threadIdx.x;
   const long long off  = args.inOff[c];
-  const int      *ids  = args.inIds + off;
   const int      *oids = ptIds + ptOff[c];
   const RbfParams rbf  = args.rbf;
   const double    cx = args.centers[3 * c], cy = args.centers[3 * c + 1], cz = args.centers[3 * c + 2];

@@ -148,7 +148,6 @@ __global__ void polySetupKernel(PumSolveArgs a, int64_t nClusters)
     return;
   PolyRec     &rec = a.poly[c];
   const int    n   = a.nIn[c];
-  const int   *ids = a.inIds + a.inOff[c];
   // SphericalVertexCluster.hpp:178: deadAxis = vector<bool>(dim, false) -> z is inactive for 2-D meshes
   int mask = a.dim == 3 ? 7 : 3;
 

@@ -3,24 +3,33 @@
 
 #include <cmath>
 
+// the helpers below are also compiled for the host, whose compiler does not know the unroll pragma
+#ifdef __CUDA_ARCH__
+#define RBF_UNROLL _Pragma("unroll")
+#define RBF_NO_UNROLL _Pragma("unroll 1")
+#else
+#define RBF_UNROLL
+#define RBF_NO_UNROLL
+#endif
+
 namespace rbfmap {
 
 // eigenvalues of a symmetric 4x4 matrix (cyclic Jacobi, everything in registers)
 __host__ __device__ inline void jacobiEigenvalues4(double a[4][4], double &evMin, double &evMax)
 {
-#pragma unroll 1
+RBF_NO_UNROLL
   for (int sweep = 0; sweep < 16; ++sweep) {
     double off = 0.0;
-#pragma unroll
+RBF_UNROLL
     for (int p = 0; p < 3; ++p)
-#pragma unroll
+RBF_UNROLL
       for (int q = p + 1; q < 4; ++q)
         off += a[p][q] * a[p][q];
     if (off == 0.0)
       break;
-#pragma unroll
+RBF_UNROLL
     for (int p = 0; p < 3; ++p)
-#pragma unroll
+RBF_UNROLL
       for (int q = p + 1; q < 4; ++q) {
         const double apq = a[p][q];
         if (fabs(apq) > 1e-300) {
@@ -32,7 +41,7 @@ __host__ __device__ inline void jacobiEigenvalues4(double a[4][4], double &evMin
           a[q][q] += t * apq;
           a[p][q] = 0.0;
           a[q][p] = 0.0;
-#pragma unroll
+RBF_UNROLL
           for (int r = 0; r < 4; ++r)
             if (r != p && r != q) {
               const double arp = a[r][p], arq = a[r][q];
