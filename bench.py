@@ -240,6 +240,7 @@ class Ctx:
         self.rank = int(os.environ.get("RANK", "0"))
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.affinity0 = os.sched_getaffinity(0)  # restored for the CPU baseline, which uses every host thread
         self.numa = bind_to_gpu_numa_node(self.local_rank)
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
@@ -853,6 +854,7 @@ def main():
         if secondary:
             line["secondary"] = secondary
         if "cpu" in legs:
+            os.sched_setaffinity(0, ctx.affinity0)  # the CPU arm gets all host cores, not only the GPU's NUMA node
             cb, ref_out, (s_in, s_out, s_vals, per) = cpu_baseline(args.ref_sample, os.cpu_count() or 1)
             # parity of the GPU path against the CPU path on the first partition of the sample, checked in the same run
             m2 = pb.PartitionOfUnityMapping("consistent", 3, BASIS, support_radius(per), "separate", VPC, OVERLAP, True,
