@@ -6,6 +6,7 @@
 //   PartitionOfUnityMappingTest.cpp:380-476  perform2DTestConservativeMapping (golden :475)
 //   PartitionOfUnityMappingTest.cpp:1102-1197 perform3DTestConsistentMappingVector (golden :1191)
 //   RadialBasisFctHelper.hpp:50-140          global mappings reproduce linear functions
+//   RadialBasisFctMappingTest.cpp:969-1034   conservative thin-plate-spline literals of the 4-rank test (union meshes)
 //   PartitionOfUnityMappingTest.cpp:772-937, 1311-1495 just-in-time read / write mapping (goldens :1423-1424)
 // Tolerance: relative 1e-9 like the reference (src/testing/main.cpp:84-87).
 // Build + run: tests/test_cxx_host.py (g++ -std=c++17 -Iinclude ... -lrbfmap). Prints "CXX MAPPING OK".
@@ -223,6 +224,30 @@ static void globalLinearReproduction()
   }
 }
 
+// RadialBasisFctMappingTest.cpp:969-1034 (DistributedConservative2DV4): the literals of the reference's 4-rank gather-scatter
+// test are those of the serial mapping between the union meshes
+static void globalConservativeGolden()
+{
+  auto inMesh = std::make_shared<mesh::Mesh>("inMesh", 2), outMesh = std::make_shared<mesh::Mesh>("outMesh", 2);
+  for (int x = 0; x < 4; ++x)
+    for (int y = 0; y < 2; ++y)
+      inMesh->createVertex({double(x), double(y)});
+  outMesh->createVertex({0.0, 1.0});
+  for (int x = 1; x < 4; ++x)
+    for (int y = 0; y < 2; ++y)
+      outMesh->createVertex({double(x), double(y)});
+  mapping::RadialBasisFctMapping mapping(Mapping::CONSERVATIVE, 2, mapping::ThinPlateSplines(), {false, false, false}, Polynomial::SEPARATE);
+  mapping.setMeshes(inMesh, outMesh);
+  mapping.computeMapping();
+  std::vector<double> out;
+  mapping.map(time::Sample{1, {1, 2, 3, 4, 5, 6, 7, 8}}, out);
+  const double expected[] = {3.1307987056295525, 4.0734031184906971, 3.0620533966233006, 4.4582564956060873,
+                             5.8784343572772633, 7.4683403859032156, 7.9287135404698859}; // :1009-1029
+  for (int i = 0; i < 7; ++i)
+    CHECK_CLOSE(out[i], expected[i]);
+  CHECK_CLOSE(std::accumulate(out.begin(), out.end(), 0.0), 36.0);
+}
+
 // Mapping.cpp:175-246: the scaled-consistent mapping preserves the surface integral of the data
 static void scaledConsistentSurface()
 {
@@ -313,6 +338,7 @@ int main()
     pumConsistentVector3D();
     errors();
     globalLinearReproduction();
+    globalConservativeGolden();
     scaledConsistentSurface();
     justInTime();
   } catch (const Error &e) {

@@ -327,6 +327,20 @@ def dead_axis_cases():
     return cases
 
 
+def distributed_cases():
+    """RadialBasisFctMappingTest.cpp:969-1034 (DistributedConservative2DV4): the reference gathers the distributed meshes
+    on rank 0, solves the global system there and scatters (RadialBasisFctMapping.hpp:116-149, 199-308), so the expected
+    values of the 4-rank test are those of the serial mapping between the unions of the rank-local meshes - full-precision
+    literals for a conservative thin-plate-spline mapping onto a smaller mesh."""
+    inp = [(0, 0), (0, 1), (1, 0), (1, 1), (2, 0), (2, 1), (3, 0), (3, 1)]
+    out = [(0, 1), (1, 0), (1, 1), (2, 0), (2, 1), (3, 0), (3, 1)]
+    golden = [3.1307987056295525, 4.0734031184906971, 3.0620533966233006, 4.4582564956060873, 5.8784343572772633,
+              7.4683403859032156, 7.9287135404698859]  # :1009-1029, sum ~36
+    return [dict(name="distributed-conservative-2d-v4",
+                 mapping=dict(constraint="conservative", dim=2, basis="thin-plate-splines", param=0.0, dead_axis=(False, False, False), polynomial="separate"),
+                 input=inp, output=out, values=[1, 2, 3, 4, 5, 6, 7, 8], dims=1, checks=list(enumerate(golden)), sum_conserved=True)]
+
+
 def run_global_case(case, make_mapping):
     m = make_mapping(**case["mapping"])
     inp, out = _f(case["input"]), _f(case["output"])

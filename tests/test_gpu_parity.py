@@ -588,6 +588,16 @@ def test_global_dead_axis_goldens(pb, case):
     refcases.run_global_case(case, lambda **kw: pb.RadialBasisFctMapping(**kw))
 
 
+DISTRIBUTED_GPU = refcases.distributed_cases()
+
+
+@pytest.mark.parametrize("case", DISTRIBUTED_GPU, ids=[c["name"] for c in DISTRIBUTED_GPU])
+def test_global_distributed_goldens(pb, case):
+    """RadialBasisFctMappingTest.cpp:969-1034: the literals of the reference's 4-rank gather-scatter test, through the C ABI
+    on the union meshes (conservative thin-plate splines, LU path, separated polynomial)."""
+    refcases.run_global_case(case, lambda **kw: pb.RadialBasisFctMapping(**kw))
+
+
 @pytest.mark.parametrize("constraint", ["consistent", "conservative"])
 @pytest.mark.parametrize("basis,param,polynomial", [("thin-plate-splines", 0.0, "on"), ("thin-plate-splines", 0.0, "separate"),
                                                     ("multiquadrics", 0.1, "on"), ("volume-splines", 0.0, "separate")])

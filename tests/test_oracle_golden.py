@@ -55,6 +55,15 @@ def test_global_dead_axis_goldens(case):
     refcases.run_global_case(case, lambda **kw: oracle.GlobalMapping(**kw))
 
 
+DISTRIBUTED = refcases.distributed_cases()
+
+
+@pytest.mark.parametrize("case", DISTRIBUTED, ids=[c["name"] for c in DISTRIBUTED])
+def test_global_distributed_goldens(case):
+    """The 4-rank gather-scatter test of the reference, as the serial mapping of the union meshes (literals at 1e-9)."""
+    refcases.run_global_case(case, lambda **kw: oracle.GlobalMapping(**kw))
+
+
 # ---------------------------------------------------------------------------------------------- just-in-time mapping
 def _jit_boxes():
     def box(x0):
