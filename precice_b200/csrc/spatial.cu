@@ -37,32 +37,38 @@ __global__ void copyScalarKernel(const double *__restrict__ src, double *__restr
 }
 
 // ------------------------------------------------------------------ bounds
-__global__ void boundsKernel(const double *__restrict__ xyz, int64_t n, unsigned long long *__restrict__ keys /*6: min xyz, max xyz*/)
+// The coordinates are read as one flat array of 3 n doubles with a stride that is a multiple of 3 (192 threads per block):
+// every thread stays on one axis and a warp reads 256 consecutive bytes per load, instead of three loads 24 bytes apart
+// per vertex. Min / max are combined per block in shared memory (ordered-integer atomics) before the six global atomics.
+constexpr int kBoundsBlock = 192;
+__global__ void __launch_bounds__(kBoundsBlock) boundsKernel(const double *__restrict__ xyz, int64_t n, unsigned long long *__restrict__ keys /*6: min xyz, max xyz*/)
 {
-  double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      const double v = xyz[3 * i + d];
-      lo[d]          = fmin(lo[d], v);
-      hi[d]          = fmax(hi[d], v);
-    }
+  __shared__ unsigned long long blockKeys[6];
+  if (threadIdx.x < 6)
+    blockKeys[threadIdx.x] = threadIdx.x < 3 ? ~0ull : 0ull;
+  __syncthreads();
+  const int64_t total  = 3 * n;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * kBoundsBlock; // multiple of 3
+  double        lo = DBL_MAX, hi = -DBL_MAX;
+  int64_t       e = blockIdx.x * static_cast<int64_t>(kBoundsBlock) + threadIdx.x;
+  for (; e + 3 * stride < total; e += 4 * stride) { // four independent loads in flight
+    const double v0 = xyz[e], v1 = xyz[e + stride], v2 = xyz[e + 2 * stride], v3 = xyz[e + 3 * stride];
+    lo = fmin(fmin(lo, v0), fmin(fmin(v1, v2), v3));
+    hi = fmax(fmax(hi, v0), fmax(fmax(v1, v2), v3));
   }
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      lo[d] = fmin(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
-      hi[d] = fmax(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
-    }
+  for (; e < total; e += stride) {
+    const double v = xyz[e];
+    lo = fmin(lo, v);
+    hi = fmax(hi, v);
   }
-  if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      atomicMin(&keys[d], encodeOrdered(lo[d]));
-      atomicMax(&keys[3 + d], encodeOrdered(hi[d]));
-    }
-  }
+  const int d = threadIdx.x % 3; // kBoundsBlock and the stride are multiples of 3: the axis of every element this thread saw
+  atomicMin(&blockKeys[d], encodeOrdered(lo)); // (DBL_MAX, -DBL_MAX) for a thread without elements, like an empty mesh
+  atomicMax(&blockKeys[3 + d], encodeOrdered(hi));
+  __syncthreads();
+  if (threadIdx.x < 3)
+    atomicMin(&keys[threadIdx.x], blockKeys[threadIdx.x]);
+  else if (threadIdx.x < 6)
+    atomicMax(&keys[threadIdx.x], blockKeys[threadIdx.x]);
 }
 
 // ------------------------------------------------------------------ nearest vertex to a few probe points
@@ -234,7 +240,9 @@ void computeBounds(const double *dXyz, int64_t n, double bbMin[3], double bbMax[
     init[3 + d] = 0ull;
   }
   RBF_CUDA(cudaMemcpyAsync(keys.p, init, sizeof(init), cudaMemcpyHostToDevice, s));
-  boundsKernel<<<gridFor(n, 4), kBlock, 0, s>>>(dXyz, n, keys.p);
+  const int64_t wantBlocks = (3 * n + 8 * kBoundsBlock - 1) / (8 * kBoundsBlock);
+  const int     grid       = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(wantBlocks, static_cast<int64_t>(smCount()) * 10)));
+  boundsKernel<<<grid, kBoundsBlock, 0, s>>>(dXyz, n, keys.p);
   RBF_LAUNCHED();
   unsigned long long out[6];
   RBF_CUDA(cudaMemcpyAsync(out, keys.p, sizeof(out), cudaMemcpyDeviceToHost, s));
