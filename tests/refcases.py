@@ -341,6 +341,46 @@ def distributed_cases():
                  input=inp, output=out, values=[1, 2, 3, 4, 5, 6, 7, 8], dims=1, checks=list(enumerate(golden)), sum_conserved=True)]
 
 
+def gaussian_integration_cases():
+    """tests/serial/mapping-rbf-gaussian (helpers.cpp:12-190 + the four XML files): rbf-global-direct, Gaussian given by a
+    support radius or the equivalent shape parameter (MappingConfiguration.cpp:512-521: shape = sqrt(-ln 1e-9) / support),
+    polynomial separate, z-dead, MeshOne (12 vertices at z = 0.3) -> MeshTwo (3 vertices). Each check carries the relative
+    tolerance of the reference's BOOST_TEST (the scalar cases are badly conditioned: "Eigen 3.3.7 ... slightly different")."""
+    import math
+    z = 0.3
+    one = [(0, 0, z), (1, 0, z), (1, 1, z), (0, 1, z), (2, 0, z), (3, 0, z), (3, 1, z), (2, 1, z), (4, 0, z), (5, 0, z), (5, 1, z), (4, 1, z)]
+    two = [(0, 0, z), (0.5, 0.5, z), (3.5, 0.5, z)]
+    cut = math.sqrt(-math.log(1e-9))
+
+    def mapping(constraint, shape):
+        return dict(constraint=constraint, dim=3, basis="gaussian", param=shape, dead_axis=(False, False, True), polynomial="separate")
+
+    def linear(mesh):  # helpers.cpp:55-68
+        return [0.1 * sum(v) + c for v in mesh for c in (0, 1, 2)]
+
+    cases = []
+    squares = [float((i + 1) ** 2) for i in range(12)]  # helpers.cpp:125-131
+    for name, shape in (("shape-parameter", 2.2761406940777196), ("support-radius", cut / 2.0)):
+        cases.append(dict(name=f"gaussian-integration-{name}", mapping=mapping("consistent", shape), input=one, output=two, values=squares, dims=1,
+                          checks=[(0, 1.0000000014191541, 1e-8), (1, 7.30892688709867, 3e-2), (2, 77.5938805368033, 2e-3)]))
+    cases.append(dict(name="gaussian-integration-vectorial-consistent", mapping=mapping("consistent", cut / 100.0), input=one, output=two,
+                      values=linear(one), dims=3, checks=[(i, v, 1e-5) for i, v in enumerate(linear(two))]))
+    cons = [-0.6, -0.6, -0.6, 0.853333, 4.85333, 8.85333, 3.70667, 11.7067, 19.7067]  # helpers.cpp:103
+    cases.append(dict(name="gaussian-integration-vectorial-conservative", mapping=mapping("conservative", cut / 100.0), input=one, output=two,
+                      values=linear(one), dims=3, checks=[(i, v, 1e-5) for i, v in enumerate(cons)]))
+    return cases
+
+
+def run_integration_case(case, make_mapping):
+    """Checks with a relative tolerance per value, boost::test_tools::tolerance style."""
+    m = make_mapping(**case["mapping"])
+    m.compute_mapping(_f(case["input"]), _f(case["output"]))
+    res = np.asarray(m.map(np.asarray(case["values"], dtype=np.float64), case["dims"]))
+    for idx, exp, tol in case["checks"]:
+        assert abs(res[idx] - exp) <= tol * max(abs(res[idx]), abs(exp)), (case["name"], idx, repr(res[idx]), exp, tol)
+    return res
+
+
 def run_global_case(case, make_mapping):
     m = make_mapping(**case["mapping"])
     inp, out = _f(case["input"]), _f(case["output"])

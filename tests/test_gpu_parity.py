@@ -588,6 +588,16 @@ def test_global_dead_axis_goldens(pb, case):
     refcases.run_global_case(case, lambda **kw: pb.RadialBasisFctMapping(**kw))
 
 
+INTEGRATION_GPU = refcases.gaussian_integration_cases()
+
+
+@pytest.mark.parametrize("case", INTEGRATION_GPU, ids=[c["name"] for c in INTEGRATION_GPU])
+def test_gaussian_integration_goldens(pb, case):
+    """tests/serial/mapping-rbf-gaussian of the reference (two participants, rbf-global-direct, Gaussian, z-dead) through the
+    C ABI, at the reference's own tolerances."""
+    refcases.run_integration_case(case, lambda **kw: pb.RadialBasisFctMapping(**kw))
+
+
 DISTRIBUTED_GPU = refcases.distributed_cases()
 
 

@@ -55,6 +55,15 @@ def test_global_dead_axis_goldens(case):
     refcases.run_global_case(case, lambda **kw: oracle.GlobalMapping(**kw))
 
 
+INTEGRATION = refcases.gaussian_integration_cases()
+
+
+@pytest.mark.parametrize("case", INTEGRATION, ids=[c["name"] for c in INTEGRATION])
+def test_gaussian_integration_goldens(case):
+    """The reference's serial integration tests of the Gaussian rbf-global-direct mapping, at their own tolerances."""
+    refcases.run_integration_case(case, lambda **kw: oracle.GlobalMapping(**kw))
+
+
 DISTRIBUTED = refcases.distributed_cases()
 
 
