@@ -588,6 +588,26 @@ def test_global_dead_axis_goldens(pb, case):
     refcases.run_global_case(case, lambda **kw: pb.RadialBasisFctMapping(**kw))
 
 
+@pytest.mark.parametrize("polynomial", ["separate", "off"])
+def test_jit_read_equals_conventional_mapping(pb, polynomial):
+    """tests/serial/just-in-time-mapping/ExplicitReadPUM.cpp:66-89 through the C ABI: mapAndReadData (just-in-time) returns
+    what readData returns after a conventional mapping onto a mesh made of the same positions (BOOST_TEST at 1e-9)."""
+    grid = np.array([(i * 0.1, j * 0.1) for i in range(10) for j in range(10)], float)
+    pos = np.array([(k * 0.2 + 0.05, l * 0.8 + 0.05) for k in range(5) for l in range(2)], float)
+    n = np.arange(100, dtype=float)
+    data = [(0.5 * n, 1), (-100.0 + 0.1 * n ** 2, 1), (np.stack([0.5 * n, 0.2 * n], 1).reshape(-1), 2),
+            (np.stack([0.1 * n * n, 100 - 0.5 * n], 1).reshape(-1), 2)]
+    args = ("consistent", 2, "compact-polynomial-c6", 1.0, polynomial, 30, 0.15, False)
+    conv = pb.PartitionOfUnityMapping(*args)
+    conv.computeMapping(grid, pos)
+    jit = pb.PartitionOfUnityMapping(*args)
+    jit.computeMappingJustInTime(grid)
+    for vals, dims in data:
+        c = jit.initializeMappingDataCache(dims)
+        jit.updateMappingDataCache(c, vals)
+        assert refcases.close(np.asarray(jit.mapConsistentAt(pos, c)).reshape(-1), conv.map(vals, dims))
+
+
 INTEGRATION_GPU = refcases.gaussian_integration_cases()
 
 

@@ -55,6 +55,33 @@ def test_global_dead_axis_goldens(case):
     refcases.run_global_case(case, lambda **kw: oracle.GlobalMapping(**kw))
 
 
+def _explicit_read_pum():
+    """tests/serial/just-in-time-mapping/ExplicitReadPUM.{cpp,xml}: MeshTwo = 10 x 10 grid, ten read positions, rbf-pum-direct
+    compact-polynomial-c6 support-radius 1, vertices-per-cluster 30, project-to-input off; data of both time steps."""
+    grid = np.array([(i * 0.1, j * 0.1) for i in range(10) for j in range(10)], float)
+    pos = np.array([(k * 0.2 + 0.05, l * 0.8 + 0.05) for k in range(5) for l in range(2)], float)
+    n = np.arange(100, dtype=float)
+    data = [(0.5 * n, 1), (-100.0 + 0.1 * n ** 2, 1), (np.stack([0.5 * n, 0.2 * n], 1).reshape(-1), 2),
+            (np.stack([0.1 * n * n, 100 - 0.5 * n], 1).reshape(-1), 2)]
+    return grid, pos, data
+
+
+@pytest.mark.parametrize("polynomial", ["separate", "off"])
+def test_jit_read_equals_conventional_mapping(polynomial):
+    """ExplicitReadPUM.cpp:66-89: mapAndReadData (just-in-time) returns what readData returns after a conventional mapping
+    onto a mesh made of the same positions (BOOST_TEST at 1e-9)."""
+    grid, pos, data = _explicit_read_pum()
+    args = ("consistent", 2, "compact-polynomial-c6", 1.0, polynomial, 30, 0.15, False)
+    conv = oracle.PumMapping(*args)
+    conv.compute_mapping(grid, pos)
+    jit = oracle.PumMapping(*args)
+    jit.compute_mapping_jit(grid)
+    for vals, dims in data:
+        c = jit.initialize_cache(dims)
+        jit.update_cache(c, vals)
+        assert refcases.close(np.asarray(jit.map_consistent_at(pos, c)).reshape(-1), conv.map(vals, dims))
+
+
 INTEGRATION = refcases.gaussian_integration_cases()
 
 
