@@ -82,6 +82,34 @@ def test_jit_read_equals_conventional_mapping(polynomial):
         assert refcases.close(np.asarray(jit.map_consistent_at(pos, c)).reshape(-1), conv.map(vals, dims))
 
 
+@pytest.mark.parametrize("polynomial", ["separate", "off"])
+def test_jit_write_equals_conventional_mapping(polynomial):
+    """tests/serial/just-in-time-mapping/ExplicitWritePUM.{cpp,xml}: writeAndMapData (just-in-time, conservative, Gaussian with
+    support radius 1, vertices-per-cluster 30, project-to-input off) onto the 250-vertex grid gives what the conventional
+    conservative mapping from a mesh made of the 30 write positions gives (per-element BOOST_TEST), for the scalar and
+    3-vector data of both time steps."""
+    import math
+    grid = np.array([(i * 0.1, j * 0.2, k * 0.2) for i in range(10) for j in range(5) for k in range(5)], float)
+    pos = np.array([(k * 0.2 + 0.05, l * 0.8 + 0.05, m * 0.15 + 0.05) for k in range(5) for l in range(2) for m in range(3)], float)
+    n = np.arange(30, dtype=float)
+    data = [(0.8 * n, 1), (np.stack([12.5 * n, 12.2 * n, -12.2 * n], 1).reshape(-1), 3), (-28.0 + 0.1 * n * n, 1),
+            (np.stack([0.28 * n * n, 100 - 0.5 * n, 100 - 0.5 * n ** 3], 1).reshape(-1), 3)]
+    args = ("conservative", 3, "gaussian", math.sqrt(-math.log(1e-9)) / 1.0, polynomial, 30, 0.15, False)
+    conv = oracle.PumMapping(*args)
+    conv.compute_mapping(pos, grid)
+    jit = oracle.PumMapping(*args)
+    jit.compute_mapping_jit(grid)
+    for vals, dims in data:
+        expected = np.asarray(conv.map(vals, dims))
+        c = jit.initialize_cache(dims)
+        jit.map_conservative_at(pos, vals, c)
+        out = np.zeros(250 * dims)
+        jit.complete_just_in_time_mapping(c, out)
+        assert np.max(np.abs(out - expected)) <= 1e-9 * np.max(np.abs(expected))
+        if polynomial == "separate":  # the separated polynomial conserves the component sums
+            assert refcases.close(out.reshape(-1, dims).sum(0), vals.reshape(-1, dims).sum(0))
+
+
 INTEGRATION = refcases.gaussian_integration_cases()
 
 
