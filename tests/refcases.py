@@ -371,6 +371,17 @@ def gaussian_integration_cases():
     return cases
 
 
+def petsc_distributed_cases():
+    """PetRadialBasisFctMappingTest.cpp:850-909 (DistributedConservative2DV4 of the PETSc mapping, 4 ranks, tolerance 1e-6):
+    Gaussian(4.0), conservative, separated polynomial (the PETSc mapping's default), the meshes of distributed_cases()."""
+    inp = [(0, 0), (0, 1), (1, 0), (1, 1), (2, 0), (2, 1), (3, 0), (3, 1)]
+    out = [(0, 1), (1, 0), (1, 1), (2, 0), (2, 1), (3, 0), (3, 1)]
+    golden = [2.4285714526861519, 3.61905, 4.14286, 5.333333295, 5.85714, 7.047619, 7.571428]  # :888-905, sum ~36
+    return [dict(name="petsc-distributed-conservative-2d-v4",
+                 mapping=dict(constraint="conservative", dim=2, basis="gaussian", param=4.0, dead_axis=(False, False, False), polynomial="separate"),
+                 input=inp, output=out, values=[1, 2, 3, 4, 5, 6, 7, 8], dims=1, checks=[(i, v, 1e-6) for i, v in enumerate(golden)])]
+
+
 def run_integration_case(case, make_mapping):
     """Checks with a relative tolerance per value, boost::test_tools::tolerance style."""
     m = make_mapping(**case["mapping"])

@@ -119,6 +119,16 @@ def test_gaussian_integration_goldens(case):
     refcases.run_integration_case(case, lambda **kw: oracle.GlobalMapping(**kw))
 
 
+PETSC_DISTRIBUTED = refcases.petsc_distributed_cases()
+
+
+@pytest.mark.parametrize("case", PETSC_DISTRIBUTED, ids=[c["name"] for c in PETSC_DISTRIBUTED])
+def test_petsc_distributed_goldens(case):
+    """The literals of the PETSc mapping's 4-rank test: the converged iterative solution is the direct one (1e-6)."""
+    res = refcases.run_integration_case(case, lambda **kw: oracle.GlobalMapping(**kw))
+    assert refcases.close(res.sum(), 36.0)
+
+
 DISTRIBUTED = refcases.distributed_cases()
 
 
